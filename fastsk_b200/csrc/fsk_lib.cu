@@ -1,0 +1,873 @@
+// Host side of the C ABI (include/fastsk_b200.h): argument checks, the combination queue,
+// virtual-stream bookkeeping of approx mode, and the launch sequence of fsk_kernels.cuh.
+// Mirrors FastSK::compute_kernel (fastsk.cpp:30-118) and KernelFunction::compute_kernel /
+// kernel_build_parallel (fastsk_kernel.cpp:24-106, 145-322) without any CPU compute path.
+#include "../../include/fastsk_b200.h"
+#include "fsk_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <ctime>
+#include <random>
+#include <string>
+#include <vector>
+
+using namespace fsk;
+
+namespace {
+
+std::string g_create_error;
+
+enum RecMode { MODE_R32 = 0, MODE_R64 = 1, MODE_KV = 2 };
+enum ProfClass { PC_PACK = 0, PC_SORT, PC_SEGMENT, PC_ACCUMULATE, PC_WELFORD, PC_NORMALISE, PC_COUNT };
+
+struct ProfSpan {
+    cudaEvent_t a, b;
+    int cls;
+};
+
+}  // namespace
+
+struct fsk_handle {
+    // parameters (FastSK::FastSK, fastsk.cpp:19-28)
+    int g = 0, m = 0, k = 0, t = -1;
+    bool approx = false, skip_variance = false;
+    double delta = 0.025;
+    int max_iters = -1;
+    // configuration
+    int device = 0, rank = 0, world = 1;
+    bool have_seed = false;
+    uint64_t seed = 0;
+    std::vector<int32_t> user_queue;
+    int opt_batch = 0;
+    bool profile = false;
+    std::string err;
+
+    // state
+    cudaStream_t stream = nullptr;
+    bool uploaded = false, built = false, finalized = false;
+    int64_t n_train = 0, n_test = 0, N = 0, nfeat = 0, n_pairs = 0, n_train_pairs = 0, ncomb = 0;
+    int A = 0, b = 0, cpw = 0, NW = 1;
+    bool gw32 = false;
+    int keybits = 0, idbits = 0, mode = MODE_R32, rec_bytes = 4;
+    SortPlan plan{};
+    int B = 1;                       // slots per batch
+    uint32_t sort_tiles = 0, seg_tiles = 0;
+    int sort_items = 16;
+    bool variance_mode = false;
+    int T_eff = 1;
+
+    // device buffers
+    void* d_gw0 = nullptr;
+    uint64_t* d_gw1 = nullptr;
+    uint32_t* d_wseq = nullptr;
+    void *d_recA = nullptr, *d_recB = nullptr;
+    uint32_t *d_valA = nullptr, *d_valB = nullptr;
+    unsigned char* d_zero = nullptr;   // [ghist | tickets | status] cleared once per batch
+    size_t zero_bytes = 0;
+    uint32_t *d_ghist = nullptr, *d_ticket = nullptr, *d_status = nullptr;
+    uint2 *d_tile_counts = nullptr, *d_tile_offs = nullptr, *d_totals = nullptr;
+    uint32_t *d_ent_seq = nullptr, *d_ent_start = nullptr, *d_ent_run = nullptr, *d_run_start = nullptr;
+    unsigned long long* d_Kint = nullptr;   // integer partial (exact / skip_variance), or per-slot Ks in variance mode
+    int ks_slots = 1;
+    std::vector<double*> d_Khat;            // one per local virtual stream
+    double* d_Kf = nullptr;                 // fp64 partial (variance mode): sum of local K_hat
+    double *d_diag = nullptr, *d_train = nullptr, *d_test = nullptr;
+    double *d_block_sums = nullptr, *d_var = nullptr;
+    unsigned long long* d_counters = nullptr;   // entries, runs, pair updates
+
+    std::vector<int32_t> queue;
+    std::vector<double> stdevs;
+
+    // statistics
+    int64_t combos_done = 0, launches = 0;
+    double ms[PC_COUNT] = {0, 0, 0, 0, 0, 0};
+    std::vector<ProfSpan> spans;
+    std::vector<cudaEvent_t> event_pool;
+};
+
+namespace {
+
+int fail(fsk_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(h, e_ == cudaErrorMemoryAllocation ? FSK_ENOMEM : FSK_ECUDA, "%s failed: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                     \
+    } while (0)
+
+template <typename T>
+int dev_alloc(fsk_handle* h, T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    CU(cudaMalloc((void**)p, count * sizeof(T)));
+    return FSK_OK;
+}
+#define ALLOC(ptr, count)                                   \
+    do {                                                    \
+        int rc_ = dev_alloc(h, &(ptr), (size_t)(count));    \
+        if (rc_) return rc_;                                \
+    } while (0)
+
+template <typename T>
+void dev_free(T*& p) {
+    if (p) cudaFree((void*)p);
+    p = nullptr;
+}
+
+void release_device(fsk_handle* h) {
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    dev_free(h->d_gw0); dev_free(h->d_gw1); dev_free(h->d_wseq);
+    dev_free(h->d_recA); dev_free(h->d_recB); dev_free(h->d_valA); dev_free(h->d_valB);
+    dev_free(h->d_zero);
+    h->d_ghist = h->d_ticket = h->d_status = nullptr;
+    dev_free(h->d_tile_counts); dev_free(h->d_tile_offs); dev_free(h->d_totals);
+    dev_free(h->d_ent_seq); dev_free(h->d_ent_start); dev_free(h->d_ent_run); dev_free(h->d_run_start);
+    dev_free(h->d_Kint); dev_free(h->d_Kf);
+    for (auto& p : h->d_Khat) dev_free(p);
+    h->d_Khat.clear();
+    dev_free(h->d_diag); dev_free(h->d_train); dev_free(h->d_test);
+    dev_free(h->d_block_sums); dev_free(h->d_var); dev_free(h->d_counters);
+    for (auto& s : h->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    h->spans.clear();
+    for (auto e : h->event_pool) cudaEventDestroy(e);
+    h->event_pool.clear();
+    h->uploaded = h->built = h->finalized = false;
+}
+
+int64_t nchoosek64(int n, int k) {   // C(n,k); the reference's int version is exact for g <= 20 (shared.cpp:335-345)
+    if (k < 0 || k > n) return 0;
+    if (2 * k > n) k = n - k;
+    int64_t r = 1;
+    for (int i = 1; i <= k; ++i) r = r * (n - k + i) / i;
+    return r;
+}
+
+// kept positions of combination number `idx` in the lexicographic order getCombinations emits
+// (shared.cpp:347-360), by combinatorial unranking instead of re-enumerating all C(g,k) subsets
+// on every iteration (fastsk_kernel.cpp:216-221).
+void unrank_combination(int g, int k, int64_t idx, int* pos) {
+    int p = 0;
+    for (int d = 0; d < k; ++d) {
+        for (;; ++p) {
+            const int64_t with_p = nchoosek64(g - 1 - p, k - 1 - d);
+            if (idx < with_p) break;
+            idx -= with_p;
+        }
+        pos[d] = p++;
+    }
+}
+
+int ceil_log2(int64_t v) {   // bits needed to store values 0 .. v-1 (at least 1)
+    int b = 1;
+    while (((int64_t)1 << b) < v) ++b;
+    return b;
+}
+
+// --- profiling spans -------------------------------------------------------------------------
+cudaEvent_t get_event(fsk_handle* h) {
+    if (!h->event_pool.empty()) {
+        cudaEvent_t e = h->event_pool.back();
+        h->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+void resolve_spans(fsk_handle* h) {
+    if (h->spans.empty()) return;
+    cudaStreamSynchronize(h->stream);
+    for (auto& s : h->spans) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) h->ms[s.cls] += ms;
+        h->event_pool.push_back(s.a);
+        h->event_pool.push_back(s.b);
+    }
+    h->spans.clear();
+}
+struct Span {
+    fsk_handle* h;
+    ProfSpan s{};
+    bool on;
+    Span(fsk_handle* h_, int cls) : h(h_), on(h_->profile) {
+        if (!on) return;
+        s.cls = cls;
+        s.a = get_event(h);
+        s.b = get_event(h);
+        cudaEventRecord(s.a, h->stream);
+    }
+    ~Span() {
+        if (!on) return;
+        cudaEventRecord(s.b, h->stream);
+        h->spans.push_back(s);
+    }
+};
+
+// --- typed launch helpers ----------------------------------------------------------------------
+template <typename RecT, bool KV>
+int launch_pack(fsk_handle* h, int nb, const BatchSpec& spec) {
+    dim3 grid((unsigned)((h->nfeat + 256 * PACK_ITEMS - 1) / (256 * PACK_ITEMS)), nb);
+    RecT* rec = (RecT*)h->d_recA;
+    const uint32_t n = (uint32_t)h->nfeat;
+    if (h->NW == 2)
+        pack_hist_kernel<RecT, KV, uint64_t, 2><<<grid, 256, 0, h->stream>>>((const uint64_t*)h->d_gw0, h->d_gw1, h->d_wseq, n, rec,
+                                                                           h->d_valA, h->d_ghist, spec, h->plan, h->k, h->b, h->idbits);
+    else if (h->gw32)
+        pack_hist_kernel<RecT, KV, uint32_t, 1><<<grid, 256, 0, h->stream>>>((const uint32_t*)h->d_gw0, nullptr, h->d_wseq, n, rec,
+                                                                           h->d_valA, h->d_ghist, spec, h->plan, h->k, h->b, h->idbits);
+    else
+        pack_hist_kernel<RecT, KV, uint64_t, 1><<<grid, 256, 0, h->stream>>>((const uint64_t*)h->d_gw0, nullptr, h->d_wseq, n, rec,
+                                                                           h->d_valA, h->d_ghist, spec, h->plan, h->k, h->b, h->idbits);
+    h->launches++;
+    CU(cudaGetLastError());
+    return FSK_OK;
+}
+
+template <typename RecT, bool KV, int ITEMS>
+size_t sort_smem() {
+    return sizeof(RecT) * SORT_THREADS * ITEMS + (KV ? 4 * SORT_THREADS * ITEMS : 0) + 4 * (8 * RADIX + 2 * RADIX + 8);
+}
+
+template <typename RecT, bool KV, int ITEMS>
+int launch_sort(fsk_handle* h, int nb) {
+    const uint32_t n = (uint32_t)h->nfeat;
+    const size_t smem = sort_smem<RecT, KV, ITEMS>();
+    for (int p = 0; p < h->plan.npass; ++p) {
+        const int shift = (KV ? 0 : h->idbits) + h->plan.shift[p];
+        uint32_t* status = h->d_status + (size_t)p * h->B * h->sort_tiles * RADIX;
+        onesweep_kernel<RecT, KV, ITEMS><<<h->sort_tiles * nb, SORT_THREADS, smem, h->stream>>>(
+            (const RecT*)h->d_recA, (RecT*)h->d_recB, h->d_valA, h->d_valB, n, h->sort_tiles, shift, h->plan.bits[p],
+            h->d_ghist + (size_t)p * RADIX, status, h->d_ticket + p);
+        h->launches++;
+        CU(cudaGetLastError());
+        std::swap(h->d_recA, h->d_recB);
+        std::swap(h->d_valA, h->d_valB);
+    }
+    return FSK_OK;
+}
+
+template <typename RecT, bool KV>
+int launch_segment(fsk_handle* h, int nb) {
+    const uint32_t n = (uint32_t)h->nfeat;
+    dim3 grid(h->seg_tiles, nb);
+    seg_count_kernel<RecT, KV><<<grid, SEG_THREADS, 0, h->stream>>>((const RecT*)h->d_recA, h->d_valA, n, h->idbits, h->seg_tiles,
+                                                                  h->d_tile_counts);
+    seg_scan_kernel<<<nb, 1024, 0, h->stream>>>(h->d_tile_counts, h->d_tile_offs, h->seg_tiles, h->d_totals, h->d_ent_start, n,
+                                              h->profile ? h->d_counters : nullptr);
+    seg_write_kernel<RecT, KV><<<grid, SEG_THREADS, 0, h->stream>>>((const RecT*)h->d_recA, h->d_valA, n, h->idbits, h->seg_tiles,
+                                                                  h->d_tile_offs, h->d_ent_seq, h->d_ent_start, h->d_ent_run,
+                                                                  h->d_run_start);
+    h->launches += 3;
+    CU(cudaGetLastError());
+    return FSK_OK;
+}
+
+// One batch of combinations: partial kernels added into K (+ slot * slot_stride).
+int run_batch(fsk_handle* h, const int32_t* combos, int nb, unsigned long long* K, size_t slot_stride) {
+    BatchSpec spec;
+    memset(&spec, 0, sizeof spec);
+    int pos[MAX_K];
+    for (int s = 0; s < nb; ++s) {
+        if (combos[s] < 0 || combos[s] >= h->ncomb) return fail(h, FSK_EINVAL, "combination index %d out of range [0, %lld)", combos[s], (long long)h->ncomb);
+        unrank_combination(h->g, h->k, combos[s], pos);
+        for (int j = 0; j < h->k; ++j) spec.src[s][j] = (uint8_t)((pos[j] / h->cpw) * 64 + (pos[j] % h->cpw) * h->b);
+    }
+    CU(cudaMemsetAsync(h->d_zero, 0, h->zero_bytes, h->stream));
+    int rc;
+    {
+        Span sp(h, PC_PACK);
+        if (h->mode == MODE_R32) rc = launch_pack<uint32_t, false>(h, nb, spec);
+        else if (h->mode == MODE_R64) rc = launch_pack<uint64_t, false>(h, nb, spec);
+        else rc = launch_pack<uint64_t, true>(h, nb, spec);
+        if (rc) return rc;
+    }
+    {
+        Span sp(h, PC_SORT);
+        if (h->mode == MODE_R32) rc = launch_sort<uint32_t, false, 16>(h, nb);
+        else if (h->mode == MODE_R64) rc = launch_sort<uint64_t, false, 16>(h, nb);
+        else rc = launch_sort<uint64_t, true, 12>(h, nb);
+        if (rc) return rc;
+    }
+    {
+        Span sp(h, PC_SEGMENT);
+        if (h->mode == MODE_R32) rc = launch_segment<uint32_t, false>(h, nb);
+        else if (h->mode == MODE_R64) rc = launch_segment<uint64_t, false>(h, nb);
+        else rc = launch_segment<uint64_t, true>(h, nb);
+        if (rc) return rc;
+    }
+    {
+        Span sp(h, PC_ACCUMULATE);
+        dim3 grid((unsigned)((h->nfeat + ACC_ROWS - 1) / ACC_ROWS), nb);
+        accumulate_kernel<unsigned long long><<<grid, 256, 0, h->stream>>>(h->d_ent_seq, h->d_ent_start, h->d_ent_run, h->d_run_start,
+                                                                         h->d_totals, (uint32_t)h->nfeat, K, slot_stride,
+                                                                         h->profile ? h->d_counters : nullptr);
+        h->launches++;
+        CU(cudaGetLastError());
+    }
+    h->combos_done += nb;
+    if (h->spans.size() > 2048) resolve_spans(h);
+    return FSK_OK;
+}
+
+int build_queue(fsk_handle* h) {
+    if (!h->user_queue.empty()) {
+        for (int32_t c : h->user_queue)
+            if (c < 0 || c >= h->ncomb) return fail(h, FSK_EINVAL, "combination %d out of range [0, %lld)", c, (long long)h->ncomb);
+        h->queue = h->user_queue;
+        return FSK_OK;
+    }
+    // fastsk_kernel.cpp:31-47: identity, then std::shuffle with std::default_random_engine
+    h->queue.resize((size_t)h->ncomb);
+    for (int64_t i = 0; i < h->ncomb; ++i) h->queue[(size_t)i] = (int32_t)i;
+    auto rng = std::default_random_engine{};
+    rng.seed(h->have_seed ? (std::default_random_engine::result_type)h->seed : (std::default_random_engine::result_type)std::time(0));
+    std::shuffle(h->queue.begin(), h->queue.end(), rng);
+    return FSK_OK;
+}
+
+int effective_streams(const fsk_handle* h, int64_t nq) {   // fastsk_kernel.cpp:54-61
+    int T = h->t == -1 ? 20 : h->t;
+    if (T < 1) T = 1;
+    if (T > nq) T = (int)nq;
+    return T;
+}
+
+template <typename T>
+int finalize_typed(fsk_handle* h, const T* K) {
+    Span sp(h, PC_NORMALISE);
+    diag_kernel<T><<<(unsigned)((h->N + 255) / 256), 256, 0, h->stream>>>(K, h->N, h->d_diag);
+    dim3 gtrain((unsigned)((h->n_train + 31) / 32), (unsigned)((h->n_train + 31) / 32));
+    normalise_block_kernel<T><<<gtrain, 256, 0, h->stream>>>(K, h->d_diag, 0, h->n_train, h->n_train, h->d_train);
+    h->launches += 2;
+    if (h->n_test > 0) {
+        dim3 gtest((unsigned)((h->n_train + 31) / 32), (unsigned)((h->n_test + 31) / 32));
+        normalise_block_kernel<T><<<gtest, 256, 0, h->stream>>>(K, h->d_diag, h->n_train, h->n_test, h->n_train, h->d_test);
+        h->launches++;
+    }
+    CU(cudaGetLastError());
+    return FSK_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char* fsk_version(void) { return "fastsk_b200 0.1 (sm_100a)"; }
+
+const char* fsk_last_error(const fsk_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int fsk_create(fsk_handle** out, int g, int m, int t, int approx, double delta, int max_iters, int skip_variance) {
+    if (!out) return fail(nullptr, FSK_EINVAL, "out is NULL");
+    *out = nullptr;
+    // the reference's validate_args (shared.cpp:380-391; never called there) asks g > m and g <= 20
+    if (g < 1 || m < 0 || g <= m) return fail(nullptr, FSK_EINVAL, "g must be greater than m (g = %d, m = %d)", g, m);
+    if (g - m > MAX_K || g > 64) return fail(nullptr, FSK_EINVAL, "g - m must be at most %d and g at most 64 (g = %d, m = %d)", MAX_K, g, m);
+    if (t == 0 || t < -1) return fail(nullptr, FSK_EINVAL, "t must be -1 or positive (t = %d)", t);
+    if (nchoosek64(g, m) > 0x7fffffffLL) return fail(nullptr, FSK_EINVAL, "C(g, m) does not fit a 32-bit combination index");
+    fsk_handle* h = new fsk_handle();
+    h->g = g; h->m = m; h->k = g - m; h->t = t;
+    h->approx = approx != 0; h->delta = delta; h->max_iters = max_iters; h->skip_variance = skip_variance != 0;
+    h->ncomb = nchoosek64(g, m);
+    *out = h;
+    return FSK_OK;
+}
+
+void fsk_destroy(fsk_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    release_device(h);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int fsk_set_device(fsk_handle* h, int device) {
+    if (h->uploaded) return fail(h, FSK_ESTATE, "fsk_set_device after upload");
+    h->device = device;
+    return FSK_OK;
+}
+int fsk_set_seed(fsk_handle* h, uint64_t seed) { h->have_seed = true; h->seed = seed; return FSK_OK; }
+int fsk_set_combo_sequence(fsk_handle* h, const int32_t* combos, int64_t n) {
+    if (n < 0 || (n > 0 && !combos)) return fail(h, FSK_EINVAL, "bad combination sequence");
+    h->user_queue.assign(combos, combos + n);
+    return FSK_OK;
+}
+int fsk_set_shard(fsk_handle* h, int rank, int world) {
+    if (world < 1 || rank < 0 || rank >= world) return fail(h, FSK_EINVAL, "bad shard %d of %d", rank, world);
+    h->rank = rank; h->world = world;
+    return FSK_OK;
+}
+int fsk_set_option(fsk_handle* h, const char* key, int64_t value) {
+    if (!key) return fail(h, FSK_EINVAL, "key is NULL");
+    if (!strcmp(key, "batch")) {
+        if (value < 0 || value > MAX_BATCH) return fail(h, FSK_EINVAL, "batch must be in [0, %d]", MAX_BATCH);
+        h->opt_batch = (int)value;
+    } else if (!strcmp(key, "profile")) {
+        h->profile = value != 0;
+    } else {
+        return fail(h, FSK_EINVAL, "unknown option '%s'", key);
+    }
+    return FSK_OK;
+}
+
+int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int64_t n_train, int64_t n_test) {
+    if (!codes || !offsets) return fail(h, FSK_EINVAL, "codes/offsets is NULL");
+    // the reference dereferences Xtrain[0] / Xtest[0] unconditionally (fastsk.cpp:33,41); compute_train passes no test set
+    if (n_train < 1 || n_test < 0) return fail(h, FSK_EINVAL, "need at least one train sequence (n_train = %lld, n_test = %lld)", (long long)n_train, (long long)n_test);
+    const int64_t N = n_train + n_test;
+    if (N >= (1LL << 31)) return fail(h, FSK_EINVAL, "too many sequences");
+    // fastsk.cpp:53-58: g longer than the shortest sequence is fatal (exit(1) there, an error code here)
+    int64_t shortest_train = INT64_MAX, shortest_test = INT64_MAX, nfeat = 0;
+    for (int64_t i = 0; i < N; ++i) {
+        const int64_t len = offsets[i + 1] - offsets[i];
+        if (len < 0) return fail(h, FSK_EINVAL, "offsets must be non-decreasing");
+        if (i < n_train) shortest_train = std::min(shortest_train, len);
+        else shortest_test = std::min(shortest_test, len);
+        nfeat += len - h->g + 1;
+    }
+    if (h->g > shortest_train)
+        return fail(h, FSK_EINVAL, "g cannot be longer than the shortest sequence in a dataset: g = %d, but shortest train sequence has length %lld", h->g, (long long)shortest_train);
+    if (n_test > 0 && h->g > shortest_test)
+        return fail(h, FSK_EINVAL, "g cannot be longer than the shortest sequence in a dataset: g = %d, but shortest test sequence has length %lld", h->g, (long long)shortest_test);
+    if (nfeat >= (1LL << 30)) return fail(h, FSK_EINVAL, "too many g-mers (%lld); at most 2^30 - 1", (long long)nfeat);
+
+    // dense re-coding: only equality of characters matters
+    const int64_t total = offsets[N] - offsets[0];
+    int32_t maxv = 0;
+    for (int64_t i = offsets[0]; i < offsets[N]; ++i) {
+        if (codes[i] < 0) return fail(h, FSK_EINVAL, "negative character code at position %lld", (long long)i);
+        maxv = std::max(maxv, codes[i]);
+    }
+    std::vector<int32_t> remap;
+    std::vector<uint8_t> dense((size_t)total);
+    int A = 0;
+    if (maxv < (1 << 22)) {
+        remap.assign((size_t)maxv + 1, -1);
+        for (int64_t i = offsets[0]; i < offsets[N]; ++i) remap[codes[i]] = 0;
+        for (auto& r : remap) if (r == 0) r = A++;
+        if (A > 256) return fail(h, FSK_EINVAL, "alphabet of %d distinct characters; at most 256 are supported", A);
+        for (int64_t i = 0; i < total; ++i) dense[(size_t)i] = (uint8_t)remap[codes[offsets[0] + i]];
+    } else {
+        std::vector<int32_t> uniq(codes + offsets[0], codes + offsets[N]);
+        std::sort(uniq.begin(), uniq.end());
+        uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+        A = (int)uniq.size();
+        if (A > 256) return fail(h, FSK_EINVAL, "alphabet of %d distinct characters; at most 256 are supported", A);
+        for (int64_t i = 0; i < total; ++i)
+            dense[(size_t)i] = (uint8_t)(std::lower_bound(uniq.begin(), uniq.end(), codes[offsets[0] + i]) - uniq.begin());
+    }
+    const int b = ceil_log2(A);
+    const int cpw = 64 / b;
+    if (h->k * b > 64) return fail(h, FSK_EINVAL, "(g - m) * bits-per-character = %d * %d exceeds the 64-bit key", h->k, b);
+    if (h->g > 2 * cpw) return fail(h, FSK_EINVAL, "g * bits-per-character = %d * %d exceeds the 128-bit g-mer word", h->g, b);
+
+    CU(cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, h->device));
+    if (prop.major < 10) return fail(h, FSK_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", h->device, prop.major, prop.minor);
+    if (!h->stream) CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    release_device(h);
+
+    h->n_train = n_train; h->n_test = n_test; h->N = N; h->nfeat = nfeat;
+    h->n_pairs = N * (N + 1) / 2;
+    h->n_train_pairs = n_train * (n_train + 1) / 2;
+    h->A = A; h->b = b; h->cpw = cpw;
+    h->NW = h->g > cpw ? 2 : 1;
+    h->gw32 = h->NW == 1 && h->g * b <= 32;
+    h->keybits = h->k * b;
+    h->idbits = ceil_log2(N);
+    if (h->keybits + h->idbits <= 32) { h->mode = MODE_R32; h->rec_bytes = 4; h->sort_items = 16; }
+    else if (h->keybits + h->idbits <= 64) { h->mode = MODE_R64; h->rec_bytes = 8; h->sort_items = 16; }
+    else { h->mode = MODE_KV; h->rec_bytes = 12; h->sort_items = 12; }
+    h->plan.npass = (h->keybits + 7) / 8;
+    {
+        const int base = h->keybits / h->plan.npass, rem = h->keybits % h->plan.npass;
+        int sh = 0;
+        for (int p = 0; p < h->plan.npass; ++p) {
+            h->plan.bits[p] = (uint8_t)(base + (p < rem ? 1 : 0));
+            h->plan.shift[p] = (uint8_t)sh;
+            sh += h->plan.bits[p];
+        }
+    }
+    h->variance_mode = h->approx && !h->skip_variance;
+
+    // batch size: enough records per launch group to fill the machine
+    int B = h->opt_batch > 0 ? h->opt_batch : (int)std::min<int64_t>(MAX_BATCH, std::max<int64_t>(1, (6LL << 20) / std::max<int64_t>(1, nfeat)));
+    h->B = B;
+    h->sort_tiles = (uint32_t)((nfeat + SORT_THREADS * h->sort_items - 1) / (SORT_THREADS * h->sort_items));
+    h->seg_tiles = (uint32_t)((nfeat + SEG_TILE - 1) / SEG_TILE);
+
+    // device inputs
+    uint8_t* d_codes = nullptr;
+    int64_t *d_off = nullptr, *d_woff = nullptr;
+    std::vector<int64_t> off0((size_t)N + 1), woff((size_t)N + 1);
+    for (int64_t i = 0; i <= N; ++i) off0[(size_t)i] = offsets[i] - offsets[0];
+    woff[0] = 0;
+    for (int64_t i = 0; i < N; ++i) woff[(size_t)i + 1] = woff[(size_t)i] + (off0[(size_t)i + 1] - off0[(size_t)i] - h->g + 1);
+    ALLOC(d_codes, total);
+    ALLOC(d_off, N + 1);
+    ALLOC(d_woff, N + 1);
+    CU(cudaMemcpyAsync(d_codes, dense.data(), (size_t)total, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_off, off0.data(), sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_woff, woff.data(), sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, h->stream));
+    if (h->gw32) { uint32_t* p; ALLOC(p, nfeat); h->d_gw0 = p; }
+    else { uint64_t* p; ALLOC(p, nfeat); h->d_gw0 = p; }
+    if (h->NW == 2) ALLOC(h->d_gw1, nfeat);
+    ALLOC(h->d_wseq, nfeat);
+    {
+        const int blocks = (int)std::min<int64_t>((N + 7) / 8, 148 * 16);
+        if (h->NW == 2)
+            build_gwords_kernel<uint64_t, 2><<<blocks, 256, 0, h->stream>>>(d_codes, d_off, d_woff, N, h->g, b, cpw, (uint64_t*)h->d_gw0, h->d_gw1, h->d_wseq);
+        else if (h->gw32)
+            build_gwords_kernel<uint32_t, 1><<<blocks, 256, 0, h->stream>>>(d_codes, d_off, d_woff, N, h->g, b, cpw, (uint32_t*)h->d_gw0, nullptr, h->d_wseq);
+        else
+            build_gwords_kernel<uint64_t, 1><<<blocks, 256, 0, h->stream>>>(d_codes, d_off, d_woff, N, h->g, b, cpw, (uint64_t*)h->d_gw0, nullptr, h->d_wseq);
+        h->launches = 1;
+        CU(cudaGetLastError());
+    }
+
+    // scratch for B slots
+    const size_t bn = (size_t)B * (size_t)nfeat;
+    { unsigned char* p; ALLOC(p, bn * (h->mode == MODE_R32 ? 4 : 8)); h->d_recA = p; }
+    { unsigned char* p; ALLOC(p, bn * (h->mode == MODE_R32 ? 4 : 8)); h->d_recB = p; }
+    if (h->mode == MODE_KV) { ALLOC(h->d_valA, bn); ALLOC(h->d_valB, bn); }
+    const size_t ghist_words = (size_t)B * MAX_PASS * RADIX, ticket_words = 64;
+    const size_t status_words = (size_t)h->plan.npass * B * h->sort_tiles * RADIX;
+    h->zero_bytes = 4 * (ghist_words + ticket_words + status_words);
+    ALLOC(h->d_zero, h->zero_bytes);
+    h->d_ghist = (uint32_t*)h->d_zero;
+    h->d_ticket = h->d_ghist + ghist_words;
+    h->d_status = h->d_ticket + ticket_words;
+    ALLOC(h->d_tile_counts, (size_t)B * h->seg_tiles);
+    ALLOC(h->d_tile_offs, (size_t)B * h->seg_tiles);
+    ALLOC(h->d_totals, B);
+    ALLOC(h->d_ent_seq, bn);
+    ALLOC(h->d_ent_start, bn + B);
+    ALLOC(h->d_ent_run, bn);
+    ALLOC(h->d_run_start, bn);
+    ALLOC(h->d_counters, 4);
+    CU(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), h->stream));
+
+    // accumulators
+    h->ks_slots = h->variance_mode ? B : 1;
+    ALLOC(h->d_Kint, (size_t)h->ks_slots * h->n_pairs);
+    CU(cudaMemsetAsync(h->d_Kint, 0, sizeof(unsigned long long) * (size_t)h->ks_slots * h->n_pairs, h->stream));
+    if (h->variance_mode) {
+        ALLOC(h->d_Kf, h->n_pairs);
+        CU(cudaMemsetAsync(h->d_Kf, 0, sizeof(double) * (size_t)h->n_pairs, h->stream));
+        ALLOC(h->d_block_sums, (size_t)B * WELFORD_BLOCKS);
+        ALLOC(h->d_var, B);
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(d_codes); cudaFree(d_off); cudaFree(d_woff);
+
+    h->combos_done = 0;
+    for (double& v : h->ms) v = 0;
+    h->stdevs.clear();
+    int rc = build_queue(h);
+    if (rc) return rc;
+    h->uploaded = true;
+    return FSK_OK;
+}
+
+int fsk_reset_partial(fsk_handle* h) {
+    if (!h->uploaded) return fail(h, FSK_ESTATE, "nothing uploaded");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemsetAsync(h->d_Kint, 0, sizeof(unsigned long long) * (size_t)h->ks_slots * h->n_pairs, h->stream));
+    if (h->d_Kf) CU(cudaMemsetAsync(h->d_Kf, 0, sizeof(double) * (size_t)h->n_pairs, h->stream));
+    h->built = h->finalized = false;
+    return FSK_OK;
+}
+
+int fsk_accumulate_combos(fsk_handle* h, const int32_t* combos, int64_t n, int sync) {
+    if (!h->uploaded) return fail(h, FSK_ESTATE, "nothing uploaded");
+    if (h->variance_mode) return fail(h, FSK_ESTATE, "fsk_accumulate_combos needs an integer mode (exact or skip_variance)");
+    CU(cudaSetDevice(h->device));
+    for (int64_t i = 0; i < n; i += h->B) {
+        const int nb = (int)std::min<int64_t>(h->B, n - i);
+        int rc = run_batch(h, combos + i, nb, h->d_Kint, 0);
+        if (rc) return rc;
+    }
+    if (sync) CU(cudaStreamSynchronize(h->stream));
+    return FSK_OK;
+}
+
+int fsk_build_partial(fsk_handle* h) {
+    if (!h->uploaded) return fail(h, FSK_ESTATE, "nothing uploaded");
+    CU(cudaSetDevice(h->device));
+    int rc = fsk_reset_partial(h);
+    if (rc) return rc;
+    h->stdevs.clear();
+    const int64_t nq = (int64_t)h->queue.size();
+    if (nq < 1) return fail(h, FSK_EINVAL, "empty combination queue");
+    const int T = effective_streams(h, nq);
+    h->T_eff = T;
+
+    if (!h->variance_mode) {
+        // integer modes: the union of what every stream would process, dealt round-robin to the shards
+        std::vector<int32_t> work;
+        if (!h->approx) {
+            work = h->queue;
+        } else {   // approx && skip_variance: stream tid runs queue[tid + T*r] until max_iters (fastsk_kernel.cpp:257-262, 275-278)
+            for (int tid = 0; tid < T; ++tid) {
+                int64_t avail = (nq - tid + T - 1) / T;
+                if (h->max_iters != -1) avail = std::min<int64_t>(avail, std::max(1, h->max_iters));
+                for (int64_t r = 0; r < avail; ++r) work.push_back(h->queue[(size_t)(tid + T * r)]);
+            }
+        }
+        std::vector<int32_t> mine;
+        for (size_t i = (size_t)h->rank; i < work.size(); i += (size_t)h->world) mine.push_back(work[i]);
+        rc = fsk_accumulate_combos(h, mine.data(), (int64_t)mine.size(), 0);
+        if (rc) return rc;
+    } else {
+        // variance mode: T independent virtual streams (fastsk_kernel.cpp:188-281), stream tid owned by rank tid % world
+        struct Stream { int tid; int64_t item; int iter; bool working; double* khat; };
+        std::vector<Stream> streams;
+        for (int tid = h->rank; tid < T; tid += h->world) {
+            double* kh;
+            ALLOC(kh, h->n_pairs);
+            h->d_Khat.push_back(kh);
+            CU(cudaMemsetAsync(kh, 0, sizeof(double) * (size_t)h->n_pairs, h->stream));
+            streams.push_back({tid, tid, 1, true, kh});
+        }
+        std::vector<double> var_host((size_t)h->B);
+        while (true) {
+            std::vector<Stream*> active;
+            for (auto& s : streams) if (s.working) active.push_back(&s);
+            if (active.empty()) break;
+            for (size_t a0 = 0; a0 < active.size(); a0 += (size_t)h->B) {
+                const int nb = (int)std::min<size_t>((size_t)h->B, active.size() - a0);
+                int32_t combos[MAX_BATCH];
+                for (int s = 0; s < nb; ++s) combos[s] = h->queue[(size_t)active[a0 + s]->item];
+                rc = run_batch(h, combos, nb, h->d_Kint, (size_t)h->n_pairs);   // Ks of each slot is zero on entry
+                if (rc) return rc;
+                {
+                    Span sp(h, PC_WELFORD);
+                    for (int s = 0; s < nb; ++s) {
+                        Stream* st = active[a0 + s];
+                        welford_kernel<unsigned long long><<<WELFORD_BLOCKS, 256, 0, h->stream>>>(
+                            h->d_Kint + (size_t)s * h->n_pairs, st->khat, h->n_pairs, h->n_train_pairs, st->iter,
+                            h->d_block_sums + (size_t)s * WELFORD_BLOCKS);
+                        welford_final_kernel<<<1, 256, 0, h->stream>>>(h->d_block_sums + (size_t)s * WELFORD_BLOCKS, WELFORD_BLOCKS, h->d_var + s);
+                        h->launches += 2;
+                    }
+                    CU(cudaGetLastError());
+                }
+                CU(cudaMemcpyAsync(var_host.data(), h->d_var, sizeof(double) * (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
+                CU(cudaStreamSynchronize(h->stream));
+                for (int s = 0; s < nb; ++s) {
+                    Stream* st = active[a0 + s];
+                    // fastsk_kernel.cpp:130-142 then 244-256
+                    double v = var_host[(size_t)s] / (double)h->n_train_pairs;
+                    if (st->iter == 1) v = 9999999;
+                    else v /= st->iter - 1;
+                    const double sd = std::sqrt(v / st->iter);
+                    if (st->tid == 0) h->stdevs.push_back(sd);
+                    if (h->delta / sd > 1.96) st->working = false;
+                    if (h->max_iters != -1 && st->iter >= h->max_iters) st->working = false;
+                    st->item += T;
+                    if (st->item >= nq) st->working = false;
+                    st->iter++;
+                }
+            }
+        }
+        // merge (fastsk_kernel.cpp:296-313): sum of the streams' running means, in stream order
+        for (auto& s : streams) {
+            add_f64_kernel<<<592, 256, 0, h->stream>>>(h->d_Kf, s.khat, h->n_pairs);
+            h->launches++;
+        }
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(h->stream));
+        for (auto& p : h->d_Khat) dev_free(p);
+        h->d_Khat.clear();
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    h->built = true;
+    return FSK_OK;
+}
+
+int fsk_partial_buffer(fsk_handle* h, void** dev_ptr, int64_t* n_elems, int* dtype) {
+    if (!h->uploaded) return fail(h, FSK_ESTATE, "nothing uploaded");
+    if (dev_ptr) *dev_ptr = h->variance_mode ? (void*)h->d_Kf : (void*)h->d_Kint;
+    if (n_elems) *n_elems = h->n_pairs;
+    if (dtype) *dtype = h->variance_mode ? FSK_DT_F64 : FSK_DT_I64;
+    return FSK_OK;
+}
+
+int fsk_finalize(fsk_handle* h) {
+    if (!h->uploaded) return fail(h, FSK_ESTATE, "nothing uploaded");
+    CU(cudaSetDevice(h->device));
+    if (!h->d_diag) ALLOC(h->d_diag, h->N);
+    if (!h->d_train) ALLOC(h->d_train, (size_t)h->n_train * h->n_train);
+    if (!h->d_test && h->n_test > 0) ALLOC(h->d_test, (size_t)h->n_test * h->n_train);
+    int rc = h->variance_mode ? finalize_typed<double>(h, h->d_Kf) : finalize_typed<unsigned long long>(h, h->d_Kint);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    h->finalized = true;
+    return FSK_OK;
+}
+
+int fsk_compute(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int64_t n_train, int64_t n_test) {
+    int rc = fsk_upload(h, codes, offsets, n_train, n_test);
+    if (rc) return rc;
+    rc = fsk_build_partial(h);
+    if (rc) return rc;
+    return fsk_finalize(h);
+}
+
+int fsk_stream(fsk_handle* h, void** cuda_stream) {
+    if (!h->stream) return fail(h, FSK_ESTATE, "no stream before upload");
+    *cuda_stream = (void*)h->stream;
+    return FSK_OK;
+}
+int fsk_synchronize(fsk_handle* h) {
+    if (!h->stream) return FSK_OK;
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    return FSK_OK;
+}
+
+int fsk_shape(fsk_handle* h, int64_t* n_train, int64_t* n_test, int64_t* nfeat, int64_t* n_combos) {
+    if (n_train) *n_train = h->n_train;
+    if (n_test) *n_test = h->n_test;
+    if (nfeat) *nfeat = h->nfeat;
+    if (n_combos) *n_combos = h->ncomb;
+    return FSK_OK;
+}
+
+#define NEED_FINAL()                                                                       \
+    do {                                                                                   \
+        if (!h->finalized) return fail(h, FSK_ESTATE, "no kernel computed yet");           \
+        CU(cudaSetDevice(h->device));                                                      \
+    } while (0)
+
+int fsk_get_train_kernel(fsk_handle* h, double* out) {
+    NEED_FINAL();
+    CU(cudaMemcpyAsync(out, h->d_train, sizeof(double) * (size_t)h->n_train * h->n_train, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return FSK_OK;
+}
+int fsk_get_test_kernel(fsk_handle* h, double* out) {
+    NEED_FINAL();
+    if (h->n_test == 0) return FSK_OK;
+    CU(cudaMemcpyAsync(out, h->d_test, sizeof(double) * (size_t)h->n_test * h->n_train, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return FSK_OK;
+}
+int fsk_train_kernel_device(fsk_handle* h, void** dev_ptr) { NEED_FINAL(); *dev_ptr = h->d_train; return FSK_OK; }
+int fsk_test_kernel_device(fsk_handle* h, void** dev_ptr) { NEED_FINAL(); *dev_ptr = h->d_test; return FSK_OK; }
+
+int fsk_get_kernel_packed(fsk_handle* h, double* out) {
+    NEED_FINAL();
+    double* d_packed;
+    ALLOC(d_packed, h->n_pairs);
+    dim3 grid((unsigned)std::min<int64_t>((h->N + 255) / 256, 64), (unsigned)h->N);
+    if (h->variance_mode) normalise_packed_kernel<double><<<grid, 256, 0, h->stream>>>(h->d_Kf, h->d_diag, h->N, d_packed);
+    else normalise_packed_kernel<unsigned long long><<<grid, 256, 0, h->stream>>>(h->d_Kint, h->d_diag, h->N, d_packed);
+    h->launches++;
+    cudaError_t e = cudaMemcpyAsync(out, d_packed, sizeof(double) * (size_t)h->n_pairs, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_packed);
+    if (e != cudaSuccess) return fail(h, FSK_ECUDA, "packed kernel copy failed: %s", cudaGetErrorString(e));
+    return FSK_OK;
+}
+
+int fsk_get_unnormalised_i64(fsk_handle* h, int64_t* out) {
+    if (!h->uploaded) return fail(h, FSK_ESTATE, "nothing uploaded");
+    if (h->variance_mode) return fail(h, FSK_ESTATE, "the integer kernel exists only in the exact and skip_variance modes");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(out, h->d_Kint, sizeof(int64_t) * (size_t)h->n_pairs, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return FSK_OK;
+}
+int fsk_get_unnormalised_f64(fsk_handle* h, double* out) {
+    if (!h->uploaded) return fail(h, FSK_ESTATE, "nothing uploaded");
+    CU(cudaSetDevice(h->device));
+    if (h->variance_mode) {
+        CU(cudaMemcpyAsync(out, h->d_Kf, sizeof(double) * (size_t)h->n_pairs, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        return FSK_OK;
+    }
+    double* d_tmp;
+    ALLOC(d_tmp, h->n_pairs);
+    to_f64_kernel<unsigned long long><<<592, 256, 0, h->stream>>>(h->d_Kint, d_tmp, h->n_pairs);
+    h->launches++;
+    cudaError_t e = cudaMemcpyAsync(out, d_tmp, sizeof(double) * (size_t)h->n_pairs, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_tmp);
+    if (e != cudaSuccess) return fail(h, FSK_ECUDA, "unnormalised kernel copy failed: %s", cudaGetErrorString(e));
+    return FSK_OK;
+}
+
+int fsk_get_stdevs(fsk_handle* h, double* out, int64_t cap, int64_t* n) {
+    if (n) *n = (int64_t)h->stdevs.size();
+    for (int64_t i = 0; out && i < cap && i < (int64_t)h->stdevs.size(); ++i) out[i] = h->stdevs[(size_t)i];
+    return FSK_OK;
+}
+
+int fsk_get_queue(fsk_handle* h, int32_t* out, int64_t cap, int64_t* n) {
+    if (!h->uploaded) {   // queue of a handle that has seen no data yet: build it now (depends on g, m, seed only)
+        int rc = build_queue(h);
+        if (rc) return rc;
+    }
+    if (n) *n = (int64_t)h->queue.size();
+    for (int64_t i = 0; out && i < cap && i < (int64_t)h->queue.size(); ++i) out[i] = h->queue[(size_t)i];
+    return FSK_OK;
+}
+
+int fsk_save_kernel(fsk_handle* h, const char* path) {
+    NEED_FINAL();
+    if (!path || !*path) return FSK_OK;   // fastsk.cpp:226: empty file name is a no-op
+    std::vector<double> K((size_t)h->n_pairs);
+    int rc = fsk_get_kernel_packed(h, K.data());
+    if (rc) return rc;
+    FILE* f = fopen(path, "w");
+    if (!f) return fail(h, FSK_EINVAL, "cannot open %s for writing", path);
+    for (int64_t i = 0; i < h->N; ++i) {
+        for (int64_t j = 0; j < h->N; ++j) {
+            const int64_t a = std::max(i, j), bb = std::min(i, j);
+            fprintf(f, "%d:%e ", (int)(j + 1), K[(size_t)(a * (a + 1) / 2 + bb)]);
+        }
+        fprintf(f, "\n");
+    }
+    fclose(f);
+    return FSK_OK;
+}
+
+int fsk_get_stats(fsk_handle* h, fsk_stats* out) {
+    if (!out) return fail(h, FSK_EINVAL, "out is NULL");
+    memset(out, 0, sizeof *out);
+    out->n_seq = h->N; out->nfeat = h->nfeat; out->n_pairs = h->n_pairs; out->n_combos_total = h->ncomb;
+    out->combos_done = h->combos_done;
+    out->kernel_launches = h->launches;
+    out->key_bits = h->keybits; out->id_bits = h->idbits; out->record_bytes = h->rec_bytes; out->sort_passes = h->plan.npass;
+    out->alphabet = h->A; out->bits_per_char = h->b; out->batch = h->B; out->acc_bytes = 8;
+    if (h->uploaded) {
+        CU(cudaSetDevice(h->device));
+        resolve_spans(h);
+        unsigned long long c[4] = {0, 0, 0, 0};
+        CU(cudaMemcpy(c, h->d_counters, sizeof c, cudaMemcpyDeviceToHost));
+        out->entries = (int64_t)c[0]; out->runs = (int64_t)c[1]; out->pair_updates = (int64_t)c[2];
+    }
+    out->ms_pack = h->ms[PC_PACK]; out->ms_sort = h->ms[PC_SORT]; out->ms_segment = h->ms[PC_SEGMENT];
+    out->ms_accumulate = h->ms[PC_ACCUMULATE]; out->ms_welford = h->ms[PC_WELFORD]; out->ms_normalise = h->ms[PC_NORMALISE];
+    for (int i = 0; i < PC_COUNT; ++i) out->ms_total += h->ms[i];
+    return FSK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,131 @@
+/*
+ * fastsk_b200 -- C ABI of the B200-native gapped k-mer kernel-matrix build.
+ *
+ * This is the drop-in boundary for the reference's pybind11 module `fastsk._fastsk`
+ * (/root/reference/src/fastsk/_fastsk/bindings.cpp:12-51).  Each entry point names the
+ * reference interface it replaces.  Plain pointers and sizes only; every buffer is owned by
+ * the caller; a handle is used from one host thread at a time.  All functions return
+ * FSK_OK (0) or an error code; fsk_last_error() gives the message.
+ *
+ * Sequences are passed flat: `codes` = all sequences back to back (train rows first, then
+ * test rows), `offsets[i] .. offsets[i+1]` = sequence i.  Any non-negative int32 values are
+ * accepted (only equality of characters matters; the library re-codes them densely, which
+ * the reference requires of its caller: fastsk.cpp:70-85, shared.cpp:171-172).
+ *
+ * There is no CPU fallback: every compute entry point fails with FSK_ECUDA when no sm_100
+ * device is usable.
+ */
+#ifndef FASTSK_B200_H
+#define FASTSK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fsk_handle fsk_handle;
+
+enum {
+    FSK_OK = 0,
+    FSK_EINVAL = 1,   /* bad argument (Python: ValueError) -- replaces the reference's printf + exit(1), shared.cpp:380-412 */
+    FSK_ECUDA = 2,    /* CUDA runtime / device error (Python: RuntimeError) */
+    FSK_ENOMEM = 3,   /* device or host memory exhausted */
+    FSK_ESTATE = 4    /* call out of order (e.g. getter before compute) */
+};
+
+/* dtype tags for fsk_partial_buffer */
+enum { FSK_DT_I64 = 0, FSK_DT_F64 = 1 };
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+
+/* FastSK::FastSK(g, m, t, approx, delta, max_iters, skip_variance)  -- fastsk.cpp:19-28,
+ * defaults bindings.cpp:14-22 (t=-1 => 20 streams, fastsk_kernel.cpp:54-60).
+ * `t` is the number of VIRTUAL streams of approx mode; it never limits GPU use. */
+int fsk_create(fsk_handle** out, int g, int m, int t, int approx, double delta, int max_iters, int skip_variance);
+void fsk_destroy(fsk_handle* h);
+/* message of the last failure on `h` (or of the last failed fsk_create when h == NULL) */
+const char* fsk_last_error(const fsk_handle* h);
+const char* fsk_version(void);
+
+/* ---- configuration (before fsk_compute / fsk_upload) ------------------------------------ */
+
+int fsk_set_device(fsk_handle* h, int device);              /* CUDA ordinal; default 0 */
+/* The reference shuffles the C(g,m) combinations with std::default_random_engine seeded by
+ * time(0) (fastsk_kernel.cpp:31-47).  Same libstdc++ calls here, with an injectable seed ...  */
+int fsk_set_seed(fsk_handle* h, uint64_t seed);
+/* ... or an explicit processing order (combination numbers in the lexicographic order of
+ * getCombinations, shared.cpp:347-360).  n may be smaller than C(g,m).  n == 0 clears it. */
+int fsk_set_combo_sequence(fsk_handle* h, const int32_t* combos, int64_t n);
+/* Multi-GPU: this handle builds shard `rank` of `world` (combinations in the integer modes,
+ * virtual streams in the variance mode).  Default 0 of 1.  The caller sums the partial
+ * buffers of all ranks (one NCCL reduction) between fsk_build_partial and fsk_finalize. */
+int fsk_set_shard(fsk_handle* h, int rank, int world);
+/* tuning / diagnostics: "batch" (combinations per launch group, 0 = auto), "profile" (1 = time
+ * every kernel class with CUDA events), "sync_every" ... unknown keys give FSK_EINVAL */
+int fsk_set_option(fsk_handle* h, const char* key, int64_t value);
+
+/* ---- compute ---------------------------------------------------------------------------- */
+
+/* FastSK::compute_kernel(Xtrain, Xtest) -- fastsk.cpp:30-118 (n_test == 0: compute_train,
+ * fastsk.cpp:120-188).  Host buffers in; equals fsk_upload + fsk_build_partial + fsk_finalize.
+ * FSK_EINVAL if g is longer than the shortest sequence (reference: exit(1), fastsk.cpp:53-58). */
+int fsk_compute(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int64_t n_train, int64_t n_test);
+
+/* staged form of the same call (multi-GPU, benchmarking with resident inputs) */
+int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int64_t n_train, int64_t n_test);
+int fsk_build_partial(fsk_handle* h);   /* KernelFunction::kernel_build_parallel for this shard, fastsk_kernel.cpp:145-322 */
+/* device pointer / element count / dtype of this rank's partial (packed lower triangle) */
+int fsk_partial_buffer(fsk_handle* h, void** dev_ptr, int64_t* n_elems, int* dtype);
+int fsk_finalize(fsk_handle* h);        /* normalisation, fastsk_kernel.cpp:96-103 */
+
+/* Benchmark hook: accumulate the integer partial kernels of the given combinations into the
+ * resident partial buffer (inputs already uploaded; no normalisation; asynchronous on the
+ * handle's stream unless `sync`). */
+int fsk_accumulate_combos(fsk_handle* h, const int32_t* combos, int64_t n, int sync);
+int fsk_reset_partial(fsk_handle* h);
+int fsk_stream(fsk_handle* h, void** cuda_stream);          /* cudaStream_t of the handle */
+int fsk_synchronize(fsk_handle* h);
+
+/* ---- results ------------------------------------------------------------------------------ */
+
+int fsk_shape(fsk_handle* h, int64_t* n_train, int64_t* n_test, int64_t* nfeat, int64_t* n_combos);
+/* FastSK::get_train_kernel -- fastsk.cpp:190-200: n_train x n_train row-major fp64 */
+int fsk_get_train_kernel(fsk_handle* h, double* out);
+/* FastSK::get_test_kernel -- fastsk.cpp:202-217: n_test x n_train row-major fp64 */
+int fsk_get_test_kernel(fsk_handle* h, double* out);
+/* the reference's `double* K`: normalised packed lower triangle, N(N+1)/2 */
+int fsk_get_kernel_packed(fsk_handle* h, double* out);
+/* unnormalised kernel before fastsk_kernel.cpp:96-103; the i64 form exists in the integer
+ * modes (exact, approx+skip_variance) only */
+int fsk_get_unnormalised_i64(fsk_handle* h, int64_t* out);
+int fsk_get_unnormalised_f64(fsk_handle* h, double* out);
+/* device-resident results for DLPack hand-off (valid until the next compute / destroy) */
+int fsk_train_kernel_device(fsk_handle* h, void** dev_ptr);
+int fsk_test_kernel_device(fsk_handle* h, void** dev_ptr);
+/* FastSK::get_stdevs -- fastsk.cpp:219-221 (stream 0's sd sequence, fastsk_kernel.cpp:243-250) */
+int fsk_get_stdevs(fsk_handle* h, double* out, int64_t cap, int64_t* n);
+/* FastSK::save_kernel -- fastsk.cpp:223-237: N lines of "%d:%e " (1-based column ids) */
+int fsk_save_kernel(fsk_handle* h, const char* path);
+/* the combination order in use (after shuffle / fsk_set_combo_sequence) */
+int fsk_get_queue(fsk_handle* h, int32_t* out, int64_t cap, int64_t* n);
+
+/* ---- statistics --------------------------------------------------------------------------- */
+
+typedef struct fsk_stats {
+    int64_t n_seq, nfeat, n_pairs, n_combos_total;
+    int64_t combos_done;        /* combinations processed by this handle since upload */
+    int64_t pair_updates;       /* sum over runs of d(d+1)/2 (only counted when "profile" is on) */
+    int64_t entries;            /* distinct (k-mer, sequence) cells seen ("profile") */
+    int64_t runs;               /* distinct k-mers seen ("profile") */
+    int64_t kernel_launches;    /* CUDA kernels launched by this handle since upload */
+    int32_t key_bits, id_bits, record_bytes, sort_passes, alphabet, bits_per_char, batch, acc_bytes;
+    /* per kernel class, milliseconds on the handle's stream ("profile" only) */
+    double ms_pack, ms_sort, ms_segment, ms_accumulate, ms_welford, ms_normalise, ms_total;
+} fsk_stats;
+int fsk_get_stats(fsk_handle* h, fsk_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTSK_B200_H */

@@ -1,0 +1,248 @@
+"""Parity of the CUDA path against the oracle, through the C ABI (needs a B200: -m gpu).
+
+Bit-exact for the integer partial kernels and the unnormalised kernel; the fp64 normalised kernel
+is compared bit-exactly in the integer modes (same IEEE mul/sqrt/div on both sides) and to 1e-12
+relative in variance mode (the block-wise fp64 reduction order differs from the reference's
+sequential sum; tolerance from BASELINE.json's north_star).
+"""
+import ctypes
+from math import comb
+
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def FastSK():
+    from fastsk_b200 import FastSK as cls
+    return cls
+
+
+def gpu_run(FastSK, d, **extra):
+    f = FastSK(d["g"], d["m"], d["T"], d["approx"], d["delta"], d["max_iters"], d["skip_variance"],
+               combo_sequence=d["queue"], **extra)
+    if d["n_test"]:
+        f.compute_kernel(d["Xtrain"], d["Xtest"])
+    else:
+        f.compute_train(d["Xtrain"])
+    return f
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_fixture(FastSK, oracle_mod, name):
+    d = load_golden(name)
+    f = gpu_run(FastSK, d)
+    n = d["n_train"] + d["n_test"]
+    welford = d["approx"] and not d["skip_variance"]
+    K_un = f.get_unnormalised(np.float64)
+    Kp = f.get_kernel_packed()
+    if welford:
+        np.testing.assert_allclose(K_un, d["K_un"], rtol=RTOL, atol=0)
+        np.testing.assert_allclose(Kp, d["K_norm"], rtol=RTOL, atol=0)
+        np.testing.assert_allclose(f.get_stdevs(), d["stdevs"], rtol=RTOL, atol=0)
+        assert len(f.get_stdevs()) == len(d["stdevs"])        # same stopping iteration
+    else:
+        assert np.array_equal(f.get_unnormalised(np.int64).astype(np.float64), d["K_un"])
+        assert np.array_equal(K_un, d["K_un"])
+        assert np.array_equal(Kp, d["K_norm"])
+        assert f.get_stdevs() == []
+    S = oracle_mod.unpack(Kp, n)
+    assert np.array_equal(f.get_train_kernel(), S[:d["n_train"], :d["n_train"]])
+    assert np.array_equal(f.get_test_kernel(), S[d["n_train"]:, :d["n_train"]])
+
+
+def random_seqs(rng, n, alpha, lo, hi, low_complexity=False):
+    X = []
+    for _ in range(n):
+        L = int(rng.integers(lo, hi + 1))
+        if low_complexity and rng.random() < 0.5:
+            X.append(np.full(L, int(rng.integers(1, alpha + 1))).tolist())      # one repeated character
+        else:
+            X.append(rng.integers(1, alpha + 1, size=L).tolist())
+    return X
+
+
+CASES = [
+    # name, n_train, n_test, alphabet, len range, g, m, batch, low complexity
+    ("dna_r32", 40, 17, 4, (12, 90), 8, 4, 0, False),
+    ("dna_len_eq_g", 9, 4, 4, (10, 10), 10, 6, 0, False),
+    ("dna_one_seq", 1, 0, 4, (30, 30), 6, 2, 0, False),
+    ("dna_lowcomplex", 30, 10, 4, (20, 120), 7, 3, 3, True),
+    ("dna_multi_tile", 300, 100, 4, (100, 100), 10, 6, 1, False),        # 36k windows: 9 sort tiles, look-back
+    ("dna5_r64", 50, 20, 5, (40, 80), 16, 4, 0, False),                  # 12 x 3 = 36 key bits -> 64-bit records
+    ("binary", 30, 10, 2, (25, 60), 12, 5, 2, True),
+    ("protein_r32", 60, 25, 21, (16, 200), 7, 3, 0, False),              # 4 x 5 = 20 bits + 7 id bits
+    ("protein_r64", 60, 25, 23, (30, 150), 12, 4, 0, False),             # 8 x 5 = 40 bits
+    ("text_kv", 40, 15, 57, (25, 300), 20, 10, 0, False),                # 10 x 6 = 60 key bits + ids -> key/value sort, 2-word g-mers
+    ("text_kv_multi_tile", 150, 50, 57, (60, 160), 20, 10, 4, False),
+    ("bytes_b8", 25, 10, 200, (20, 90), 9, 2, 0, False),                 # 8-bit characters, 56 key bits
+    ("wide_alphabet_ids", 20, 8, 30, (18, 50), 6, 3, 0, False),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_random_exact_vs_oracle(FastSK, oracle_mod, case):
+    name, ntr, nte, alpha, (lo, hi), g, m, batch, lowc = case
+    rng = np.random.default_rng(abs(hash(name)) % (2 ** 31))
+    X = random_seqs(rng, ntr + nte, alpha, max(lo, g), hi, lowc)
+    if name == "wide_alphabet_ids":
+        X = [[v * 1000003 for v in x] for x in X]        # sparse, huge ids: the library re-codes densely
+    nc = comb(g, m)
+    queue = rng.permutation(nc)[:min(nc, 60)].astype(np.int32)
+    f = FastSK(g, m, combo_sequence=queue)
+    if batch:
+        f.set_option("batch", batch)
+    f.compute_kernel(X[:ntr], X[ntr:]) if nte else f.compute_train(X[:ntr])
+    lut = {}
+    Xd = [[lut.setdefault(v, len(lut) + 1) for v in x] for x in X]
+    K, Ki, _ = oracle_mod.run("c", Xd[:ntr], Xd[ntr:], g, m, queue)
+    assert np.array_equal(f.get_unnormalised().astype(np.uint64), Ki)
+    assert np.array_equal(f.get_kernel_packed(), oracle_mod.normalise(K, ntr + nte))
+    st = f.stats()
+    assert st["combos_done"] == len(queue) and st["kernel_launches"] > 0
+
+
+@pytest.mark.parametrize("alpha,g,m", [(4, 8, 4), (21, 6, 2), (57, 12, 6)])
+def test_per_combination_counts(FastSK, oracle_mod, alpha, g, m):
+    """Integer partial kernel of every single combination (fastsk_kernel.cpp:224-241 for one work item)."""
+    from fastsk_b200 import _lib
+    rng = np.random.default_rng(alpha * 100 + g)
+    X = random_seqs(rng, 24, alpha, g, 70)
+    f = FastSK(g, m, combo_sequence=[0])
+    f.compute_train(X)
+    n = len(X)
+    out = np.empty(n * (n + 1) // 2, dtype=np.int64)
+    for c in rng.permutation(comb(g, m))[:12]:
+        f._call("fsk_reset_partial")
+        arr = np.array([c], dtype=np.int32)
+        f._call("fsk_accumulate_combos", arr.ctypes.data_as(_lib.c_i32p), 1, 1)
+        f._call("fsk_get_unnormalised_i64", out.ctypes.data_as(_lib.c_i64p))
+        want = oracle_mod.partial(X, g, oracle_mod.combination(g, g - m, int(c)))
+        assert np.array_equal(out.astype(np.uint64), want), f"combination {c}"
+
+
+@pytest.mark.parametrize("T,max_iters,skip,delta", [(1, 12, False, 0.025), (3, 8, False, 0.025), (5, 4, True, 0.025),
+                                                    (2, -1, False, 3.0), (-1, 3, False, 0.025), (4, -1, True, 0.025)])
+def test_approx_modes_vs_oracle(FastSK, oracle_mod, T, max_iters, skip, delta):
+    rng = np.random.default_rng(42 + (T % 7) + 3 * max_iters)
+    g, m = 9, 5
+    X = random_seqs(rng, 36, 4, 20, 70)
+    queue = rng.permutation(comb(g, m)).astype(np.int32)
+    f = FastSK(g, m, T, True, delta, max_iters, skip, combo_sequence=queue)
+    f.compute_kernel(X[:24], X[24:])
+    K, Ki, sd = oracle_mod.run("c", X[:24], X[24:], g, m, queue, T=T, approx=True, delta=delta, max_iters=max_iters,
+                               skip_variance=skip)
+    Kn = oracle_mod.normalise(K, 36)
+    if skip:
+        assert np.array_equal(f.get_unnormalised().astype(np.uint64), Ki)
+        assert np.array_equal(f.get_kernel_packed(), Kn)
+        assert f.get_stdevs() == []
+    else:
+        np.testing.assert_allclose(f.get_unnormalised(np.float64), K, rtol=RTOL, atol=0)
+        np.testing.assert_allclose(f.get_kernel_packed(), Kn, rtol=RTOL, atol=0)
+        assert len(f.get_stdevs()) == len(sd)
+        np.testing.assert_allclose(f.get_stdevs(), sd, rtol=RTOL, atol=0)
+        assert f.get_stdevs()[0] == 3162.2775020544923
+
+
+def test_seeded_shuffle_is_reproducible_and_exact_is_order_invariant(FastSK):
+    rng = np.random.default_rng(3)
+    X = random_seqs(rng, 30, 4, 15, 60)
+    a = FastSK(8, 4, seed=1)
+    b = FastSK(8, 4, seed=2)
+    a.compute_train(X)
+    b.compute_train(X)
+    assert not np.array_equal(a.get_queue(), b.get_queue())
+    assert sorted(a.get_queue().tolist()) == list(range(comb(8, 4)))
+    assert np.array_equal(a.get_unnormalised(), b.get_unnormalised())
+    c = FastSK(8, 4, seed=1)
+    assert np.array_equal(a.get_queue(), c.get_queue())
+
+
+def test_shards_sum_to_the_whole(FastSK):
+    """(e) multi-GPU contract on one device: partial kernels of the shards add up to the full build."""
+    import torch
+    rng = np.random.default_rng(9)
+    X = random_seqs(rng, 40, 4, 30, 80)
+    g, m = 10, 6
+    full = FastSK(g, m, seed=7)
+    full.compute_train(X)
+    codes, offsets = np.concatenate([np.asarray(x, np.int32) for x in X]), np.cumsum([0] + [len(x) for x in X]).astype(np.int64)
+    from fastsk_b200 import _lib
+    total = None
+    for world in (3,):
+        for rank in range(world):
+            s = FastSK(g, m, seed=7)
+            s._call("fsk_set_shard", rank, world)
+            s._call("fsk_upload", codes.ctypes.data_as(_lib.c_i32p), offsets.ctypes.data_as(_lib.c_i64p), len(X), 0)
+            s._call("fsk_build_partial")
+            part = s.partial_tensor().clone()
+            total = part if total is None else total + part
+    assert np.array_equal(total.cpu().numpy(), full.get_unnormalised())
+
+
+def test_synthetic_c4_shape_reduced(FastSK, oracle_mod):
+    """BASELINE configs[3] shape (200-bp DNA, g=16, m=8) at N the oracle finishes in seconds."""
+    rng = np.random.default_rng(0)
+    X = rng.integers(1, 5, size=(600, 200), dtype=np.int32)
+    queue = np.random.default_rng(1).permutation(comb(16, 8))[:6].astype(np.int32)
+    f = FastSK(16, 8, combo_sequence=queue, profile=True)
+    f.compute_kernel(X[:480], X[480:])
+    _, Ki, _ = oracle_mod.run("c", X[:480].tolist(), X[480:].tolist(), 16, 8, queue)
+    assert np.array_equal(f.get_unnormalised().astype(np.uint64), Ki)
+    st = f.stats()
+    assert st["record_bytes"] == 4 and st["sort_passes"] == 2 and st["key_bits"] == 16
+    assert st["pair_updates"] > 0 and st["ms_accumulate"] > 0
+
+
+def test_full_size_properties(FastSK, oracle_mod):
+    """At a size the oracle cannot reach quickly: symmetry-free invariants of the domain.
+    K_ij depends only on sequences i and j, so a sub-block of a large build must equal
+    an oracle run on that subset; partial kernels are additive over combinations."""
+    rng = np.random.default_rng(5)
+    N = 6000
+    X = rng.integers(1, 5, size=(N, 200), dtype=np.int32)
+    queue = np.random.default_rng(2).permutation(comb(16, 8))[:4].astype(np.int32)
+    f = FastSK(16, 8, combo_sequence=queue)
+    f.compute_train(X)
+    Ku = f.get_unnormalised()
+    idx = np.sort(rng.choice(N, size=40, replace=False))
+    _, Ki, _ = oracle_mod.run("c", X[idx].tolist(), [], 16, 8, queue)
+    sub = np.array([[Ku[max(a, b) * (max(a, b) + 1) // 2 + min(a, b)] for b in idx] for a in idx], dtype=np.uint64)
+    assert np.array_equal(sub, oracle_mod.unpack(Ki, 40))
+    # additivity: two halves of the queue
+    a = FastSK(16, 8, combo_sequence=queue[:2]); a.compute_train(X)
+    b = FastSK(16, 8, combo_sequence=queue[2:]); b.compute_train(X)
+    assert np.array_equal(a.get_unnormalised() + b.get_unnormalised(), Ku)
+    # normalised diagonal is exactly 1 and the train kernel is symmetric
+    Kt = f.get_train_kernel()
+    assert np.array_equal(np.diag(Kt), np.ones(N)) and np.array_equal(Kt, Kt.T)
+
+
+def test_errors_and_api_surface(FastSK, tmp_path):
+    with pytest.raises(ValueError):
+        FastSK(5, 5)
+    f = FastSK(6, 2)
+    with pytest.raises(ValueError):
+        f.compute_kernel([[1, 2, 3, 4, 5]], [[1, 2, 3, 4, 5, 6, 7]])          # g > shortest train (fastsk.cpp:53-55)
+    with pytest.raises(ValueError):
+        f.compute_kernel([[1, 2, 3, 4, 5, 6, 7]], [[1, 2, 3]])                # g > shortest test (fastsk.cpp:56-58)
+    with pytest.raises(RuntimeError):
+        FastSK(6, 2).get_train_kernel()                                        # getter before compute
+    f = FastSK(3, 1, combo_sequence=[0, 1, 2])
+    f.compute_kernel([[1, 2, 1, 2, 1], [1, 1, 1, 2, 1]], [[1, 2, 1, 2, 1], [1, 1, 2, 2, 1]])
+    assert f.get_train_kernel().tolist() == [[1.0, 0.6445033866354896], [0.6445033866354896, 1.0]]
+    assert f.get_test_kernel().tolist() == [[1.0, 0.6445033866354896], [0.3892494720807615, 0.5853694070049635]]
+    p = tmp_path / "k.txt"
+    f.save_kernel(str(p))
+    rows = p.read_text().strip("\n").split("\n")
+    assert len(rows) == 4 and rows[0].split(" ")[1] == "2:%e" % 0.6445033866354896
+    t = f.get_train_kernel_tensor()
+    assert t.is_cuda and t.shape == (2, 2) and t.cpu().numpy().tolist() == f.get_train_kernel().tolist()
+    f.fit(C=1.0, kernel_type="fastsk", Ytrain=[1, 0])
+    assert 0.0 <= f.score("accuracy", Ytest=[1, 0]) <= 1.0

@@ -1,0 +1,115 @@
+"""Host-side logic and the C-ABI surface, no GPU needed."""
+import ctypes
+import os
+import re
+from math import comb
+
+import numpy as np
+import pytest
+
+from conftest import DATA_DIR, ROOT
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from fastsk_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "fastsk_b200.h")).read()
+    declared = set(re.findall(r"\b(fsk_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert b"sm_100a" in lib.fsk_version()
+
+
+def test_stats_struct_matches_header():
+    from fastsk_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "fastsk_b200.h")).read()
+    body = header[header.index("typedef struct fsk_stats {"):header.index("} fsk_stats;")]
+    names = []
+    for decl in re.findall(r"(?:int64_t|int32_t|double)\s+([^;]+);", body):
+        names += [n.strip() for n in decl.split(",")]
+    assert names == [n for n, _ in _lib.FskStats._fields_]
+
+
+def test_constructor_validation_and_queue():
+    from fastsk_b200 import FastSK
+    for g, m in [(3, 3), (2, 5), (0, 0)]:
+        with pytest.raises(ValueError):
+            FastSK(g, m)
+    with pytest.raises(ValueError):
+        FastSK(6, 2, t=0)
+    f = FastSK(10, 6, seed=123)
+    q = f.get_queue()
+    assert sorted(q.tolist()) == list(range(comb(10, 6)))
+    assert np.array_equal(q, FastSK(10, 6, seed=123).get_queue())
+    assert not np.array_equal(q, FastSK(10, 6, seed=124).get_queue())
+    assert FastSK(10, 6, combo_sequence=[5, 1, 7]).get_queue().tolist() == [5, 1, 7]
+    with pytest.raises(ValueError):
+        FastSK(10, 6, combo_sequence=[5, 999]).get_queue()
+    with pytest.raises(ValueError):
+        f.set_option("no_such_option", 1)
+
+
+def test_seeded_queue_equals_libstdcxx_reference_shuffle():
+    """fastsk_kernel.cpp:31-38: std::shuffle over 0..C-1 with std::default_random_engine(seed)."""
+    import subprocess, tempfile
+    src = r"""
+    #include <algorithm>
+    #include <cstdio>
+    #include <random>
+    #include <vector>
+    int main() { std::vector<int> v(35); for (int i = 0; i < 35; i++) v[i] = i;
+      auto rng = std::default_random_engine{}; rng.seed(77); std::shuffle(v.begin(), v.end(), rng);
+      for (int x : v) printf("%d ", x); return 0; }
+    """
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "s.cpp"), "w").write(src)
+        subprocess.run(["g++", "-O1", "-o", os.path.join(d, "s"), os.path.join(d, "s.cpp")], check=True)
+        want = [int(x) for x in subprocess.run([os.path.join(d, "s")], capture_output=True, text=True, check=True).stdout.split()]
+    from fastsk_b200 import FastSK
+    assert FastSK(7, 3, seed=77).get_queue().tolist() == want
+
+
+def test_compute_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from fastsk_b200 import FastSK
+    with pytest.raises(RuntimeError):
+        FastSK(3, 1).compute_kernel([[1, 2, 1, 2, 1]], [[1, 2, 1, 2, 2]])
+
+
+def test_argument_errors_precede_device_use():
+    from fastsk_b200 import FastSK
+    with pytest.raises(ValueError, match="shortest train"):
+        FastSK(6, 2).compute_kernel([[1, 2, 3]], [[1, 2, 3, 4, 5, 6]])
+    with pytest.raises(ValueError, match="shortest test"):
+        FastSK(6, 2).compute_kernel([[1, 2, 3, 4, 5, 6]], [[1, 2]])
+    with pytest.raises(ValueError):
+        FastSK(6, 2).compute_kernel([[1, -2, 3, 4, 5, 6]], [[1, 2, 3, 4, 5, 6]])
+
+
+def test_fasta_utility_matches_reference_encoding():
+    from fastsk_b200 import FastaUtility
+    r = FastaUtility()
+    X, Y = r.read_data(os.path.join(DATA_DIR, "small.train.fasta"))
+    assert X == [[1, 2, 1, 2, 1], [1, 1, 1, 2, 1]] and Y == [1, 0]        # ACACA / AAACA, ids from 1 in first-seen order
+    X2, _ = r.read_data(os.path.join(DATA_DIR, "small.test.fasta"))
+    assert X2 == [[1, 2, 1, 2, 1], [1, 1, 2, 2, 1]]
+    for name, n, vocab in [("EP300", 2000, 5), ("1.1", 2339, 24), ("AImed", 1500, 56)]:
+        r = FastaUtility()
+        X, Y = r.read_data(os.path.join(DATA_DIR, name + ".train.fasta"))
+        assert len(X) == n == len(Y) and r._vocab.size() == vocab
+        codes, offsets, labels = FastaUtility().read_encoded(os.path.join(DATA_DIR, name + ".train.fasta"))
+        assert labels == Y and codes.tolist() == [v for x in X for v in x] and offsets[-1] == len(codes)
+    assert FastaUtility().shortest_seq(os.path.join(DATA_DIR, "small.train.fasta")) == 5
+
+
+def test_flatten_accepts_lists_arrays_and_flat_pairs():
+    from fastsk_b200.fastsk import _flatten
+    c, o = _flatten([[1, 2, 3], [4, 5]])
+    assert c.tolist() == [1, 2, 3, 4, 5] and o.tolist() == [0, 3, 5]
+    c, o = _flatten(np.arange(6).reshape(2, 3))
+    assert c.tolist() == list(range(6)) and o.tolist() == [0, 3, 6]
+    c2, o2 = _flatten((c, o))
+    assert c2 is c or c2.tolist() == c.tolist()
