@@ -60,6 +60,7 @@ SIGNATURES = {
     "fsk_get_stdevs": (ctypes.c_int, [_H, c_f64p, ctypes.c_int64, c_i64p]),
     "fsk_save_kernel": (ctypes.c_int, [_H, ctypes.c_char_p]),
     "fsk_get_queue": (ctypes.c_int, [_H, c_i32p, ctypes.c_int64, c_i64p]),
+    "fsk_get_shard_work": (ctypes.c_int, [_H, c_i32p, ctypes.c_int64, c_i64p]),
     "fsk_get_stats": (ctypes.c_int, [_H, ctypes.POINTER(FskStats)]),
 }
 

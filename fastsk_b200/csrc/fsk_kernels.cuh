@@ -439,6 +439,94 @@ accumulate_kernel(const uint32_t* __restrict__ ent_seq, const uint32_t* __restri
 }
 
 // ------------------------------------------------------------------------------------------
+// Row-stationary accumulate (the default path).
+//
+// Measured on B200 (profiles/r01_atomic_microbench.txt): scattered RED into the 10 GB packed
+// triangle runs at 20 G updates/s (DRAM sector read-modify-write), L2-resident at 210 G/s, and
+// shared-memory atomics at > 800 G/s.  So the update is re-ordered by OUTPUT ROW: one CTA owns
+// row b of K for a whole batch of combinations, keeps it in shared memory (4 B x (b+1), <= 227 KB),
+// streams the run prefixes of b's k-mers and flushes the row to HBM once per batch.
+//
+// seg_finish turns every entry (k-mer, sequence b) into a task (run start, entry) filed under
+// row b: task[woff[b] + i], i < row_count[b] (a sequence has at most as many entries as
+// windows, so its window range is its task range), and packs (sequence, count) into one word.
+__global__ void __launch_bounds__(256)
+seg_finish_kernel(const uint32_t* __restrict__ ent_seq, const uint32_t* __restrict__ ent_start,
+                  const uint32_t* __restrict__ ent_run, const uint32_t* __restrict__ run_start,
+                  const uint2* __restrict__ totals, uint32_t n, uint32_t nseq, int idbits,
+                  const uint32_t* __restrict__ woff, uint32_t* __restrict__ row_count,
+                  uint32_t* __restrict__ ent_pack, uint2* __restrict__ task) {
+    const int slot = blockIdx.y;
+    const uint32_t e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= totals[slot].x) return;
+    const size_t sbase = (size_t)slot * n, ebase = (size_t)slot * (n + 1);
+    const uint32_t sb = ent_seq[sbase + e] & 0x7fffffffu;
+    const uint32_t cnt = ent_start[ebase + e + 1] - ent_start[ebase + e];
+    const uint32_t rs = run_start[sbase + ent_run[sbase + e]];
+    ent_pack[sbase + e] = sb | (cnt << idbits);
+    const uint32_t pos = atomicAdd(&row_count[(size_t)slot * nseq + sb], 1u);
+    task[sbase + woff[sb] + pos] = make_uint2(rs, e);
+}
+
+// grid = (rows, groups); the slots [group * slots_per_group, +slots_per_group) add into the same K.
+// Row N-1 first: the longest rows lead, the short ones fill the tail.
+template <typename AccT, int UNROLL>
+__global__ void __launch_bounds__(1024)
+accumulate_rows_kernel(const uint32_t* __restrict__ ent_pack, const uint2* __restrict__ task,
+                       const uint32_t* __restrict__ row_count, const uint32_t* __restrict__ woff, uint32_t n,
+                       uint32_t nseq, int idbits, int slots_per_group, AccT* __restrict__ K, size_t k_group_stride,
+                       unsigned long long* __restrict__ stat_counters) {
+    extern __shared__ uint32_t row[];
+    const uint32_t b = nseq - 1 - blockIdx.x;
+    const int group = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    uint32_t any = 0;
+    for (int s = 0; s < slots_per_group; ++s) any |= row_count[(size_t)(group * slots_per_group + s) * nseq + b];
+    if (any == 0) return;
+    for (uint32_t i = threadIdx.x; i <= b; i += blockDim.x) row[i] = 0;
+    __syncthreads();
+    const uint32_t idmask = (1u << idbits) - 1;
+    const uint32_t wb = woff[b];
+    unsigned long long updates = 0;
+    for (int s = 0; s < slots_per_group; ++s) {
+        const int slot = group * slots_per_group + s;
+        const uint32_t nt = row_count[(size_t)slot * nseq + b];
+        const uint2* __restrict__ tk = task + (size_t)slot * n + wb;
+        const uint32_t* __restrict__ ep = ent_pack + (size_t)slot * n;
+        for (uint32_t t0 = warp * UNROLL; t0 < nt; t0 += nwarps * UNROLL) {
+            uint32_t rs[UNROLL], len[UNROLL], cb[UNROLL], maxlen = 0;
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                len[u] = 0; rs[u] = 0; cb[u] = 0;
+                if (t0 + u < nt) {
+                    const uint2 q = tk[t0 + u];
+                    rs[u] = q.x;
+                    len[u] = q.y - q.x + 1;
+                    cb[u] = ep[q.y] >> idbits;
+                    maxlen = max(maxlen, len[u]);
+                    updates += len[u];
+                }
+            }
+            for (uint32_t off = lane; off < maxlen; off += 32) {
+                uint32_t p[UNROLL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) p[u] = off < len[u] ? ep[rs[u] + off] : 0u;
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u)
+                    if (off < len[u]) atomicAdd(&row[p[u] & idmask], (p[u] >> idbits) * cb[u]);
+            }
+        }
+    }
+    __syncthreads();
+    AccT* __restrict__ Krow = K + (size_t)group * k_group_stride + ((size_t)b * (b + 1) >> 1);
+    for (uint32_t i = threadIdx.x; i <= b; i += blockDim.x) {
+        const uint32_t v = row[i];
+        if (v) Krow[i] += (AccT)v;
+    }
+    if (stat_counters && lane == 0 && updates) atomicAdd(&stat_counters[2], updates);
+}
+
+// ------------------------------------------------------------------------------------------
 // normalisation (fastsk_kernel.cpp:96-103): out = K_ij / sqrt(K_ii * K_jj) with IEEE mul, sqrt,
 // div (bit-identical to the reference's x86-64 doubles); the diagonal formula K_ii/sqrt(K_ii*K_ii)
 // is the same expression.

@@ -43,6 +43,7 @@ struct fsk_handle {
     uint64_t seed = 0;
     std::vector<int32_t> user_queue;
     int opt_batch = 0;
+    int opt_acc_path = 0;            // 0 auto, 1 global RED, 2 row-stationary shared memory
     bool profile = false;
     std::string err;
 
@@ -71,6 +72,12 @@ struct fsk_handle {
     uint32_t *d_ghist = nullptr, *d_ticket = nullptr, *d_status = nullptr;
     uint2 *d_tile_counts = nullptr, *d_tile_offs = nullptr, *d_totals = nullptr;
     uint32_t *d_ent_seq = nullptr, *d_ent_start = nullptr, *d_ent_run = nullptr, *d_run_start = nullptr;
+    uint32_t *d_woff32 = nullptr, *d_row_count = nullptr, *d_ent_pack = nullptr;
+    uint2* d_task = nullptr;
+    bool rows_path = false;
+    int rows_threads = 256;
+    size_t rows_smem = 0;
+    int64_t maxwin = 0;
     unsigned long long* d_Kint = nullptr;   // integer partial (exact / skip_variance), or per-slot Ks in variance mode
     int ks_slots = 1;
     std::vector<double*> d_Khat;            // one per local virtual stream
@@ -137,6 +144,8 @@ void release_device(fsk_handle* h) {
     h->d_ghist = h->d_ticket = h->d_status = nullptr;
     dev_free(h->d_tile_counts); dev_free(h->d_tile_offs); dev_free(h->d_totals);
     dev_free(h->d_ent_seq); dev_free(h->d_ent_start); dev_free(h->d_ent_run); dev_free(h->d_run_start);
+    dev_free(h->d_woff32); dev_free(h->d_ent_pack); dev_free(h->d_task);
+    h->d_row_count = nullptr;
     dev_free(h->d_Kint); dev_free(h->d_Kf);
     for (auto& p : h->d_Khat) dev_free(p);
     h->d_Khat.clear();
@@ -312,11 +321,24 @@ int run_batch(fsk_handle* h, const int32_t* combos, int nb, unsigned long long* 
     }
     {
         Span sp(h, PC_ACCUMULATE);
-        dim3 grid((unsigned)((h->nfeat + ACC_ROWS - 1) / ACC_ROWS), nb);
-        accumulate_kernel<unsigned long long><<<grid, 256, 0, h->stream>>>(h->d_ent_seq, h->d_ent_start, h->d_ent_run, h->d_run_start,
-                                                                         h->d_totals, (uint32_t)h->nfeat, K, slot_stride,
-                                                                         h->profile ? h->d_counters : nullptr);
-        h->launches++;
+        const uint32_t n = (uint32_t)h->nfeat;
+        if (h->rows_path) {
+            dim3 gfin((unsigned)((h->nfeat + 255) / 256), nb);
+            seg_finish_kernel<<<gfin, 256, 0, h->stream>>>(h->d_ent_seq, h->d_ent_start, h->d_ent_run, h->d_run_start, h->d_totals, n,
+                                                        (uint32_t)h->N, h->idbits, h->d_woff32, h->d_row_count, h->d_ent_pack, h->d_task);
+            const int groups = slot_stride ? nb : 1, per_group = slot_stride ? 1 : nb;
+            dim3 grid((unsigned)h->N, groups);
+            accumulate_rows_kernel<unsigned long long, 4><<<grid, h->rows_threads, h->rows_smem, h->stream>>>(
+                h->d_ent_pack, h->d_task, h->d_row_count, h->d_woff32, n, (uint32_t)h->N, h->idbits, per_group, K, slot_stride,
+                h->profile ? h->d_counters : nullptr);
+            h->launches += 2;
+        } else {
+            dim3 grid((unsigned)((h->nfeat + ACC_ROWS - 1) / ACC_ROWS), nb);
+            accumulate_kernel<unsigned long long><<<grid, 256, 0, h->stream>>>(h->d_ent_seq, h->d_ent_start, h->d_ent_run, h->d_run_start,
+                                                                             h->d_totals, n, K, slot_stride,
+                                                                             h->profile ? h->d_counters : nullptr);
+            h->launches++;
+        }
         CU(cudaGetLastError());
     }
     h->combos_done += nb;
@@ -345,6 +367,31 @@ int effective_streams(const fsk_handle* h, int64_t nq) {   // fastsk_kernel.cpp:
     if (T < 1) T = 1;
     if (T > nq) T = (int)nq;
     return T;
+}
+
+// What this shard processes.  Integer modes (exact, approx && skip_variance): the union of what every
+// reference thread would process -- stream tid runs queue[tid + T*r] until max_iters or the end of the
+// queue (fastsk_kernel.cpp:257-262, 275-278) -- dealt round-robin to the ranks; K is an integer sum, so
+// any partition gives the same result.  Variance mode: the ids of the virtual streams this rank owns.
+void shard_work(const fsk_handle* h, std::vector<int32_t>& out) {
+    out.clear();
+    const int64_t nq = (int64_t)h->queue.size();
+    const int T = effective_streams(h, nq);
+    if (h->approx && !h->skip_variance) {
+        for (int tid = h->rank; tid < T; tid += h->world) out.push_back(tid);
+        return;
+    }
+    std::vector<int32_t> work;
+    if (!h->approx) {
+        work = h->queue;
+    } else {
+        for (int tid = 0; tid < T; ++tid) {
+            int64_t avail = (nq - tid + T - 1) / T;
+            if (h->max_iters != -1) avail = std::min<int64_t>(avail, std::max(1, h->max_iters));
+            for (int64_t r = 0; r < avail; ++r) work.push_back(h->queue[(size_t)(tid + T * r)]);
+        }
+    }
+    for (size_t i = (size_t)h->rank; i < work.size(); i += (size_t)h->world) out.push_back(work[i]);
 }
 
 template <typename T>
@@ -417,6 +464,9 @@ int fsk_set_option(fsk_handle* h, const char* key, int64_t value) {
     if (!strcmp(key, "batch")) {
         if (value < 0 || value > MAX_BATCH) return fail(h, FSK_EINVAL, "batch must be in [0, %d]", MAX_BATCH);
         h->opt_batch = (int)value;
+    } else if (!strcmp(key, "acc_path")) {
+        if (value < 0 || value > 2) return fail(h, FSK_EINVAL, "acc_path must be 0 (auto), 1 (global RED) or 2 (shared-memory rows)");
+        h->opt_acc_path = (int)value;
     } else if (!strcmp(key, "profile")) {
         h->profile = value != 0;
     } else {
@@ -432,13 +482,14 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     const int64_t N = n_train + n_test;
     if (N >= (1LL << 31)) return fail(h, FSK_EINVAL, "too many sequences");
     // fastsk.cpp:53-58: g longer than the shortest sequence is fatal (exit(1) there, an error code here)
-    int64_t shortest_train = INT64_MAX, shortest_test = INT64_MAX, nfeat = 0;
+    int64_t shortest_train = INT64_MAX, shortest_test = INT64_MAX, nfeat = 0, maxwin = 0;
     for (int64_t i = 0; i < N; ++i) {
         const int64_t len = offsets[i + 1] - offsets[i];
         if (len < 0) return fail(h, FSK_EINVAL, "offsets must be non-decreasing");
         if (i < n_train) shortest_train = std::min(shortest_train, len);
         else shortest_test = std::min(shortest_test, len);
         nfeat += len - h->g + 1;
+        maxwin = std::max(maxwin, len - h->g + 1);
     }
     if (h->g > shortest_train)
         return fail(h, FSK_EINVAL, "g cannot be longer than the shortest sequence in a dataset: g = %d, but shortest train sequence has length %lld", h->g, (long long)shortest_train);
@@ -506,9 +557,42 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     }
     h->variance_mode = h->approx && !h->skip_variance;
 
-    // batch size: enough records per launch group to fill the machine
-    int B = h->opt_batch > 0 ? h->opt_batch : (int)std::min<int64_t>(MAX_BATCH, std::max<int64_t>(1, (6LL << 20) / std::max<int64_t>(1, nfeat)));
-    h->B = B;
+    h->maxwin = maxwin;
+    // accumulate path: rows of K in shared memory (4 B per column, one CTA per row) whenever a row fits
+    // and (sequence id, count) pack into 32 bits; otherwise global RED on the packed triangle
+    int max_smem = 0;
+    CU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    const bool rows_ok = (size_t)N * 4 + 64 <= (size_t)max_smem && h->idbits + ceil_log2(maxwin + 1) <= 32 &&
+                         (double)maxwin * (double)maxwin < 4294967296.0;
+    if (h->opt_acc_path == 2 && !rows_ok) return fail(h, FSK_EINVAL, "acc_path = 2 needs N * 4 B <= %d B of shared memory and id + count bits <= 32", max_smem);
+    h->rows_path = h->opt_acc_path == 2 || (h->opt_acc_path == 0 && rows_ok);
+    h->rows_smem = (size_t)N * 4;
+    h->rows_threads = N >= 16384 ? 1024 : (N >= 4096 ? 512 : 256);
+    if (h->rows_path)
+        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
+
+    // batch: combinations per launch group.  The row path flushes every row of K once per batch, so it
+    // wants the batch as large as memory allows; the u32 shared-memory accumulators bound it by 2^32 / maxwin^2.
+    const int64_t per_slot_bytes = nfeat * (2 * (h->mode == MODE_R32 ? 4 : 8) + (h->mode == MODE_KV ? 8 : 0) + 16 + (h->rows_path ? 12 : 0)) +
+                                   (int64_t)h->plan.npass * ((nfeat + 3071) / 3072) * RADIX * 4 + N * 4 + 4096;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    const int64_t k_bytes = h->n_pairs * 8 * (h->variance_mode ? 3 : 1) + (int64_t)n_train * N * 8;
+    int64_t Bsel = h->opt_batch > 0 ? h->opt_batch : MAX_BATCH;
+    if (h->opt_batch == 0) {
+        if (!h->rows_path) Bsel = std::max<int64_t>(1, (6LL << 20) / std::max<int64_t>(1, nfeat));
+        const int64_t budget = ((int64_t)free_b - k_bytes) * 4 / 10;
+        Bsel = std::min(Bsel, std::max<int64_t>(1, budget / std::max<int64_t>(1, per_slot_bytes + (h->variance_mode ? h->n_pairs * 8 : 0))));
+    }
+    Bsel = std::min<int64_t>(Bsel, MAX_BATCH);
+    Bsel = std::min<int64_t>(Bsel, std::max<int64_t>(1, (int64_t)(4294967295.0 / ((double)maxwin * (double)maxwin))));
+    Bsel = std::min<int64_t>(Bsel, std::max<int64_t>(1, h->user_queue.empty() ? h->ncomb : (int64_t)h->user_queue.size()));
+    if (h->variance_mode) {   // one slot per live virtual stream of this rank is all a round can use
+        const int64_t nq = h->user_queue.empty() ? h->ncomb : (int64_t)h->user_queue.size();
+        const int T = effective_streams(h, nq);
+        Bsel = std::min<int64_t>(Bsel, std::max(1, (T + h->world - 1) / h->world));
+    }
+    h->B = (int)Bsel;
     h->sort_tiles = (uint32_t)((nfeat + SORT_THREADS * h->sort_items - 1) / (SORT_THREADS * h->sort_items));
     h->seg_tiles = (uint32_t)((nfeat + SEG_TILE - 1) / SEG_TILE);
 
@@ -542,17 +626,20 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     }
 
     // scratch for B slots
-    const size_t bn = (size_t)B * (size_t)nfeat;
+    const size_t bn = (size_t)h->B * (size_t)nfeat;
     { unsigned char* p; ALLOC(p, bn * (h->mode == MODE_R32 ? 4 : 8)); h->d_recA = p; }
     { unsigned char* p; ALLOC(p, bn * (h->mode == MODE_R32 ? 4 : 8)); h->d_recB = p; }
     if (h->mode == MODE_KV) { ALLOC(h->d_valA, bn); ALLOC(h->d_valB, bn); }
+    const int B = h->B;
     const size_t ghist_words = (size_t)B * MAX_PASS * RADIX, ticket_words = 64;
+    const size_t rowcount_words = h->rows_path ? (size_t)B * (size_t)N : 0;
     const size_t status_words = (size_t)h->plan.npass * B * h->sort_tiles * RADIX;
-    h->zero_bytes = 4 * (ghist_words + ticket_words + status_words);
+    h->zero_bytes = 4 * (ghist_words + ticket_words + status_words + rowcount_words);
     ALLOC(h->d_zero, h->zero_bytes);
     h->d_ghist = (uint32_t*)h->d_zero;
     h->d_ticket = h->d_ghist + ghist_words;
     h->d_status = h->d_ticket + ticket_words;
+    h->d_row_count = h->d_status + status_words;
     ALLOC(h->d_tile_counts, (size_t)B * h->seg_tiles);
     ALLOC(h->d_tile_offs, (size_t)B * h->seg_tiles);
     ALLOC(h->d_totals, B);
@@ -560,6 +647,14 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     ALLOC(h->d_ent_start, bn + B);
     ALLOC(h->d_ent_run, bn);
     ALLOC(h->d_run_start, bn);
+    if (h->rows_path) {
+        ALLOC(h->d_ent_pack, bn);
+        ALLOC(h->d_task, bn);
+        std::vector<uint32_t> w32((size_t)N + 1);
+        for (int64_t i = 0; i <= N; ++i) w32[(size_t)i] = (uint32_t)woff[(size_t)i];
+        ALLOC(h->d_woff32, N + 1);
+        CU(cudaMemcpy(h->d_woff32, w32.data(), sizeof(uint32_t) * (size_t)(N + 1), cudaMemcpyHostToDevice));
+    }
     ALLOC(h->d_counters, 4);
     CU(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), h->stream));
 
@@ -619,26 +714,17 @@ int fsk_build_partial(fsk_handle* h) {
     h->T_eff = T;
 
     if (!h->variance_mode) {
-        // integer modes: the union of what every stream would process, dealt round-robin to the shards
-        std::vector<int32_t> work;
-        if (!h->approx) {
-            work = h->queue;
-        } else {   // approx && skip_variance: stream tid runs queue[tid + T*r] until max_iters (fastsk_kernel.cpp:257-262, 275-278)
-            for (int tid = 0; tid < T; ++tid) {
-                int64_t avail = (nq - tid + T - 1) / T;
-                if (h->max_iters != -1) avail = std::min<int64_t>(avail, std::max(1, h->max_iters));
-                for (int64_t r = 0; r < avail; ++r) work.push_back(h->queue[(size_t)(tid + T * r)]);
-            }
-        }
         std::vector<int32_t> mine;
-        for (size_t i = (size_t)h->rank; i < work.size(); i += (size_t)h->world) mine.push_back(work[i]);
+        shard_work(h, mine);
         rc = fsk_accumulate_combos(h, mine.data(), (int64_t)mine.size(), 0);
         if (rc) return rc;
     } else {
         // variance mode: T independent virtual streams (fastsk_kernel.cpp:188-281), stream tid owned by rank tid % world
         struct Stream { int tid; int64_t item; int iter; bool working; double* khat; };
         std::vector<Stream> streams;
-        for (int tid = h->rank; tid < T; tid += h->world) {
+        std::vector<int32_t> my_streams;
+        shard_work(h, my_streams);
+        for (int tid : my_streams) {
             double* kh;
             ALLOC(kh, h->n_pairs);
             h->d_Khat.push_back(kh);
@@ -827,6 +913,18 @@ int fsk_get_queue(fsk_handle* h, int32_t* out, int64_t cap, int64_t* n) {
     }
     if (n) *n = (int64_t)h->queue.size();
     for (int64_t i = 0; out && i < cap && i < (int64_t)h->queue.size(); ++i) out[i] = h->queue[(size_t)i];
+    return FSK_OK;
+}
+
+int fsk_get_shard_work(fsk_handle* h, int32_t* out, int64_t cap, int64_t* n) {
+    if (!h->uploaded) {
+        int rc = build_queue(h);
+        if (rc) return rc;
+    }
+    std::vector<int32_t> mine;
+    shard_work(h, mine);
+    if (n) *n = (int64_t)mine.size();
+    for (int64_t i = 0; out && i < cap && i < (int64_t)mine.size(); ++i) out[i] = mine[(size_t)i];
     return FSK_OK;
 }
 

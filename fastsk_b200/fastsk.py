@@ -132,10 +132,27 @@ class FastSK:
         self._call("fsk_set_shard", rank, world)
         self._call("fsk_upload", cp, op, n_train, n_test)
         self._call("fsk_build_partial")
-        part = self.partial_tensor()
-        dist.all_reduce(part, op=dist.ReduceOp.SUM)
+        self.reduce_partial(self.partial_tensor(), dist)
         torch.cuda.current_stream().synchronize()
         self._call("fsk_finalize")
+
+    @staticmethod
+    def reduce_partial(part, dist):
+        """The one collective of the path: sum the ranks' partial kernels in place (int64 in the integer
+        modes, float64 running means in variance mode).  NCCL over NVLink on the GPU box, gloo in CPU tests."""
+        dist.all_reduce(part, op=dist.ReduceOp.SUM)
+        return part
+
+    def set_shard(self, rank, world):
+        self._call("fsk_set_shard", int(rank), int(world))
+
+    def get_shard_work(self):
+        """Combination numbers (integer modes) or virtual stream ids (variance mode) of this handle's shard."""
+        n = ctypes.c_int64()
+        self._call("fsk_get_shard_work", None, 0, ctypes.byref(n))
+        out = np.zeros(max(n.value, 1), dtype=np.int32)
+        self._call("fsk_get_shard_work", out.ctypes.data_as(c_i32p), n.value, ctypes.byref(n))
+        return out[:n.value]
 
     def partial_tensor(self):
         """This rank's unnormalised partial kernel (packed lower triangle) as a zero-copy torch tensor."""

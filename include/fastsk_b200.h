@@ -62,7 +62,9 @@ int fsk_set_combo_sequence(fsk_handle* h, const int32_t* combos, int64_t n);
  * buffers of all ranks (one NCCL reduction) between fsk_build_partial and fsk_finalize. */
 int fsk_set_shard(fsk_handle* h, int rank, int world);
 /* tuning / diagnostics: "batch" (combinations per launch group, 0 = auto), "profile" (1 = time
- * every kernel class with CUDA events), "sync_every" ... unknown keys give FSK_EINVAL */
+ * every kernel class with CUDA events and count entries / runs / pair updates), "acc_path" (0 = auto,
+ * 1 = global RED on the packed triangle, 2 = row-stationary shared-memory accumulate); unknown keys
+ * give FSK_EINVAL */
 int fsk_set_option(fsk_handle* h, const char* key, int64_t value);
 
 /* ---- compute ---------------------------------------------------------------------------- */
@@ -109,6 +111,10 @@ int fsk_get_stdevs(fsk_handle* h, double* out, int64_t cap, int64_t* n);
 int fsk_save_kernel(fsk_handle* h, const char* path);
 /* the combination order in use (after shuffle / fsk_set_combo_sequence) */
 int fsk_get_queue(fsk_handle* h, int32_t* out, int64_t cap, int64_t* n);
+
+/* What this shard (fsk_set_shard) will process: combination numbers in the integer modes, virtual
+ * stream ids in the variance mode.  Needs no device. */
+int fsk_get_shard_work(fsk_handle* h, int32_t* out, int64_t cap, int64_t* n);
 
 /* ---- statistics --------------------------------------------------------------------------- */
 

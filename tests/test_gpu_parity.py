@@ -85,8 +85,9 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("acc_path", [0, 1], ids=["rows", "global_red"])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-def test_random_exact_vs_oracle(FastSK, oracle_mod, case):
+def test_random_exact_vs_oracle(FastSK, oracle_mod, case, acc_path):
     name, ntr, nte, alpha, (lo, hi), g, m, batch, lowc = case
     rng = np.random.default_rng(abs(hash(name)) % (2 ** 31))
     X = random_seqs(rng, ntr + nte, alpha, max(lo, g), hi, lowc)
@@ -97,6 +98,7 @@ def test_random_exact_vs_oracle(FastSK, oracle_mod, case):
     f = FastSK(g, m, combo_sequence=queue)
     if batch:
         f.set_option("batch", batch)
+    f.set_option("acc_path", acc_path)
     f.compute_kernel(X[:ntr], X[ntr:]) if nte else f.compute_train(X[:ntr])
     lut = {}
     Xd = [[lut.setdefault(v, len(lut) + 1) for v in x] for x in X]
