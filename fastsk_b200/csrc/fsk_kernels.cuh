@@ -221,15 +221,26 @@ onesweep_kernel(const RecT* __restrict__ in, RecT* __restrict__ out, const uint3
     const uint32_t gexcl = block_excl_scan_256(ghist[(size_t)slot * MAX_PASS * RADIX + tid], warp_sums, dummy);
     const uint32_t dstart = block_excl_scan_256(total, warp_sums, dummy);
 
+    // decoupled look-back, LOOK predecessors per step with independent loads in flight: the first wave of
+    // resident tiles has to walk back over every tile that started with it
     uint32_t excl = 0;
     if (tile > 0) {
-        const uint32_t* sp = my_status - RADIX;
-        while (true) {
-            uint32_t s;
-            do { s = ld_volatile_u32(sp); } while ((s >> 30) == 0);
-            excl += s & 0x3fffffffu;
-            if (s >> 31) break;
-            sp -= RADIX;
+        constexpr int LOOK = 8;
+        int64_t pt = (int64_t)tile - 1;
+        bool done = false;
+        while (!done) {
+            uint32_t sv[LOOK];
+#pragma unroll
+            for (int i = 0; i < LOOK; ++i) sv[i] = (pt - i >= 0) ? ld_volatile_u32(my_status - (size_t)(tile - (pt - i)) * RADIX) : 0x80000000u;
+#pragma unroll
+            for (int i = 0; i < LOOK; ++i) {
+                if (done) break;
+                uint32_t v = sv[i];
+                while ((v >> 30) == 0) v = ld_volatile_u32(my_status - (size_t)(tile - (pt - i)) * RADIX);
+                excl += v & 0x3fffffffu;
+                if (v >> 31) done = true;
+            }
+            pt -= LOOK;
         }
         st_volatile_u32(my_status, (total + excl) | 0x80000000u);
     }
@@ -465,11 +476,16 @@ seg_finish_kernel(const uint32_t* __restrict__ ent_seq, const uint32_t* __restri
     const uint32_t rs = run_start[sbase + ent_run[sbase + e]];
     ent_pack[sbase + e] = sb | (cnt << idbits);
     const uint32_t pos = atomicAdd(&row_count[(size_t)slot * nseq + sb], 1u);
-    task[sbase + woff[sb] + pos] = make_uint2(rs, e);
+    // task = (first entry of the run, prefix length - 1 | own count << idbits): same idbits + countbits <= 32
+    // condition as ent_pack
+    task[sbase + woff[sb] + pos] = make_uint2(rs, (e - rs) | (cnt << idbits));   // length - 1: 0 .. nseq-1 fits idbits
 }
 
 // grid = (rows, groups); the slots [group * slots_per_group, +slots_per_group) add into the same K.
 // Row N-1 first: the longest rows lead, the short ones fill the tail.
+// All (slot, task) pairs of the row are cut into chunks of 32 tasks; a warp takes a chunk, its lanes load
+// the 32 task words in one coalesced access, then the warp walks the tasks UNROLL at a time so that
+// UNROLL independent entry loads are in flight per lane ahead of the shared-memory atomics.
 template <typename AccT, int UNROLL>
 __global__ void __launch_bounds__(1024)
 accumulate_rows_kernel(const uint32_t* __restrict__ ent_pack, const uint2* __restrict__ task,
@@ -477,44 +493,79 @@ accumulate_rows_kernel(const uint32_t* __restrict__ ent_pack, const uint2* __res
                        uint32_t nseq, int idbits, int slots_per_group, AccT* __restrict__ K, size_t k_group_stride,
                        unsigned long long* __restrict__ stat_counters) {
     extern __shared__ uint32_t row[];
+    __shared__ uint32_t chunk_prefix[MAX_BATCH + 1];
+    __shared__ uint32_t next_chunk;
     const uint32_t b = nseq - 1 - blockIdx.x;
     const int group = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    uint32_t any = 0;
-    for (int s = 0; s < slots_per_group; ++s) any |= row_count[(size_t)(group * slots_per_group + s) * nseq + b];
-    if (any == 0) return;
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int s = 0; s < slots_per_group; ++s) {
+            chunk_prefix[s] = acc;
+            acc += (row_count[(size_t)(group * slots_per_group + s) * nseq + b] + 31) >> 5;
+        }
+        chunk_prefix[slots_per_group] = acc;
+        next_chunk = 0;
+    }
+    __syncthreads();
+    const uint32_t nchunks = chunk_prefix[slots_per_group];
+    if (nchunks == 0) return;
     for (uint32_t i = threadIdx.x; i <= b; i += blockDim.x) row[i] = 0;
     __syncthreads();
     const uint32_t idmask = (1u << idbits) - 1;
     const uint32_t wb = woff[b];
+    const uint32_t lane_le = 0xffffffffu >> (31 - lane);
     unsigned long long updates = 0;
-    for (int s = 0; s < slots_per_group; ++s) {
+    int s = 0;
+    while (true) {
+        // dynamic chunk scheduling: chunk ids only grow, so a warp's slot cursor only moves forward
+        uint32_t c = 0;
+        if (lane == 0) c = atomicAdd(&next_chunk, 1u);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= nchunks) break;
+        while (chunk_prefix[s + 1] <= c) ++s;
         const int slot = group * slots_per_group + s;
         const uint32_t nt = row_count[(size_t)slot * nseq + b];
-        const uint2* __restrict__ tk = task + (size_t)slot * n + wb;
+        const uint32_t t = ((c - chunk_prefix[s]) << 5) + lane;
         const uint32_t* __restrict__ ep = ent_pack + (size_t)slot * n;
-        for (uint32_t t0 = warp * UNROLL; t0 < nt; t0 += nwarps * UNROLL) {
-            uint32_t rs[UNROLL], len[UNROLL], cb[UNROLL], maxlen = 0;
+        uint2 q = make_uint2(0, 0);
+        uint32_t my_len = 0;
+        if (t < nt) {
+            q = task[(size_t)slot * n + wb + t];
+            my_len = (q.y & idmask) + 1;
+        }
+        const uint32_t my_cb = q.y >> idbits;
+        // load-balanced expansion of the 32 run prefixes over the lanes: P = start of task `lane` in the
+        // concatenation, W = total length.  For a window of 32 positions the tasks starting inside it are a
+        // bit mask (one REDUX); the task owning position i is the number of starts at or before i, minus 1.
+        uint32_t incl = my_len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        const uint32_t P = incl - my_len;
+        const uint32_t W = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t delta = q.x - P;                       // entry index = delta[j] + position
+        const bool unit = __all_sync(0xffffffffu, my_cb <= 1u);   // every own count is 1: skip one shuffle
+        updates += my_len;
+        uint32_t started = 0;
+        for (uint32_t base = 0; base < W; base += 32 * UNROLL) {
+            uint32_t a[UNROLL], cb[UNROLL], p[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
-                len[u] = 0; rs[u] = 0; cb[u] = 0;
-                if (t0 + u < nt) {
-                    const uint2 q = tk[t0 + u];
-                    rs[u] = q.x;
-                    len[u] = q.y - q.x + 1;
-                    cb[u] = ep[q.y] >> idbits;
-                    maxlen = max(maxlen, len[u]);
-                    updates += len[u];
-                }
+                const uint32_t rel = P - (base + 32 * u);
+                const uint32_t m = __reduce_or_sync(0xffffffffu, (rel < 32u && my_len) ? (1u << rel) : 0u);
+                const uint32_t j = (started + __popc(m & lane_le) - 1) & 31;
+                started += __popc(m);
+                a[u] = __shfl_sync(0xffffffffu, delta, j) + base + 32 * u + lane;
+                cb[u] = unit ? 1u : __shfl_sync(0xffffffffu, my_cb, j);
             }
-            for (uint32_t off = lane; off < maxlen; off += 32) {
-                uint32_t p[UNROLL];
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u) p[u] = off < len[u] ? ep[rs[u] + off] : 0u;
+            for (int u = 0; u < UNROLL; ++u) p[u] = (base + 32 * u + lane < W) ? ep[a[u]] : 0u;
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u)
-                    if (off < len[u]) atomicAdd(&row[p[u] & idmask], (p[u] >> idbits) * cb[u]);
-            }
+            for (int u = 0; u < UNROLL; ++u)
+                if (base + 32 * u + lane < W) atomicAdd(&row[p[u] & idmask], (p[u] >> idbits) * cb[u]);
         }
     }
     __syncthreads();
@@ -523,7 +574,11 @@ accumulate_rows_kernel(const uint32_t* __restrict__ ent_pack, const uint2* __res
         const uint32_t v = row[i];
         if (v) Krow[i] += (AccT)v;
     }
-    if (stat_counters && lane == 0 && updates) atomicAdd(&stat_counters[2], updates);
+    if (stat_counters) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) updates += __shfl_xor_sync(0xffffffffu, updates, o);
+        if (lane == 0 && updates) atomicAdd(&stat_counters[2], updates);
+    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -562,7 +562,7 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     // and (sequence id, count) pack into 32 bits; otherwise global RED on the packed triangle
     int max_smem = 0;
     CU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-    const bool rows_ok = (size_t)N * 4 + 64 <= (size_t)max_smem && h->idbits + ceil_log2(maxwin + 1) <= 32 &&
+    const bool rows_ok = (size_t)N * 4 + 1024 <= (size_t)max_smem && h->idbits + ceil_log2(maxwin + 1) <= 32 &&
                          (double)maxwin * (double)maxwin < 4294967296.0;
     if (h->opt_acc_path == 2 && !rows_ok) return fail(h, FSK_EINVAL, "acc_path = 2 needs N * 4 B <= %d B of shared memory and id + count bits <= 32", max_smem);
     h->rows_path = h->opt_acc_path == 2 || (h->opt_acc_path == 0 && rows_ok);

@@ -1,0 +1,43 @@
+"""Profiling driver (run under ncu): the C4 workload, one warm-up batch and one profiled batch.
+
+    ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
+        python tools/profile_step.py --batch 8
+"""
+import argparse
+import os
+import sys
+from math import comb
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fastsk_b200 import FastSK, _lib  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=8)
+ap.add_argument("--n", type=int, default=50000)
+ap.add_argument("--len", type=int, default=200)
+ap.add_argument("--g", type=int, default=16)
+ap.add_argument("--m", type=int, default=8)
+ap.add_argument("--alphabet", type=int, default=4)
+ap.add_argument("--acc-path", type=int, default=0)
+ap.add_argument("--reps", type=int, default=1)
+a = ap.parse_args()
+
+X = np.random.default_rng(0).integers(1, a.alphabet + 1, size=(a.n, a.len), dtype=np.int32)
+order = np.random.default_rng(0).permutation(comb(a.g, a.m)).astype(np.int32)
+f = FastSK(a.g, a.m, combo_sequence=order, distributed=False, profile=True)
+f.set_option("batch", a.batch)
+f.set_option("acc_path", a.acc_path)
+codes = np.ascontiguousarray(X.reshape(-1))
+offsets = np.arange(a.n + 1, dtype=np.int64) * a.len
+f._call("fsk_upload", codes.ctypes.data_as(_lib.c_i32p), offsets.ctypes.data_as(_lib.c_i64p), int(a.n * 0.8), a.n - int(a.n * 0.8))
+for r in range(1 + a.reps):
+    q = np.ascontiguousarray(order[r * a.batch:(r + 1) * a.batch])
+    f._call("fsk_accumulate_combos", q.ctypes.data_as(_lib.c_i32p), len(q), 1)
+    if r == 0:
+        s0 = f.stats()
+s1 = f.stats()
+d = {k: s1[k] - s0[k] for k in s1 if k.startswith("ms_") or k in ("pair_updates", "entries", "runs", "combos_done", "kernel_launches")}
+print({k: (round(v, 3) if isinstance(v, float) else v) for k, v in d.items()})
+print({k: s1[k] for k in ("nfeat", "n_pairs", "key_bits", "id_bits", "record_bytes", "sort_passes", "batch")})
