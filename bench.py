@@ -230,6 +230,7 @@ def run_b200(args):
     f = FastSK(G, M, combo_sequence=order, device=local, distributed=False, profile=True)
     f.set_option("batch", args.batch)
     f.set_option("acc_path", args.acc_path)
+    f.set_option("wave", args.wave)
     codes = np.ascontiguousarray(X.reshape(-1))
     offsets = np.arange(N_SEQ + 1, dtype=np.int64) * SEQ_LEN
     f._call("fsk_upload", codes.ctypes.data_as(_lib.c_i32p), offsets.ctypes.data_as(_lib.c_i64p), N_TRAIN, N_SEQ - N_TRAIN)
@@ -310,6 +311,7 @@ def run_b200(args):
         fe = FastSK(G, M, combo_sequence=q, device=local)
         fe.set_option("batch", args.batch)
         fe.set_option("acc_path", args.acc_path)
+        fe.set_option("wave", args.wave)
         fe.compute_kernel(Xtr_p, Xte_p)
         if rank == 0:
             fe.get_train_kernel(out=out_tr)
@@ -362,6 +364,7 @@ def main():
     ap.add_argument("--combos-per-step", type=int, default=96)
     ap.add_argument("--batch", type=int, default=0, help="combinations per launch group (0 = auto)")
     ap.add_argument("--acc-path", type=int, default=0, help="0 auto, 1 global RED, 2 shared-memory rows")
+    ap.add_argument("--wave", type=int, default=1, help="accumulate launch = wave x resident CTAs rows")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of reference CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

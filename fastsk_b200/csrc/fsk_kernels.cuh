@@ -7,8 +7,10 @@
 //   onesweep    stable LSD radix sort over the key bits only, one kernel per 8-bit digit:
 //               warp match ranking + decoupled look-back (replaces cntsrtna, shared.cpp:156-191,
 //               and the gather of sorted features, fastsk_kernel.cpp:233-238)
-//   segment     run boundaries and per-(k-mer, sequence) counts (shared.cpp:280-315)
-//   accumulate  K[i][j] += c_i * c_j on the packed lower triangle (shared.cpp:316-327)
+//   segment     run boundaries of the sorted records -> one task (run start, prefix length) per record,
+//               filed under the record's sequence (shared.cpp:280-315)
+//   accumulate  K[i][j] += c_i * c_j on the packed lower triangle (shared.cpp:316-327), one row of K
+//               per CTA in shared memory
 // plus normalise (fastsk_kernel.cpp:96-103) and the Welford / variance pass
 // (fastsk_kernel.cpp:108-143).
 #pragma once
@@ -22,10 +24,6 @@ constexpr int MAX_BATCH = 48;    // combinations per launch group (kernel-parame
 constexpr int MAX_PASS = 8;      // 64 key bits / 8
 constexpr int RADIX = 256;
 constexpr int SORT_THREADS = 256;
-constexpr int SEG_THREADS = 256;
-constexpr int SEG_ITEMS = 8;
-constexpr int SEG_TILE = SEG_THREADS * SEG_ITEMS;
-constexpr int ACC_ROWS = 64;     // entries (rows of updates) per accumulate CTA
 constexpr int PACK_ITEMS = 8;
 
 struct BatchSpec {               // by value in kernel parameter space
@@ -154,7 +152,7 @@ pack_hist_kernel(const GwT* __restrict__ gw0, const uint64_t* __restrict__ gw1, 
 template <typename RecT, bool KV, int ITEMS>
 __global__ void __launch_bounds__(SORT_THREADS)
 onesweep_kernel(const RecT* __restrict__ in, RecT* __restrict__ out, const uint32_t* __restrict__ vin,
-                uint32_t* __restrict__ vout, uint32_t n, uint32_t tiles_per_slot, int shift, int bits,
+                uint32_t* __restrict__ vout, uint32_t n, uint32_t tiles_per_slot, uint32_t nslots, int shift, int bits,
                 const uint32_t* __restrict__ ghist /* [slot][MAX_PASS][RADIX], pre-offset to this pass */,
                 uint32_t* __restrict__ status /* [slot][tile][RADIX] of this pass */, uint32_t* __restrict__ ticket) {
     constexpr int TILE = SORT_THREADS * ITEMS;
@@ -171,8 +169,10 @@ onesweep_kernel(const RecT* __restrict__ in, RecT* __restrict__ out, const uint3
     if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
     for (int i = tid; i < 8 * RADIX; i += SORT_THREADS) warp_hist[i] = 0;
     __syncthreads();
-    const uint32_t slot = s_ticket / tiles_per_slot;
-    const uint32_t tile = s_ticket - slot * tiles_per_slot;
+    // tickets deal the slots round-robin: the tiles in flight at any time are spread over all slots of the batch, so a
+    // tile's look-back crosses only the few running tiles of its own slot (not every resident CTA of the chip)
+    const uint32_t tile = s_ticket / nslots;
+    const uint32_t slot = s_ticket - tile * nslots;
     const size_t sbase = (size_t)slot * n;
     const uint32_t tile0 = tile * TILE;
     const uint32_t dmask = (1u << bits) - 1;
@@ -270,314 +270,305 @@ onesweep_kernel(const RecT* __restrict__ in, RecT* __restrict__ out, const uint3
 }
 
 // ------------------------------------------------------------------------------------------
-// segmentation of the sorted records.
-//   entry = one distinct (k-mer, sequence) cell; ent_seq (bit 31: first entry of its run),
-//           ent_start (index of its first record; count = ent_start[e+1] - ent_start[e]),
-//           ent_run (index of its run);  run_start[r] = first entry of run r.
-template <typename RecT, bool KV>
-__device__ __forceinline__ void seg_flags(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, size_t sbase,
-                                          uint32_t i, int idbits, bool& new_ent, bool& new_run, uint32_t& seq) {
-    const RecT r = rec[sbase + i];
-    if (KV) {
-        seq = val[sbase + i];
-        if (i == 0) { new_ent = new_run = true; return; }
-        const RecT p = rec[sbase + i - 1];
-        new_run = p != r;
-        new_ent = new_run || val[sbase + i - 1] != seq;
-    } else {
-        seq = (uint32_t)(r & (((RecT)1 << idbits) - 1));
-        if (i == 0) { new_ent = new_run = true; return; }
-        const RecT p = rec[sbase + i - 1];
-        new_run = (p >> idbits) != (r >> idbits);
-        new_ent = p != r;
-    }
-}
+// segmentation of the sorted records (shared.cpp:280-315 without materialising the per-run count
+// table).
+//
+// Every sorted record i is one TASK of its own sequence b = seq(i): "add 1 to K[b][seq(j)] for every
+// record j of the same run from the run's first record rs(i) to the last record ge(i) of b's own group".
+// Summed over the c_b records of b in the run this gives K[b][a] += c_a * c_b for every a <= b of the run
+// and K[b][b] += c_b^2 -- exactly the update of shared.cpp:316-327 -- with no per-(k-mer, sequence)
+// compaction pass: the sorted records themselves are the entry list (ids ascend inside a run because the
+// sort is stable).
+//
+// Outputs: ids[i] = seq(i) (IdT = u16 when N <= 65536, else u32), and the tasks filed by row:
+//   task[woff[b] + fill[b]++] = (rs, ge - rs + 1)          (a sequence has exactly as many tasks as windows).
+// A warp owns SEG_ROWS x 32 consecutive records; run heads / group tails are warp ballots, so the last
+// head at or before a record and the first tail at or after it are bit scans.
+constexpr int SEG_THREADS = 256;
+constexpr int SEG_ROWS = 16;
+constexpr int SEG_WARP_RECS = SEG_ROWS * 32;
+constexpr int SEG_TILE = (SEG_THREADS / 32) * SEG_WARP_RECS;
 
 template <typename RecT, bool KV>
+struct RecOps {
+    static __device__ __forceinline__ bool same_key(RecT a, RecT b, int idbits) { return KV ? a == b : ((a ^ b) >> idbits) == 0; }
+    static __device__ __forceinline__ bool key_less(RecT a, RecT b, int idbits) { return KV ? a < b : (a >> idbits) < (b >> idbits); }
+};
+
+template <typename RecT, bool KV, typename IdT>
 __global__ void __launch_bounds__(SEG_THREADS)
-seg_count_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, uint32_t n, int idbits,
-                 uint32_t tiles_per_slot, uint2* __restrict__ tile_counts) {
-    __shared__ uint32_t se[8], sr[8];
+segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, uint32_t n, size_t ids_stride, int idbits,
+               uint32_t nseq, const uint32_t* __restrict__ woff, uint32_t* __restrict__ fill, IdT* __restrict__ ids,
+               uint2* __restrict__ task, unsigned long long* __restrict__ stat_counters) {
+    using Ops = RecOps<RecT, KV>;
     const int slot = blockIdx.y;
-    const size_t sbase = (size_t)slot * n;
-    const uint32_t i0 = blockIdx.x * SEG_TILE + threadIdx.x * SEG_ITEMS;
-    uint32_t ce = 0, cr = 0;
-#pragma unroll
-    for (int j = 0; j < SEG_ITEMS; ++j) {
-        const uint32_t i = i0 + j;
-        if (i < n) {
-            bool ne, nr;
-            uint32_t seq;
-            seg_flags<RecT, KV>(rec, val, sbase, i, idbits, ne, nr, seq);
-            ce += ne;
-            cr += nr;
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        ce += __shfl_xor_sync(0xffffffffu, ce, o);
-        cr += __shfl_xor_sync(0xffffffffu, cr, o);
-    }
-    if ((threadIdx.x & 31) == 0) { se[threadIdx.x >> 5] = ce; sr[threadIdx.x >> 5] = cr; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t e = 0, r = 0;
-        for (int w = 0; w < 8; ++w) { e += se[w]; r += sr[w]; }
-        tile_counts[(size_t)slot * tiles_per_slot + blockIdx.x] = make_uint2(e, r);
-    }
-}
-
-// one CTA per slot: exclusive scan of the tile counts; totals; sentinel ent_start[E] = n
-__global__ void __launch_bounds__(1024)
-seg_scan_kernel(const uint2* __restrict__ tile_counts, uint2* __restrict__ tile_offs, uint32_t tiles_per_slot,
-                uint2* __restrict__ totals, uint32_t* __restrict__ ent_start, uint32_t n, unsigned long long* __restrict__ stat_counters) {
-    __shared__ uint32_t we[32], wr[32];
-    __shared__ uint32_t carry_e, carry_r;
-    const int slot = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) { carry_e = 0; carry_r = 0; }
-    __syncthreads();
-    for (uint32_t base = 0; base < tiles_per_slot; base += 1024) {
-        const uint32_t t = base + threadIdx.x;
-        uint2 c = make_uint2(0, 0);
-        if (t < tiles_per_slot) c = tile_counts[(size_t)slot * tiles_per_slot + t];
-        uint32_t ie = c.x, ir = c.y;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t a = __shfl_up_sync(0xffffffffu, ie, o), b = __shfl_up_sync(0xffffffffu, ir, o);
-            if (lane >= o) { ie += a; ir += b; }
-        }
-        if (lane == 31) { we[warp] = ie; wr[warp] = ir; }
-        __syncthreads();
-        uint32_t be = carry_e, br = carry_r, te = 0, tr = 0;
-        for (int w = 0; w < 32; ++w) {
-            if (w < warp) { be += we[w]; br += wr[w]; }
-            te += we[w];
-            tr += wr[w];
-        }
-        if (t < tiles_per_slot) tile_offs[(size_t)slot * tiles_per_slot + t] = make_uint2(be + ie - c.x, br + ir - c.y);
-        __syncthreads();
-        if (threadIdx.x == 0) { carry_e += te; carry_r += tr; }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        totals[slot] = make_uint2(carry_e, carry_r);
-        ent_start[(size_t)slot * (n + 1) + carry_e] = n;
-        if (stat_counters) {
-            atomicAdd(&stat_counters[0], (unsigned long long)carry_e);
-            atomicAdd(&stat_counters[1], (unsigned long long)carry_r);
-        }
-    }
-}
-
-template <typename RecT, bool KV>
-__global__ void __launch_bounds__(SEG_THREADS)
-seg_write_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, uint32_t n, int idbits,
-                 uint32_t tiles_per_slot, const uint2* __restrict__ tile_offs, uint32_t* __restrict__ ent_seq,
-                 uint32_t* __restrict__ ent_start, uint32_t* __restrict__ ent_run, uint32_t* __restrict__ run_start) {
-    __shared__ uint32_t warp_sums[8];
-    const int slot = blockIdx.y;
     const size_t sbase = (size_t)slot * n;
-    const size_t ebase = (size_t)slot * (n + 1);
-    const uint32_t i0 = blockIdx.x * SEG_TILE + threadIdx.x * SEG_ITEMS;
-    uint32_t fe = 0, fr = 0, seqs[SEG_ITEMS];
-    uint32_t ce = 0, cr = 0;
+    const RecT* __restrict__ R = rec + sbase;
+    const uint32_t* __restrict__ V = KV ? val + sbase : nullptr;
+    const uint32_t seg0 = blockIdx.x * SEG_TILE + warp * SEG_WARP_RECS;
+    if (seg0 >= n) return;
+    const RecT idmask = KV ? (RecT)0 : (((RecT)1 << idbits) - 1);
+
+    RecT r[SEG_ROWS];
+    uint32_t sq[SEG_ROWS];
 #pragma unroll
-    for (int j = 0; j < SEG_ITEMS; ++j) {
-        const uint32_t i = i0 + j;
-        seqs[j] = 0;
+    for (int k = 0; k < SEG_ROWS; ++k) {
+        const uint32_t i = seg0 + k * 32 + lane;
+        r[k] = 0;
+        sq[k] = 0;
         if (i < n) {
-            bool ne, nr;
-            seg_flags<RecT, KV>(rec, val, sbase, i, idbits, ne, nr, seqs[j]);
-            fe |= (uint32_t)ne << j;
-            fr |= (uint32_t)nr << j;
-            ce += ne;
-            cr += nr;
+            r[k] = R[i];
+            sq[k] = KV ? V[i] : (uint32_t)(r[k] & idmask);
         }
     }
-    uint32_t total;
-    const uint32_t ex = block_excl_scan_256(ce | (cr << 16), warp_sums, total);   // <= 2048 each: 12 bits
-    const uint2 off = tile_offs[(size_t)slot * tiles_per_slot + blockIdx.x];
-    uint32_t e = off.x + (ex & 0xffffu);
-    uint32_t r = off.y + (ex >> 16);
-#pragma unroll
-    for (int j = 0; j < SEG_ITEMS; ++j) {
-        if (fe >> j & 1) {
-            const bool head = fr >> j & 1;
-            if (head) { run_start[sbase + r] = e; ++r; }
-            ent_seq[sbase + e] = seqs[j] | (head ? 0x80000000u : 0u);
-            ent_start[ebase + e] = i0 + j;
-            ent_run[sbase + e] = r - 1;
-            ++e;
-        }
-    }
-}
+    // the records just outside the warp's segment
+    RecT r_before = 0, r_after = 0;
+    uint32_t s_before = 0, s_after = 0;
+    const uint32_t seg_end = min(seg0 + SEG_WARP_RECS, n);   // exclusive
+    if (seg0 > 0) { r_before = R[seg0 - 1]; if (KV) s_before = V[seg0 - 1]; }
+    if (seg_end < n) { r_after = R[seg_end]; if (KV) s_after = V[seg_end]; }
 
-// ------------------------------------------------------------------------------------------
-// accumulate: each entry b of a run is one row of updates K[seq_b][seq_a] += c_a * c_b over the
-// entries a <= b of the same run (ids ascend inside a run, so seq_a <= seq_b: packed lower
-// triangle, 64-bit index; shared.cpp:97-117 uses int).  One warp per row, lanes over a.
-// grid = (ceil(n / ACC_ROWS), slots); CTAs beyond the slot's entry count exit.
-template <typename AccT>
-__global__ void __launch_bounds__(256)
-accumulate_kernel(const uint32_t* __restrict__ ent_seq, const uint32_t* __restrict__ ent_start,
-                  const uint32_t* __restrict__ ent_run, const uint32_t* __restrict__ run_start,
-                  const uint2* __restrict__ totals, uint32_t n, AccT* __restrict__ K, size_t k_slot_stride,
-                  unsigned long long* __restrict__ stat_counters) {
-    const int slot = blockIdx.y;
-    const uint32_t E = totals[slot].x;
-    const uint32_t first = blockIdx.x * ACC_ROWS;
-    if (first >= E) return;
-    const size_t sbase = (size_t)slot * n;
-    const size_t ebase = (size_t)slot * (n + 1);
-    AccT* Ks = K + (size_t)slot * k_slot_stride;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t last = min(first + ACC_ROWS, E);
+    uint32_t hm[SEG_ROWS], tm[SEG_ROWS];   // run-head / group-tail ballots (warp-uniform)
+    uint32_t n_groups = 0;
+#pragma unroll
+    for (int k = 0; k < SEG_ROWS; ++k) {
+        const uint32_t i = seg0 + k * 32 + lane;
+        // previous record of lane 0 is lane 31 of the previous row; next record of lane 31 is lane 0 of the next row
+        RecT pr = __shfl_up_sync(0xffffffffu, r[k], 1);
+        uint32_t ps = __shfl_up_sync(0xffffffffu, sq[k], 1);
+        RecT nr = __shfl_down_sync(0xffffffffu, r[k], 1);
+        uint32_t ns = __shfl_down_sync(0xffffffffu, sq[k], 1);
+        const RecT pr_row = k > 0 ? __shfl_sync(0xffffffffu, r[k > 0 ? k - 1 : 0], 31) : r_before;
+        const uint32_t ps_row = k > 0 ? __shfl_sync(0xffffffffu, sq[k > 0 ? k - 1 : 0], 31) : s_before;
+        const RecT nr_row = k < SEG_ROWS - 1 ? __shfl_sync(0xffffffffu, r[k < SEG_ROWS - 1 ? k + 1 : k], 0) : r_after;
+        const uint32_t ns_row = k < SEG_ROWS - 1 ? __shfl_sync(0xffffffffu, sq[k < SEG_ROWS - 1 ? k + 1 : k], 0) : s_after;
+        if (lane == 0) { pr = pr_row; ps = ps_row; }
+        if (lane == 31) { nr = nr_row; ns = ns_row; }
+        const bool valid = i < n;
+        const bool head = valid && (i == 0 || !Ops::same_key(pr, r[k], idbits));
+        const bool ghead = valid && (i == 0 || pr != r[k] || (KV && ps != sq[k]));
+        const bool tail = valid && (i + 1 >= n || nr != r[k] || (KV && ns != sq[k]));
+        hm[k] = __ballot_sync(0xffffffffu, head);
+        tm[k] = __ballot_sync(0xffffffffu, tail);
+        n_groups += __popc(__ballot_sync(0xffffffffu, ghead));
+    }
+
+    // run start of the segment's first record when its run began before the segment: walk back in blocks of 32
+    // (typical runs are short), then lower_bound over the sorted records for very long runs
+    uint32_t carry_head = seg0;
+    if (seg0 > 0 && !(hm[0] & 1u)) {
+        const RecT r_first = __shfl_sync(0xffffffffu, r[0], 0);
+        uint32_t lo_known = 0;              // a position known to be <= the run start
+        bool found = false;
+        uint32_t p = seg0;                  // records [p, seg0) all have the key of r_first
+        for (int step = 0; step < 8 && p > 0 && !found; ++step) {
+            const uint32_t j = p - 1 - lane;               // may wrap below 0
+            const bool inb = lane < p;
+            const bool differs = inb && !Ops::same_key(R[inb ? j : 0], r_first, idbits);
+            const uint32_t dm = __ballot_sync(0xffffffffu, differs);
+            if (dm) { p = p - (__ffs(dm) - 1); found = true; }      // first differing record going backwards is at p-1-l
+            else p = p > 32 ? p - 32 : 0;
+        }
+        if (!found && p > 0) {              // lower_bound of the key in [lo_known, p)
+            uint32_t lo = lo_known, hi = p;
+            while (lo < hi) {
+                const uint32_t mid = lo + ((hi - lo) >> 1);
+                if (Ops::key_less(R[mid], r_first, idbits)) lo = mid + 1;
+                else hi = mid;
+            }
+            p = lo;
+        }
+        carry_head = p;
+    }
+
+    // first group tail at or after each record, scanning the rows backwards
+    uint32_t ge[SEG_ROWS];
+    {
+        uint32_t next_tail = 0xffffffffu;   // first tail in the rows after row k (warp-uniform)
+        const uint32_t lane_ge = 0xffffffffu << lane;
+#pragma unroll
+        for (int k = SEG_ROWS - 1; k >= 0; --k) {
+            const uint32_t base = seg0 + k * 32;
+            const uint32_t m = tm[k] & lane_ge;
+            ge[k] = m ? base + (__ffs(m) - 1) : next_tail;
+            if (tm[k]) next_tail = base + (__ffs(tm[k]) - 1);
+        }
+    }
     unsigned long long updates = 0;
-    for (uint32_t eb = first + warp; eb < last; eb += 8) {
-        const uint32_t sb = ent_seq[sbase + eb] & 0x7fffffffu;
-        const uint32_t cb = ent_start[ebase + eb + 1] - ent_start[ebase + eb];
-        const uint32_t rs = run_start[sbase + ent_run[sbase + eb]];
-        AccT* row = Ks + ((size_t)sb * (sb + 1) >> 1);
-        for (uint32_t a = rs + lane; a <= eb; a += 32) {
-            const uint32_t sa = ent_seq[sbase + a] & 0x7fffffffu;
-            const uint32_t ca = ent_start[ebase + a + 1] - ent_start[ebase + a];
-            atomicAdd(row + sa, (AccT)ca * (AccT)cb);
+    uint32_t last_head = carry_head;
+    const uint32_t lane_le = 0xffffffffu >> (31 - lane);
+#pragma unroll
+    for (int k = 0; k < SEG_ROWS; ++k) {
+        const uint32_t base = seg0 + k * 32;
+        const uint32_t i = base + lane;
+        const uint32_t m = hm[k] & lane_le;
+        const uint32_t rs = m ? base + (31 - __clz(m)) : last_head;
+        if (hm[k]) last_head = base + (31 - __clz(hm[k]));
+        if (i < n) {
+            uint32_t g = ge[k];
+            if (g == 0xffffffffu) {          // the group runs past the warp's segment (rare): follow it
+                g = seg_end - 1;
+                while (g + 1 < n && R[g + 1] == r[k] && (!KV || V[g + 1] == sq[k])) ++g;
+            }
+            const uint32_t len = g - rs + 1;
+            const uint32_t b = sq[k];
+            ids[(size_t)slot * ids_stride + i] = (IdT)b;
+            const uint32_t pos = atomicAdd(&fill[(size_t)slot * nseq + b], 1u);
+            task[sbase + woff[b] + pos] = make_uint2(rs, len);
+            updates += len;
         }
-        updates += eb - rs + 1;
     }
-    if (stat_counters && lane == 0) atomicAdd(&stat_counters[2], updates);
+    if (stat_counters) {
+        uint32_t n_runs = 0;
+#pragma unroll
+        for (int k = 0; k < SEG_ROWS; ++k) n_runs += __popc(hm[k]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) updates += __shfl_xor_sync(0xffffffffu, updates, o);
+        if (lane == 0) {
+            atomicAdd(&stat_counters[0], (unsigned long long)n_groups);
+            atomicAdd(&stat_counters[1], (unsigned long long)n_runs);
+            atomicAdd(&stat_counters[2], updates);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
-// Row-stationary accumulate (the default path).
+// accumulate (shared.cpp:316-327): K[b][ids[j]] += 1 for every task (rs, len) of row b and every j in
+// [rs, rs + len).
 //
-// Measured on B200 (profiles/r01_atomic_microbench.txt): scattered RED into the 10 GB packed
-// triangle runs at 20 G updates/s (DRAM sector read-modify-write), L2-resident at 210 G/s, and
-// shared-memory atomics at > 800 G/s.  So the update is re-ordered by OUTPUT ROW: one CTA owns
-// row b of K for a whole batch of combinations, keeps it in shared memory (4 B x (b+1), <= 227 KB),
-// streams the run prefixes of b's k-mers and flushes the row to HBM once per batch.
+// Measured on B200 (profiles/r01_atomic_microbench.txt): scattered RED into the 10 GB packed triangle
+// runs at 20 G updates/s (DRAM sector read-modify-write), L2-resident at 210 G/s, shared-memory atomics
+// at > 800 G/s.  So the update is ordered by OUTPUT ROW: one CTA owns row b of K for a whole batch of
+// combinations, keeps it in shared memory (4 B x (b+1) <= 227 KB), streams the id ranges of its tasks and
+// adds the row to HBM once per batch.
 //
-// seg_finish turns every entry (k-mer, sequence b) into a task (run start, entry) filed under
-// row b: task[woff[b] + i], i < row_count[b] (a sequence has at most as many entries as
-// windows, so its window range is its task range), and packs (sequence, count) into one word.
-__global__ void __launch_bounds__(256)
-seg_finish_kernel(const uint32_t* __restrict__ ent_seq, const uint32_t* __restrict__ ent_start,
-                  const uint32_t* __restrict__ ent_run, const uint32_t* __restrict__ run_start,
-                  const uint2* __restrict__ totals, uint32_t n, uint32_t nseq, int idbits,
-                  const uint32_t* __restrict__ woff, uint32_t* __restrict__ row_count,
-                  uint32_t* __restrict__ ent_pack, uint2* __restrict__ task) {
-    const int slot = blockIdx.y;
-    const uint32_t e = blockIdx.x * 256 + threadIdx.x;
-    if (e >= totals[slot].x) return;
-    const size_t sbase = (size_t)slot * n, ebase = (size_t)slot * (n + 1);
-    const uint32_t sb = ent_seq[sbase + e] & 0x7fffffffu;
-    const uint32_t cnt = ent_start[ebase + e + 1] - ent_start[ebase + e];
-    const uint32_t rs = run_start[sbase + ent_run[sbase + e]];
-    ent_pack[sbase + e] = sb | (cnt << idbits);
-    const uint32_t pos = atomicAdd(&row_count[(size_t)slot * nseq + sb], 1u);
-    // task = (first entry of the run, prefix length - 1 | own count << idbits): same idbits + countbits <= 32
-    // condition as ent_pack
-    task[sbase + woff[sb] + pos] = make_uint2(rs, (e - rs) | (cnt << idbits));   // length - 1: 0 .. nseq-1 fits idbits
+// The id ranges are read in aligned 16-byte units (8 u16 ids).  A warp takes 32 tasks (one coalesced
+// load), cuts their ranges into units, and deals the concatenated units over its lanes 32 at a time
+// (load-balanced expansion: the task owning position i is the number of task starts at or before i), so
+// every load instruction is 32 x 16 B in a handful of cache lines and every lane then issues 8 shared-
+// memory atomics; units that straddle a range end are masked.
+__device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
+    uint4 v;
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
 }
 
-// grid = (rows, groups); the slots [group * slots_per_group, +slots_per_group) add into the same K.
-// Row N-1 first: the longest rows lead, the short ones fill the tail.
-// All (slot, task) pairs of the row are cut into chunks of 32 tasks; a warp takes a chunk, its lanes load
-// the 32 task words in one coalesced access, then the warp walks the tasks UNROLL at a time so that
-// UNROLL independent entry loads are in flight per lane ahead of the shared-memory atomics.
-template <typename AccT, int UNROLL>
-__global__ void __launch_bounds__(1024)
-accumulate_rows_kernel(const uint32_t* __restrict__ ent_pack, const uint2* __restrict__ task,
-                       const uint32_t* __restrict__ row_count, const uint32_t* __restrict__ woff, uint32_t n,
-                       uint32_t nseq, int idbits, int slots_per_group, AccT* __restrict__ K, size_t k_group_stride,
-                       unsigned long long* __restrict__ stat_counters) {
-    extern __shared__ uint32_t row[];
-    __shared__ uint32_t chunk_prefix[MAX_BATCH + 1];
-    __shared__ uint32_t next_chunk;
-    const uint32_t b = nseq - 1 - blockIdx.x;
-    const int group = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    if (threadIdx.x == 0) {
-        uint32_t acc = 0;
-        for (int s = 0; s < slots_per_group; ++s) {
-            chunk_prefix[s] = acc;
-            acc += (row_count[(size_t)(group * slots_per_group + s) * nseq + b] + 31) >> 5;
-        }
-        chunk_prefix[slots_per_group] = acc;
-        next_chunk = 0;
+// masked-off ids (outside the task's range) go to a per-lane dump word behind the row instead of branching
+template <typename IdT>
+__device__ __forceinline__ void apply_unit(uint32_t* row, const uint4 v, const uint32_t msk, const uint32_t dump) {
+    if (sizeof(IdT) == 2) {
+        const uint32_t i0 = (msk & 1u) ? (v.x & 0xffffu) : dump, i1 = (msk & 2u) ? (v.x >> 16) : dump;
+        const uint32_t i2 = (msk & 4u) ? (v.y & 0xffffu) : dump, i3 = (msk & 8u) ? (v.y >> 16) : dump;
+        const uint32_t i4 = (msk & 16u) ? (v.z & 0xffffu) : dump, i5 = (msk & 32u) ? (v.z >> 16) : dump;
+        const uint32_t i6 = (msk & 64u) ? (v.w & 0xffffu) : dump, i7 = (msk & 128u) ? (v.w >> 16) : dump;
+        atomicAdd(&row[i0], 1u); atomicAdd(&row[i1], 1u); atomicAdd(&row[i2], 1u); atomicAdd(&row[i3], 1u);
+        atomicAdd(&row[i4], 1u); atomicAdd(&row[i5], 1u); atomicAdd(&row[i6], 1u); atomicAdd(&row[i7], 1u);
+    } else {
+        const uint32_t i0 = (msk & 1u) ? v.x : dump, i1 = (msk & 2u) ? v.y : dump;
+        const uint32_t i2 = (msk & 4u) ? v.z : dump, i3 = (msk & 8u) ? v.w : dump;
+        atomicAdd(&row[i0], 1u); atomicAdd(&row[i1], 1u); atomicAdd(&row[i2], 1u); atomicAdd(&row[i3], 1u);
     }
-    __syncthreads();
-    const uint32_t nchunks = chunk_prefix[slots_per_group];
-    if (nchunks == 0) return;
+}
+
+// grid = (rows of this wave, groups): CTA x owns row b = row_hi - x; the slots [group * slots_per_group,
+// +slots_per_group) add into the same K.  The host launches the rows in waves of a few CTAs per SM, longest
+// rows first: the CTAs of a wave walk the slots in the same order at the same pace, so the id arrays of only
+// a few slots are live in L2 at any time and every id is fetched from HBM about once per wave, not once per row.
+template <typename AccT, typename IdT, int UNROLL>
+__global__ void __launch_bounds__(1024)
+accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uint2* __restrict__ task,
+                       const uint32_t* __restrict__ woff, uint32_t n, uint32_t row_hi, int slots_per_group,
+                       AccT* __restrict__ K, size_t k_group_stride) {
+    constexpr int PER = 16 / sizeof(IdT);
+    constexpr int SH = PER == 8 ? 3 : 2;
+    extern __shared__ uint32_t row[];
+    __shared__ uint32_t next_chunk;
+    const uint32_t b = row_hi - blockIdx.x;
+    const int group = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const uint32_t wb = woff[b], nw = woff[b + 1] - wb;
+    const uint32_t cps = (nw + 31) >> 5;                     // chunks of 32 tasks per slot
+    const uint32_t nchunks = cps * (uint32_t)slots_per_group;
+    if (threadIdx.x == 0) next_chunk = 0;
     for (uint32_t i = threadIdx.x; i <= b; i += blockDim.x) row[i] = 0;
     __syncthreads();
-    const uint32_t idmask = (1u << idbits) - 1;
-    const uint32_t wb = woff[b];
     const uint32_t lane_le = 0xffffffffu >> (31 - lane);
-    unsigned long long updates = 0;
-    int s = 0;
+    const uint32_t dump = b + 1 + lane;                      // 32 words behind the row
     while (true) {
-        // dynamic chunk scheduling: chunk ids only grow, so a warp's slot cursor only moves forward
         uint32_t c = 0;
         if (lane == 0) c = atomicAdd(&next_chunk, 1u);
         c = __shfl_sync(0xffffffffu, c, 0);
         if (c >= nchunks) break;
-        while (chunk_prefix[s + 1] <= c) ++s;
-        const int slot = group * slots_per_group + s;
-        const uint32_t nt = row_count[(size_t)slot * nseq + b];
-        const uint32_t t = ((c - chunk_prefix[s]) << 5) + lane;
-        const uint32_t* __restrict__ ep = ent_pack + (size_t)slot * n;
+        const uint32_t s = c / cps;
+        const uint32_t t = ((c - s * cps) << 5) + lane;
+        const size_t slot = (size_t)group * slots_per_group + s;
+        const IdT* __restrict__ ip = ids + slot * ids_stride;
         uint2 q = make_uint2(0, 0);
-        uint32_t my_len = 0;
-        if (t < nt) {
-            q = task[(size_t)slot * n + wb + t];
-            my_len = (q.y & idmask) + 1;
-        }
-        const uint32_t my_cb = q.y >> idbits;
-        // load-balanced expansion of the 32 run prefixes over the lanes: P = start of task `lane` in the
-        // concatenation, W = total length.  For a window of 32 positions the tasks starting inside it are a
-        // bit mask (one REDUX); the task owning position i is the number of starts at or before i, minus 1.
-        uint32_t incl = my_len;
+        if (t < nw) q = task[slot * n + wb + t];
+        const uint32_t rs = q.x, end = q.x + q.y;
+        const uint32_t my_units = q.y ? ((end + PER - 1) >> SH) - (rs >> SH) : 0u;
+        uint32_t incl = my_units;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += up;
         }
-        const uint32_t P = incl - my_len;
+        const uint32_t P = incl - my_units;                 // first position of this lane's task in the concatenation
         const uint32_t W = __shfl_sync(0xffffffffu, incl, 31);
-        const uint32_t delta = q.x - P;                       // entry index = delta[j] + position
-        const bool unit = __all_sync(0xffffffffu, my_cb <= 1u);   // every own count is 1: skip one shuffle
-        updates += my_len;
+        const uint32_t u0 = (rs >> SH) - P;                  // unit index = u0[owner] + position
         uint32_t started = 0;
         for (uint32_t base = 0; base < W; base += 32 * UNROLL) {
-            uint32_t a[UNROLL], cb[UNROLL], p[UNROLL];
+            uint4 v[UNROLL];
+            uint32_t msk[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
-                const uint32_t rel = P - (base + 32 * u);
-                const uint32_t m = __reduce_or_sync(0xffffffffu, (rel < 32u && my_len) ? (1u << rel) : 0u);
+                const uint32_t wbase = base + 32 * u;
+                const uint32_t rel = P - wbase;
+                const uint32_t m = __reduce_or_sync(0xffffffffu, (rel < 32u && my_units) ? (1u << rel) : 0u);
                 const uint32_t j = (started + __popc(m & lane_le) - 1) & 31;
                 started += __popc(m);
-                a[u] = __shfl_sync(0xffffffffu, delta, j) + base + 32 * u + lane;
-                cb[u] = unit ? 1u : __shfl_sync(0xffffffffu, my_cb, j);
+                const uint32_t a = (__shfl_sync(0xffffffffu, u0, j) + wbase + lane) << SH;   // first id of the unit
+                const uint32_t trs = __shfl_sync(0xffffffffu, rs, j);
+                const uint32_t tend = __shfl_sync(0xffffffffu, end, j);
+                msk[u] = 0;
+                v[u] = make_uint4(0, 0, 0, 0);
+                if (wbase + lane < W) {
+                    v[u] = ldg_stream_u4(ip + a);
+                    const uint32_t lo = max(trs, a) - a, hi = min(tend, a + PER) - a;
+                    msk[u] = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+                }
             }
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) p[u] = (base + 32 * u + lane < W) ? ep[a[u]] : 0u;
-#pragma unroll
             for (int u = 0; u < UNROLL; ++u)
-                if (base + 32 * u + lane < W) atomicAdd(&row[p[u] & idmask], (p[u] >> idbits) * cb[u]);
+                if (base + 32 * u < W) apply_unit<IdT>(row, v[u], msk[u], dump);   // warp-uniform skip of empty tail windows
         }
     }
     __syncthreads();
     AccT* __restrict__ Krow = K + (size_t)group * k_group_stride + ((size_t)b * (b + 1) >> 1);
     for (uint32_t i = threadIdx.x; i <= b; i += blockDim.x) {
         const uint32_t v = row[i];
-        if (v) Krow[i] += (AccT)v;
+        if (v) atomicAdd(&Krow[i], (AccT)v);                 // RED: no read round trip on the flush
     }
-    if (stat_counters) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) updates += __shfl_xor_sync(0xffffffffu, updates, o);
-        if (lane == 0 && updates) atomicAdd(&stat_counters[2], updates);
+}
+
+// Fallback when a row of K does not fit in shared memory (N > ~56 000): the same tasks, added with global
+// RED on the packed triangle.  One warp per task; tasks live at their row's window range, so the window ->
+// sequence table gives the row.
+template <typename AccT, typename IdT>
+__global__ void __launch_bounds__(256)
+accumulate_global_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uint2* __restrict__ task,
+                         const uint32_t* __restrict__ wseq, uint32_t n, AccT* __restrict__ K, size_t k_slot_stride) {
+    const int slot = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const uint32_t t0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 32;
+    const IdT* __restrict__ ip = ids + (size_t)slot * ids_stride;
+    AccT* __restrict__ Ks = K + (size_t)slot * k_slot_stride;
+    for (uint32_t t = t0; t < min(t0 + 32u, n); ++t) {
+        const uint2 q = task[(size_t)slot * n + t];
+        const size_t b = wseq[t];
+        AccT* __restrict__ Krow = Ks + (b * (b + 1) >> 1);
+        for (uint32_t a = lane; a < q.y; a += 32) atomicAdd(&Krow[ip[q.x + a]], (AccT)1);
     }
 }
 

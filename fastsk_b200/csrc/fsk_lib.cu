@@ -44,6 +44,7 @@ struct fsk_handle {
     std::vector<int32_t> user_queue;
     int opt_batch = 0;
     int opt_acc_path = 0;            // 0 auto, 1 global RED, 2 row-stationary shared memory
+    int opt_wave = 1;                // accumulate launch = opt_wave x (CTAs resident on the chip) rows
     bool profile = false;
     std::string err;
 
@@ -70,13 +71,15 @@ struct fsk_handle {
     unsigned char* d_zero = nullptr;   // [ghist | tickets | status] cleared once per batch
     size_t zero_bytes = 0;
     uint32_t *d_ghist = nullptr, *d_ticket = nullptr, *d_status = nullptr;
-    uint2 *d_tile_counts = nullptr, *d_tile_offs = nullptr, *d_totals = nullptr;
-    uint32_t *d_ent_seq = nullptr, *d_ent_start = nullptr, *d_ent_run = nullptr, *d_run_start = nullptr;
-    uint32_t *d_woff32 = nullptr, *d_row_count = nullptr, *d_ent_pack = nullptr;
+    uint32_t *d_woff32 = nullptr, *d_fill = nullptr;   // window offsets per sequence; tasks filed so far per (slot, sequence)
+    void* d_ids = nullptr;                             // sequence id of every sorted record (u16 when N <= 65536, else u32)
+    size_t ids_stride = 0;                             // per-slot stride of d_ids, a multiple of 64 elements
+    bool ids16 = false;
     uint2* d_task = nullptr;
     bool rows_path = false;
     int rows_threads = 256;
     size_t rows_smem = 0;
+    int wave_rows = 148;                               // rows per accumulate launch
     int64_t maxwin = 0;
     unsigned long long* d_Kint = nullptr;   // integer partial (exact / skip_variance), or per-slot Ks in variance mode
     int ks_slots = 1;
@@ -142,10 +145,8 @@ void release_device(fsk_handle* h) {
     dev_free(h->d_recA); dev_free(h->d_recB); dev_free(h->d_valA); dev_free(h->d_valB);
     dev_free(h->d_zero);
     h->d_ghist = h->d_ticket = h->d_status = nullptr;
-    dev_free(h->d_tile_counts); dev_free(h->d_tile_offs); dev_free(h->d_totals);
-    dev_free(h->d_ent_seq); dev_free(h->d_ent_start); dev_free(h->d_ent_run); dev_free(h->d_run_start);
-    dev_free(h->d_woff32); dev_free(h->d_ent_pack); dev_free(h->d_task);
-    h->d_row_count = nullptr;
+    dev_free(h->d_woff32); dev_free(h->d_ids); dev_free(h->d_task);
+    h->d_fill = nullptr;
     dev_free(h->d_Kint); dev_free(h->d_Kf);
     for (auto& p : h->d_Khat) dev_free(p);
     h->d_Khat.clear();
@@ -260,7 +261,7 @@ int launch_sort(fsk_handle* h, int nb) {
         const int shift = (KV ? 0 : h->idbits) + h->plan.shift[p];
         uint32_t* status = h->d_status + (size_t)p * h->B * h->sort_tiles * RADIX;
         onesweep_kernel<RecT, KV, ITEMS><<<h->sort_tiles * nb, SORT_THREADS, smem, h->stream>>>(
-            (const RecT*)h->d_recA, (RecT*)h->d_recB, h->d_valA, h->d_valB, n, h->sort_tiles, shift, h->plan.bits[p],
+            (const RecT*)h->d_recA, (RecT*)h->d_recB, h->d_valA, h->d_valB, n, h->sort_tiles, (uint32_t)nb, shift, h->plan.bits[p],
             h->d_ghist + (size_t)p * RADIX, status, h->d_ticket + p);
         h->launches++;
         CU(cudaGetLastError());
@@ -274,14 +275,39 @@ template <typename RecT, bool KV>
 int launch_segment(fsk_handle* h, int nb) {
     const uint32_t n = (uint32_t)h->nfeat;
     dim3 grid(h->seg_tiles, nb);
-    seg_count_kernel<RecT, KV><<<grid, SEG_THREADS, 0, h->stream>>>((const RecT*)h->d_recA, h->d_valA, n, h->idbits, h->seg_tiles,
-                                                                  h->d_tile_counts);
-    seg_scan_kernel<<<nb, 1024, 0, h->stream>>>(h->d_tile_counts, h->d_tile_offs, h->seg_tiles, h->d_totals, h->d_ent_start, n,
-                                              h->profile ? h->d_counters : nullptr);
-    seg_write_kernel<RecT, KV><<<grid, SEG_THREADS, 0, h->stream>>>((const RecT*)h->d_recA, h->d_valA, n, h->idbits, h->seg_tiles,
-                                                                  h->d_tile_offs, h->d_ent_seq, h->d_ent_start, h->d_ent_run,
-                                                                  h->d_run_start);
-    h->launches += 3;
+    unsigned long long* stat = h->profile ? h->d_counters : nullptr;
+    if (h->ids16)
+        segment_kernel<RecT, KV, uint16_t><<<grid, SEG_THREADS, 0, h->stream>>>((const RecT*)h->d_recA, h->d_valA, n, h->ids_stride, h->idbits,
+                                                                                (uint32_t)h->N, h->d_woff32, h->d_fill, (uint16_t*)h->d_ids,
+                                                                                h->d_task, stat);
+    else
+        segment_kernel<RecT, KV, uint32_t><<<grid, SEG_THREADS, 0, h->stream>>>((const RecT*)h->d_recA, h->d_valA, n, h->ids_stride, h->idbits,
+                                                                                (uint32_t)h->N, h->d_woff32, h->d_fill, (uint32_t*)h->d_ids,
+                                                                                h->d_task, stat);
+    h->launches++;
+    CU(cudaGetLastError());
+    return FSK_OK;
+}
+
+template <typename IdT>
+int launch_accumulate(fsk_handle* h, int nb, unsigned long long* K, size_t slot_stride) {
+    const uint32_t n = (uint32_t)h->nfeat;
+    const IdT* ids = (const IdT*)h->d_ids;
+    if (h->rows_path) {
+        // slot_stride != 0 (variance mode): every slot adds into its own K; else all slots add into one K
+        const int groups = slot_stride ? nb : 1, per_group = slot_stride ? 1 : nb;
+        const int wave = std::max(1, h->wave_rows / groups);
+        for (int64_t hi = h->N - 1; hi >= 0; hi -= wave) {
+            dim3 grid((unsigned)std::min<int64_t>(wave, hi + 1), groups);
+            accumulate_rows_kernel<unsigned long long, IdT, 4><<<grid, h->rows_threads, h->rows_smem, h->stream>>>(
+                ids, h->ids_stride, h->d_task, h->d_woff32, n, (uint32_t)hi, per_group, K, slot_stride);
+            h->launches++;
+        }
+    } else {
+        dim3 grid((unsigned)((h->nfeat + 255) / 256), nb);
+        accumulate_global_kernel<unsigned long long, IdT><<<grid, 256, 0, h->stream>>>(ids, h->ids_stride, h->d_task, h->d_wseq, n, K, slot_stride);
+        h->launches++;
+    }
     CU(cudaGetLastError());
     return FSK_OK;
 }
@@ -321,25 +347,8 @@ int run_batch(fsk_handle* h, const int32_t* combos, int nb, unsigned long long* 
     }
     {
         Span sp(h, PC_ACCUMULATE);
-        const uint32_t n = (uint32_t)h->nfeat;
-        if (h->rows_path) {
-            dim3 gfin((unsigned)((h->nfeat + 255) / 256), nb);
-            seg_finish_kernel<<<gfin, 256, 0, h->stream>>>(h->d_ent_seq, h->d_ent_start, h->d_ent_run, h->d_run_start, h->d_totals, n,
-                                                        (uint32_t)h->N, h->idbits, h->d_woff32, h->d_row_count, h->d_ent_pack, h->d_task);
-            const int groups = slot_stride ? nb : 1, per_group = slot_stride ? 1 : nb;
-            dim3 grid((unsigned)h->N, groups);
-            accumulate_rows_kernel<unsigned long long, 4><<<grid, h->rows_threads, h->rows_smem, h->stream>>>(
-                h->d_ent_pack, h->d_task, h->d_row_count, h->d_woff32, n, (uint32_t)h->N, h->idbits, per_group, K, slot_stride,
-                h->profile ? h->d_counters : nullptr);
-            h->launches += 2;
-        } else {
-            dim3 grid((unsigned)((h->nfeat + ACC_ROWS - 1) / ACC_ROWS), nb);
-            accumulate_kernel<unsigned long long><<<grid, 256, 0, h->stream>>>(h->d_ent_seq, h->d_ent_start, h->d_ent_run, h->d_run_start,
-                                                                             h->d_totals, n, K, slot_stride,
-                                                                             h->profile ? h->d_counters : nullptr);
-            h->launches++;
-        }
-        CU(cudaGetLastError());
+        rc = h->ids16 ? launch_accumulate<uint16_t>(h, nb, K, slot_stride) : launch_accumulate<uint32_t>(h, nb, K, slot_stride);
+        if (rc) return rc;
     }
     h->combos_done += nb;
     if (h->spans.size() > 2048) resolve_spans(h);
@@ -467,6 +476,9 @@ int fsk_set_option(fsk_handle* h, const char* key, int64_t value) {
     } else if (!strcmp(key, "acc_path")) {
         if (value < 0 || value > 2) return fail(h, FSK_EINVAL, "acc_path must be 0 (auto), 1 (global RED) or 2 (shared-memory rows)");
         h->opt_acc_path = (int)value;
+    } else if (!strcmp(key, "wave")) {
+        if (value < 1 || value > 1024) return fail(h, FSK_EINVAL, "wave must be in [1, 1024]");
+        h->opt_wave = (int)value;
     } else if (!strcmp(key, "profile")) {
         h->profile = value != 0;
     } else {
@@ -558,22 +570,31 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     h->variance_mode = h->approx && !h->skip_variance;
 
     h->maxwin = maxwin;
-    // accumulate path: rows of K in shared memory (4 B per column, one CTA per row) whenever a row fits
-    // and (sequence id, count) pack into 32 bits; otherwise global RED on the packed triangle
-    int max_smem = 0;
+    // accumulate path: rows of K in shared memory (4 B per column, one CTA per row) whenever a row fits;
+    // otherwise global RED on the packed triangle
+    int max_smem = 0, n_sm = 148;
     CU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-    const bool rows_ok = (size_t)N * 4 + 1024 <= (size_t)max_smem && h->idbits + ceil_log2(maxwin + 1) <= 32 &&
-                         (double)maxwin * (double)maxwin < 4294967296.0;
-    if (h->opt_acc_path == 2 && !rows_ok) return fail(h, FSK_EINVAL, "acc_path = 2 needs N * 4 B <= %d B of shared memory and id + count bits <= 32", max_smem);
+    CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device));
+    const bool rows_ok = (size_t)N * 4 + 128 + 1024 <= (size_t)max_smem && (double)maxwin * (double)maxwin < 4294967296.0;
+    if (h->opt_acc_path == 2 && !rows_ok) return fail(h, FSK_EINVAL, "acc_path = 2 needs N * 4 B <= %d B of shared memory", max_smem);
     h->rows_path = h->opt_acc_path == 2 || (h->opt_acc_path == 0 && rows_ok);
-    h->rows_smem = (size_t)N * 4;
+    h->rows_smem = (size_t)N * 4 + 128;   // + one dump word per lane for masked-off ids
     h->rows_threads = N >= 16384 ? 1024 : (N >= 4096 ? 512 : 256);
-    if (h->rows_path)
-        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
+    h->ids16 = N <= 65536;
+    h->ids_stride = (size_t)((nfeat + 8 + 63) / 64 * 64);
+    {
+        // rows per accumulate launch: the CTAs resident at once, times opt_wave (default 1)
+        const int per_sm = std::max(1, std::min(2048 / h->rows_threads, (int)((size_t)(max_smem + 1024) / (h->rows_smem + 1024))));
+        h->wave_rows = n_sm * per_sm * std::max(1, h->opt_wave);
+    }
+    if (h->rows_path) {
+        if (h->ids16) CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
+        else CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
+    }
 
     // batch: combinations per launch group.  The row path flushes every row of K once per batch, so it
     // wants the batch as large as memory allows; the u32 shared-memory accumulators bound it by 2^32 / maxwin^2.
-    const int64_t per_slot_bytes = nfeat * (2 * (h->mode == MODE_R32 ? 4 : 8) + (h->mode == MODE_KV ? 8 : 0) + 16 + (h->rows_path ? 12 : 0)) +
+    const int64_t per_slot_bytes = nfeat * (2 * (h->mode == MODE_R32 ? 4 : 8) + (h->mode == MODE_KV ? 8 : 0) + 8 + (h->ids16 ? 2 : 4)) +
                                    (int64_t)h->plan.npass * ((nfeat + 3071) / 3072) * RADIX * 4 + N * 4 + 4096;
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
@@ -632,24 +653,17 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     if (h->mode == MODE_KV) { ALLOC(h->d_valA, bn); ALLOC(h->d_valB, bn); }
     const int B = h->B;
     const size_t ghist_words = (size_t)B * MAX_PASS * RADIX, ticket_words = 64;
-    const size_t rowcount_words = h->rows_path ? (size_t)B * (size_t)N : 0;
+    const size_t rowcount_words = (size_t)B * (size_t)N;
     const size_t status_words = (size_t)h->plan.npass * B * h->sort_tiles * RADIX;
     h->zero_bytes = 4 * (ghist_words + ticket_words + status_words + rowcount_words);
     ALLOC(h->d_zero, h->zero_bytes);
     h->d_ghist = (uint32_t*)h->d_zero;
     h->d_ticket = h->d_ghist + ghist_words;
     h->d_status = h->d_ticket + ticket_words;
-    h->d_row_count = h->d_status + status_words;
-    ALLOC(h->d_tile_counts, (size_t)B * h->seg_tiles);
-    ALLOC(h->d_tile_offs, (size_t)B * h->seg_tiles);
-    ALLOC(h->d_totals, B);
-    ALLOC(h->d_ent_seq, bn);
-    ALLOC(h->d_ent_start, bn + B);
-    ALLOC(h->d_ent_run, bn);
-    ALLOC(h->d_run_start, bn);
-    if (h->rows_path) {
-        ALLOC(h->d_ent_pack, bn);
-        ALLOC(h->d_task, bn);
+    h->d_fill = h->d_status + status_words;
+    { unsigned char* p; ALLOC(p, (size_t)B * h->ids_stride * (h->ids16 ? 2 : 4)); h->d_ids = p; }
+    ALLOC(h->d_task, bn);
+    {
         std::vector<uint32_t> w32((size_t)N + 1);
         for (int64_t i = 0; i <= N; ++i) w32[(size_t)i] = (uint32_t)woff[(size_t)i];
         ALLOC(h->d_woff32, N + 1);

@@ -22,6 +22,7 @@ ap.add_argument("--m", type=int, default=8)
 ap.add_argument("--alphabet", type=int, default=4)
 ap.add_argument("--acc-path", type=int, default=0)
 ap.add_argument("--reps", type=int, default=1)
+ap.add_argument("--wave", type=int, default=1)
 a = ap.parse_args()
 
 X = np.random.default_rng(0).integers(1, a.alphabet + 1, size=(a.n, a.len), dtype=np.int32)
@@ -29,6 +30,7 @@ order = np.random.default_rng(0).permutation(comb(a.g, a.m)).astype(np.int32)
 f = FastSK(a.g, a.m, combo_sequence=order, distributed=False, profile=True)
 f.set_option("batch", a.batch)
 f.set_option("acc_path", a.acc_path)
+f.set_option("wave", a.wave)
 codes = np.ascontiguousarray(X.reshape(-1))
 offsets = np.arange(a.n + 1, dtype=np.int64) * a.len
 f._call("fsk_upload", codes.ctypes.data_as(_lib.c_i32p), offsets.ctypes.data_as(_lib.c_i64p), int(a.n * 0.8), a.n - int(a.n * 0.8))
