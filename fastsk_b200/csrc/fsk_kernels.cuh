@@ -15,6 +15,7 @@
 // (fastsk_kernel.cpp:108-143).
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 namespace fsk {
@@ -26,8 +27,12 @@ constexpr int RADIX = 256;
 constexpr int SORT_THREADS = 256;
 constexpr int PACK_ITEMS = 8;
 
+// The kept characters of a combination, as maximal stretches of consecutive kept positions inside one g-mer
+// word: seg = source bit position (word * 64 + shift) | (width in bits - 1) << 7.  The stretches are laid into
+// the key from bit 0 upwards; any injective packing gives the same runs (only equality of k-mers matters).
 struct BatchSpec {               // by value in kernel parameter space
-    uint8_t src[MAX_BATCH][MAX_K];   // bit position (word * 64 + shift) of each kept character
+    uint16_t seg[MAX_BATCH][MAX_K];
+    uint8_t nseg[MAX_BATCH];
 };
 struct SortPlan {
     int npass;
@@ -102,13 +107,15 @@ template <typename RecT, bool KV, typename GwT, int NW>
 __global__ void __launch_bounds__(256)
 pack_hist_kernel(const GwT* __restrict__ gw0, const uint64_t* __restrict__ gw1, const uint32_t* __restrict__ wseq,
                  uint32_t nfeat, RecT* __restrict__ rec, uint32_t* __restrict__ val, uint32_t* __restrict__ ghist,
-                 const __grid_constant__ BatchSpec spec, const __grid_constant__ SortPlan plan, int k, int b, int idbits) {
+                 const __grid_constant__ BatchSpec spec, const __grid_constant__ SortPlan plan, int idbits) {
+    // a 32-bit g-mer word holds a key of at most 32 bits: keep the arithmetic in 32 bits then
+    using KeyT = typename std::conditional<sizeof(GwT) == 4, uint32_t, uint64_t>::type;
     __shared__ uint32_t sh[MAX_PASS * RADIX];
     const int slot = blockIdx.y;
+    const int nseg = spec.nseg[slot];
     const int npass = plan.npass;
     for (int i = threadIdx.x; i < npass * RADIX; i += blockDim.x) sh[i] = 0;
     __syncthreads();
-    const uint64_t cmask = (1ull << b) - 1;
     const size_t sbase = (size_t)slot * nfeat;
     const uint32_t tile0 = blockIdx.x * (256 * PACK_ITEMS);
 #pragma unroll 2
@@ -118,18 +125,25 @@ pack_hist_kernel(const GwT* __restrict__ gw0, const uint64_t* __restrict__ gw1, 
             const uint64_t lo = gw0[w];
             uint64_t hi = 0;
             if (NW == 2) hi = gw1[w];
-            uint64_t key = 0;
-            for (int j = 0; j < k; ++j) {
-                const uint32_t sp = spec.src[slot][j];
-                const uint64_t word = (NW == 2 && (sp & 64)) ? hi : lo;
-                key = (key << b) | ((word >> (sp & 63)) & cmask);
+            KeyT key = 0;
+            int dst = 0;
+            for (int j = 0; j < nseg; ++j) {
+                const uint32_t e = spec.seg[slot][j];
+                const int width = (int)(e >> 7) + 1;
+                if (NW == 2) {
+                    const uint64_t word = (e & 64u) ? hi : lo;
+                    key |= (KeyT)((word >> (e & 63u)) & (~0ull >> (64 - width))) << dst;
+                } else {
+                    key |= (KeyT)(((KeyT)lo >> (e & 63u)) & ((KeyT)~(KeyT)0 >> ((int)sizeof(KeyT) * 8 - width))) << dst;
+                }
+                dst += width;
             }
             const uint32_t seq = wseq[w];
             if (KV) {
                 rec[sbase + w] = (RecT)key;
                 val[sbase + w] = seq;
             } else {
-                rec[sbase + w] = (RecT)((key << idbits) | seq);
+                rec[sbase + w] = ((RecT)key << idbits) | (RecT)seq;
             }
             for (int p = 0; p < npass; ++p) {
                 const uint32_t d = (uint32_t)(key >> plan.shift[p]) & ((1u << plan.bits[p]) - 1);
@@ -163,11 +177,12 @@ onesweep_kernel(const RecT* __restrict__ in, RecT* __restrict__ out, const uint3
     uint32_t* digit_start = warp_hist + 8 * RADIX;    // [RADIX]
     uint32_t* scatter_base = digit_start + RADIX;     // [RADIX]
     uint32_t* warp_sums = scatter_base + RADIX;       // [8]
+    uint32_t* match_mask = warp_sums + 8;             // [8][RADIX]
     __shared__ uint32_t s_ticket;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
-    for (int i = tid; i < 8 * RADIX; i += SORT_THREADS) warp_hist[i] = 0;
+    for (int i = tid; i < 8 * RADIX; i += SORT_THREADS) { warp_hist[i] = 0; match_mask[i] = 0; }
     __syncthreads();
     // tickets deal the slots round-robin: the tiles in flight at any time are spread over all slots of the batch, so a
     // tile's look-back crosses only the few running tiles of its own slot (not every resident CTA of the chip)
@@ -190,17 +205,24 @@ onesweep_kernel(const RecT* __restrict__ in, RecT* __restrict__ out, const uint3
             if (KV) val[j] = vin[sbase + idx];
         }
     }
+    // Lanes holding the same digit find each other through a per-warp match mask in shared memory (atomicOr of
+    // the lane bit, read back, cleared by the lowest lane): measured 2.8x faster than match.any, whose MATCH
+    // instruction saturates the ADU pipe (tools/rank_bench.cu, profiles/r01_rank_microbench.txt).
+    const uint32_t lane_lt = (1u << lane) - 1u;
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         const uint32_t idx = tile0 + warp * (32 * ITEMS) + j * 32 + lane;
         const bool valid = idx < n;
-        const uint32_t d = valid ? ((uint32_t)(key[j] >> shift) & dmask) : (0x80000000u | lane);
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        const uint32_t lower = peers & ((1u << lane) - 1);
-        uint32_t prev = 0;
-        if (valid) prev = warp_hist[warp * RADIX + d];
+        const uint32_t d = (uint32_t)(key[j] >> shift) & dmask;
+        uint32_t* mm = match_mask + warp * RADIX + d;
+        uint32_t* wh = warp_hist + warp * RADIX + d;
+        if (valid) atomicOr(mm, 1u << lane);
         __syncwarp();
-        if (valid && lower == 0) warp_hist[warp * RADIX + d] = prev + __popc(peers);
+        uint32_t peers = 0, prev = 0;
+        if (valid) { peers = *mm; prev = *wh; }
+        __syncwarp();
+        const uint32_t lower = peers & lane_lt;
+        if (valid && lower == 0) { *wh = prev + __popc(peers); *mm = 0; }
         __syncwarp();
         rank[j] = prev + __popc(lower);
     }
@@ -296,7 +318,7 @@ struct RecOps {
 };
 
 template <typename RecT, bool KV, typename IdT>
-__global__ void __launch_bounds__(SEG_THREADS)
+__global__ void __launch_bounds__(SEG_THREADS, (sizeof(RecT) == 4 ? 4 : 2))
 segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, uint32_t n, size_t ids_stride, int idbits,
                uint32_t nseq, const uint32_t* __restrict__ woff, uint32_t* __restrict__ fill, IdT* __restrict__ ids,
                uint2* __restrict__ task, unsigned long long* __restrict__ stat_counters) {

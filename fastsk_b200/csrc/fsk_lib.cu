@@ -236,13 +236,13 @@ int launch_pack(fsk_handle* h, int nb, const BatchSpec& spec) {
     const uint32_t n = (uint32_t)h->nfeat;
     if (h->NW == 2)
         pack_hist_kernel<RecT, KV, uint64_t, 2><<<grid, 256, 0, h->stream>>>((const uint64_t*)h->d_gw0, h->d_gw1, h->d_wseq, n, rec,
-                                                                           h->d_valA, h->d_ghist, spec, h->plan, h->k, h->b, h->idbits);
+                                                                           h->d_valA, h->d_ghist, spec, h->plan, h->idbits);
     else if (h->gw32)
         pack_hist_kernel<RecT, KV, uint32_t, 1><<<grid, 256, 0, h->stream>>>((const uint32_t*)h->d_gw0, nullptr, h->d_wseq, n, rec,
-                                                                           h->d_valA, h->d_ghist, spec, h->plan, h->k, h->b, h->idbits);
+                                                                           h->d_valA, h->d_ghist, spec, h->plan, h->idbits);
     else
         pack_hist_kernel<RecT, KV, uint64_t, 1><<<grid, 256, 0, h->stream>>>((const uint64_t*)h->d_gw0, nullptr, h->d_wseq, n, rec,
-                                                                           h->d_valA, h->d_ghist, spec, h->plan, h->k, h->b, h->idbits);
+                                                                           h->d_valA, h->d_ghist, spec, h->plan, h->idbits);
     h->launches++;
     CU(cudaGetLastError());
     return FSK_OK;
@@ -250,13 +250,15 @@ int launch_pack(fsk_handle* h, int nb, const BatchSpec& spec) {
 
 template <typename RecT, bool KV, int ITEMS>
 size_t sort_smem() {
-    return sizeof(RecT) * SORT_THREADS * ITEMS + (KV ? 4 * SORT_THREADS * ITEMS : 0) + 4 * (8 * RADIX + 2 * RADIX + 8);
+    return sizeof(RecT) * SORT_THREADS * ITEMS + (KV ? 4 * SORT_THREADS * ITEMS : 0) + 4 * (8 * RADIX + 2 * RADIX + 8 + 8 * RADIX);
 }
 
 template <typename RecT, bool KV, int ITEMS>
 int launch_sort(fsk_handle* h, int nb) {
     const uint32_t n = (uint32_t)h->nfeat;
     const size_t smem = sort_smem<RecT, KV, ITEMS>();
+    // opt in to more than 48 KB of dynamic shared memory (per device, so not cached across handles)
+    CU(cudaFuncSetAttribute(onesweep_kernel<RecT, KV, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int p = 0; p < h->plan.npass; ++p) {
         const int shift = (KV ? 0 : h->idbits) + h->plan.shift[p];
         uint32_t* status = h->d_status + (size_t)p * h->B * h->sort_tiles * RADIX;
@@ -320,7 +322,15 @@ int run_batch(fsk_handle* h, const int32_t* combos, int nb, unsigned long long* 
     for (int s = 0; s < nb; ++s) {
         if (combos[s] < 0 || combos[s] >= h->ncomb) return fail(h, FSK_EINVAL, "combination index %d out of range [0, %lld)", combos[s], (long long)h->ncomb);
         unrank_combination(h->g, h->k, combos[s], pos);
-        for (int j = 0; j < h->k; ++j) spec.src[s][j] = (uint8_t)((pos[j] / h->cpw) * 64 + (pos[j] % h->cpw) * h->b);
+        int nseg = 0;
+        for (int j = 0; j < h->k;) {   // maximal stretch of consecutive kept positions inside one g-mer word
+            int e = j + 1;
+            while (e < h->k && pos[e] == pos[e - 1] + 1 && pos[e] / h->cpw == pos[j] / h->cpw) ++e;
+            const int src = (pos[j] / h->cpw) * 64 + (pos[j] % h->cpw) * h->b, width = (e - j) * h->b;
+            spec.seg[s][nseg++] = (uint16_t)(src | (width - 1) << 7);
+            j = e;
+        }
+        spec.nseg[s] = (uint8_t)nseg;
     }
     CU(cudaMemsetAsync(h->d_zero, 0, h->zero_bytes, h->stream));
     int rc;
