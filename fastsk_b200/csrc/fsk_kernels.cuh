@@ -163,7 +163,7 @@ pack_hist_kernel(const GwT* __restrict__ gw0, const uint64_t* __restrict__ gw1, 
 // the look-back).  Stable: keys keep their input order within a digit, so sequence ids stay
 // ascending inside every run of equal k-mers (the property countAndUpdateTri relies on).
 // status word = flag (2 bits: 1 = tile aggregate, 2 = inclusive prefix) | count (30 bits).
-template <typename RecT, bool KV, int ITEMS>
+template <typename RecT, bool KV, int ITEMS, bool OPTIMISTIC>
 __global__ void __launch_bounds__(SORT_THREADS)
 onesweep_kernel(const RecT* __restrict__ in, RecT* __restrict__ out, const uint32_t* __restrict__ vin,
                 uint32_t* __restrict__ vout, uint32_t n, uint32_t tiles_per_slot, uint32_t nslots, int shift, int bits,
@@ -182,7 +182,7 @@ onesweep_kernel(const RecT* __restrict__ in, RecT* __restrict__ out, const uint3
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
-    for (int i = tid; i < 8 * RADIX; i += SORT_THREADS) { warp_hist[i] = 0; match_mask[i] = 0; }
+    for (int i = tid; i < 8 * RADIX; i += SORT_THREADS) { warp_hist[i] = 0; if (!OPTIMISTIC) match_mask[i] = 0; }
     __syncthreads();
     // tickets deal the slots round-robin: the tiles in flight at any time are spread over all slots of the batch, so a
     // tile's look-back crosses only the few running tiles of its own slot (not every resident CTA of the chip)
@@ -205,26 +205,35 @@ onesweep_kernel(const RecT* __restrict__ in, RecT* __restrict__ out, const uint3
             if (KV) val[j] = vin[sbase + idx];
         }
     }
-    // Lanes holding the same digit find each other through a per-warp match mask in shared memory (atomicOr of
-    // the lane bit, read back, cleared by the lowest lane): measured 2.8x faster than match.any, whose MATCH
-    // instruction saturates the ADU pipe (tools/rank_bench.cu, profiles/r01_rank_microbench.txt).
+    // In-warp stable ranking of the digits.
+    //   OPTIMISTIC: one shared-memory atomicAdd with return per key.  Lanes of one instruction that hit the same counter
+    //   are served in lane order on this hardware (tools/rank_bench.cu: 0 mismatches in 74 M keys, 1.75x faster than the
+    //   next best) but nothing documents that, so segment_kernel verifies that the final records are non-decreasing -- which,
+    //   the scatter being a permutation, holds iff every pass was stable -- and the host repeats the build with the safe
+    //   ranking if the check ever fails.
+    //   safe: lanes holding the same digit find each other through a per-warp match mask (atomicOr of the lane bit, read
+    //   back, cleared by the lowest lane); 2.8x faster than match.any, whose MATCH instruction saturates the ADU pipe.
     const uint32_t lane_lt = (1u << lane) - 1u;
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         const uint32_t idx = tile0 + warp * (32 * ITEMS) + j * 32 + lane;
         const bool valid = idx < n;
         const uint32_t d = (uint32_t)(key[j] >> shift) & dmask;
-        uint32_t* mm = match_mask + warp * RADIX + d;
         uint32_t* wh = warp_hist + warp * RADIX + d;
-        if (valid) atomicOr(mm, 1u << lane);
-        __syncwarp();
-        uint32_t peers = 0, prev = 0;
-        if (valid) { peers = *mm; prev = *wh; }
-        __syncwarp();
-        const uint32_t lower = peers & lane_lt;
-        if (valid && lower == 0) { *wh = prev + __popc(peers); *mm = 0; }
-        __syncwarp();
-        rank[j] = prev + __popc(lower);
+        if (OPTIMISTIC) {
+            rank[j] = valid ? atomicAdd(wh, 1u) : 0u;
+        } else {
+            uint32_t* mm = match_mask + warp * RADIX + d;
+            if (valid) atomicOr(mm, 1u << lane);
+            __syncwarp();
+            uint32_t peers = 0, prev = 0;
+            if (valid) { peers = *mm; prev = *wh; }
+            __syncwarp();
+            const uint32_t lower = peers & lane_lt;
+            if (valid && lower == 0) { *wh = prev + __popc(peers); *mm = 0; }
+            __syncwarp();
+            rank[j] = prev + __popc(lower);
+        }
     }
     __syncthreads();
 
@@ -318,10 +327,10 @@ struct RecOps {
 };
 
 template <typename RecT, bool KV, typename IdT>
-__global__ void __launch_bounds__(SEG_THREADS, (sizeof(RecT) == 4 ? 4 : 2))
+__global__ void __launch_bounds__(SEG_THREADS, (sizeof(RecT) == 4 ? 3 : 2))
 segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, uint32_t n, size_t ids_stride, int idbits,
                uint32_t nseq, const uint32_t* __restrict__ woff, uint32_t* __restrict__ fill, IdT* __restrict__ ids,
-               uint2* __restrict__ task, unsigned long long* __restrict__ stat_counters) {
+               uint2* __restrict__ task, uint32_t* __restrict__ unsorted_flag, unsigned long long* __restrict__ stat_counters) {
     using Ops = RecOps<RecT, KV>;
     const int slot = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -371,6 +380,8 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
         const bool head = valid && (i == 0 || !Ops::same_key(pr, r[k], idbits));
         const bool ghead = valid && (i == 0 || pr != r[k] || (KV && ps != sq[k]));
         const bool tail = valid && (i + 1 >= n || nr != r[k] || (KV && ns != sq[k]));
+        // the sort must have left the records non-decreasing (key, then sequence id): see onesweep_kernel
+        if (valid && i > 0 && (KV ? (pr > r[k] || (pr == r[k] && ps > sq[k])) : pr > r[k])) *unsorted_flag = 1u;
         hm[k] = __ballot_sync(0xffffffffu, head);
         tm[k] = __ballot_sync(0xffffffffu, tail);
         n_groups += __popc(__ballot_sync(0xffffffffu, ghead));
@@ -417,28 +428,55 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
             if (tm[k]) next_tail = base + (__ffs(tm[k]) - 1);
         }
     }
+    // run start and prefix length of every record; a group that runs past the warp's segment is followed in
+    // global memory (rare)
     unsigned long long updates = 0;
-    uint32_t last_head = carry_head;
-    const uint32_t lane_le = 0xffffffffu >> (31 - lane);
+    uint32_t rs[SEG_ROWS], len[SEG_ROWS];
+    {
+        uint32_t last_head = carry_head;
+        const uint32_t lane_le = 0xffffffffu >> (31 - lane);
 #pragma unroll
-    for (int k = 0; k < SEG_ROWS; ++k) {
-        const uint32_t base = seg0 + k * 32;
-        const uint32_t i = base + lane;
-        const uint32_t m = hm[k] & lane_le;
-        const uint32_t rs = m ? base + (31 - __clz(m)) : last_head;
-        if (hm[k]) last_head = base + (31 - __clz(hm[k]));
-        if (i < n) {
-            uint32_t g = ge[k];
-            if (g == 0xffffffffu) {          // the group runs past the warp's segment (rare): follow it
-                g = seg_end - 1;
-                while (g + 1 < n && R[g + 1] == r[k] && (!KV || V[g + 1] == sq[k])) ++g;
+        for (int k = 0; k < SEG_ROWS; ++k) {
+            const uint32_t base = seg0 + k * 32;
+            const uint32_t m = hm[k] & lane_le;
+            rs[k] = m ? base + (31 - __clz(m)) : last_head;
+            if (hm[k]) last_head = base + (31 - __clz(hm[k]));
+            len[k] = ge[k] - rs[k] + 1;           // garbage where ge is unknown or the record is out of range: fixed below
+        }
+        if (__any_sync(0xffffffffu, ge[SEG_ROWS - 1] == 0xffffffffu && seg0 + (SEG_ROWS - 1) * 32 + lane < n)) {
+#pragma unroll
+            for (int k = 0; k < SEG_ROWS; ++k) {
+                const uint32_t i = seg0 + k * 32 + lane;
+                if (i < n && ge[k] == 0xffffffffu) {
+                    uint32_t g = seg_end - 1;
+                    while (g + 1 < n && R[g + 1] == r[k] && (!KV || V[g + 1] == sq[k])) ++g;
+                    len[k] = g - rs[k] + 1;
+                }
             }
-            const uint32_t len = g - rs + 1;
-            const uint32_t b = sq[k];
-            ids[(size_t)slot * ids_stride + i] = (IdT)b;
-            const uint32_t pos = atomicAdd(&fill[(size_t)slot * nseq + b], 1u);
-            task[sbase + woff[b] + pos] = make_uint2(rs, len);
-            updates += len;
+        }
+    }
+    // file the tasks: all the atomics of half the rows in flight before the first dependent store
+    constexpr int HALF = SEG_ROWS / 2;
+#pragma unroll
+    for (int h0 = 0; h0 < SEG_ROWS; h0 += HALF) {
+        uint32_t pos[HALF], wo[HALF];
+#pragma unroll
+        for (int k = 0; k < HALF; ++k) {
+            const uint32_t i = seg0 + (h0 + k) * 32 + lane;
+            pos[k] = wo[k] = 0;
+            if (i < n) {
+                pos[k] = atomicAdd(&fill[(size_t)slot * nseq + sq[h0 + k]], 1u);
+                wo[k] = woff[sq[h0 + k]];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < HALF; ++k) {
+            const uint32_t i = seg0 + (h0 + k) * 32 + lane;
+            if (i < n) {
+                ids[(size_t)slot * ids_stride + i] = (IdT)sq[h0 + k];
+                task[sbase + wo[k] + pos[k]] = make_uint2(rs[h0 + k], len[h0 + k]);
+                updates += len[h0 + k];
+            }
         }
     }
     if (stat_counters) {

@@ -44,6 +44,7 @@ struct fsk_handle {
     std::vector<int32_t> user_queue;
     int opt_batch = 0;
     int opt_acc_path = 0;            // 0 auto, 1 global RED, 2 row-stationary shared memory
+    bool safe_rank = false;          // onesweep ranking: false = one atomic per key, verified afterwards; true = match masks
     int opt_wave = 1;                // accumulate launch = opt_wave x (CTAs resident on the chip) rows
     bool profile = false;
     std::string err;
@@ -88,12 +89,14 @@ struct fsk_handle {
     double *d_diag = nullptr, *d_train = nullptr, *d_test = nullptr;
     double *d_block_sums = nullptr, *d_var = nullptr;
     unsigned long long* d_counters = nullptr;   // entries, runs, pair updates
+    uint32_t* d_flag = nullptr;                 // set by segment_kernel when a sorted batch is not non-decreasing
 
     std::vector<int32_t> queue;
     std::vector<double> stdevs;
 
     // statistics
     int64_t combos_done = 0, launches = 0;
+    int rank_fallbacks = 0;
     double ms[PC_COUNT] = {0, 0, 0, 0, 0, 0};
     std::vector<ProfSpan> spans;
     std::vector<cudaEvent_t> event_pool;
@@ -151,7 +154,7 @@ void release_device(fsk_handle* h) {
     for (auto& p : h->d_Khat) dev_free(p);
     h->d_Khat.clear();
     dev_free(h->d_diag); dev_free(h->d_train); dev_free(h->d_test);
-    dev_free(h->d_block_sums); dev_free(h->d_var); dev_free(h->d_counters);
+    dev_free(h->d_block_sums); dev_free(h->d_var); dev_free(h->d_counters); dev_free(h->d_flag);
     for (auto& s : h->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     h->spans.clear();
     for (auto e : h->event_pool) cudaEventDestroy(e);
@@ -258,11 +261,12 @@ int launch_sort(fsk_handle* h, int nb) {
     const uint32_t n = (uint32_t)h->nfeat;
     const size_t smem = sort_smem<RecT, KV, ITEMS>();
     // opt in to more than 48 KB of dynamic shared memory (per device, so not cached across handles)
-    CU(cudaFuncSetAttribute(onesweep_kernel<RecT, KV, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kernel = h->safe_rank ? onesweep_kernel<RecT, KV, ITEMS, false> : onesweep_kernel<RecT, KV, ITEMS, true>;
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int p = 0; p < h->plan.npass; ++p) {
         const int shift = (KV ? 0 : h->idbits) + h->plan.shift[p];
         uint32_t* status = h->d_status + (size_t)p * h->B * h->sort_tiles * RADIX;
-        onesweep_kernel<RecT, KV, ITEMS><<<h->sort_tiles * nb, SORT_THREADS, smem, h->stream>>>(
+        kernel<<<h->sort_tiles * nb, SORT_THREADS, smem, h->stream>>>(
             (const RecT*)h->d_recA, (RecT*)h->d_recB, h->d_valA, h->d_valB, n, h->sort_tiles, (uint32_t)nb, shift, h->plan.bits[p],
             h->d_ghist + (size_t)p * RADIX, status, h->d_ticket + p);
         h->launches++;
@@ -281,11 +285,11 @@ int launch_segment(fsk_handle* h, int nb) {
     if (h->ids16)
         segment_kernel<RecT, KV, uint16_t><<<grid, SEG_THREADS, 0, h->stream>>>((const RecT*)h->d_recA, h->d_valA, n, h->ids_stride, h->idbits,
                                                                                 (uint32_t)h->N, h->d_woff32, h->d_fill, (uint16_t*)h->d_ids,
-                                                                                h->d_task, stat);
+                                                                                h->d_task, h->d_flag, stat);
     else
         segment_kernel<RecT, KV, uint32_t><<<grid, SEG_THREADS, 0, h->stream>>>((const RecT*)h->d_recA, h->d_valA, n, h->ids_stride, h->idbits,
                                                                                 (uint32_t)h->N, h->d_woff32, h->d_fill, (uint32_t*)h->d_ids,
-                                                                                h->d_task, stat);
+                                                                                h->d_task, h->d_flag, stat);
     h->launches++;
     CU(cudaGetLastError());
     return FSK_OK;
@@ -429,6 +433,18 @@ int finalize_typed(fsk_handle* h, const T* K) {
     return FSK_OK;
 }
 
+// Did segment_kernel see a batch that the sort left out of order?  (Only possible if the optimistic ranking of
+// onesweep_kernel was not served in lane order.)  Synchronises the stream.
+int sort_was_unstable(fsk_handle* h, bool* bad) {
+    uint32_t f = 0;
+    CU(cudaMemcpyAsync(&f, h->d_flag, sizeof f, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *bad = f != 0;
+    return FSK_OK;
+}
+
+int build_partial_once(fsk_handle* h);
+
 }  // namespace
 
 // ================================================================================================
@@ -486,6 +502,8 @@ int fsk_set_option(fsk_handle* h, const char* key, int64_t value) {
     } else if (!strcmp(key, "acc_path")) {
         if (value < 0 || value > 2) return fail(h, FSK_EINVAL, "acc_path must be 0 (auto), 1 (global RED) or 2 (shared-memory rows)");
         h->opt_acc_path = (int)value;
+    } else if (!strcmp(key, "safe_rank")) {
+        h->safe_rank = value != 0;
     } else if (!strcmp(key, "wave")) {
         if (value < 1 || value > 1024) return fail(h, FSK_EINVAL, "wave must be in [1, 1024]");
         h->opt_wave = (int)value;
@@ -681,6 +699,8 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     }
     ALLOC(h->d_counters, 4);
     CU(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), h->stream));
+    ALLOC(h->d_flag, 1);
+    CU(cudaMemsetAsync(h->d_flag, 0, sizeof(uint32_t), h->stream));
 
     // accumulators
     h->ks_slots = h->variance_mode ? B : 1;
@@ -722,13 +742,38 @@ int fsk_accumulate_combos(fsk_handle* h, const int32_t* combos, int64_t n, int s
         int rc = run_batch(h, combos + i, nb, h->d_Kint, 0);
         if (rc) return rc;
     }
-    if (sync) CU(cudaStreamSynchronize(h->stream));
+    if (sync) {
+        bool bad = false;
+        int rc = sort_was_unstable(h, &bad);
+        if (rc) return rc;
+        if (bad) return fail(h, FSK_ECUDA, "sort verification failed: records out of order after the optimistic ranking; set option safe_rank = 1");
+    }
     return FSK_OK;
 }
 
 int fsk_build_partial(fsk_handle* h) {
     if (!h->uploaded) return fail(h, FSK_ESTATE, "nothing uploaded");
     CU(cudaSetDevice(h->device));
+    for (int attempt = 0;; ++attempt) {
+        int rc = build_partial_once(h);
+        if (rc) return rc;
+        bool bad = false;
+        rc = sort_was_unstable(h, &bad);
+        if (rc) return rc;
+        if (!bad) break;
+        if (h->safe_rank || attempt > 0) return fail(h, FSK_ECUDA, "sort verification failed with the safe ranking");
+        h->safe_rank = true;       // never observed; repeat the whole build with the match-mask ranking
+        h->rank_fallbacks++;
+        CU(cudaMemsetAsync(h->d_flag, 0, sizeof(uint32_t), h->stream));
+    }
+    h->built = true;
+    return FSK_OK;
+}
+
+}  // extern "C"
+
+namespace {
+int build_partial_once(fsk_handle* h) {
     int rc = fsk_reset_partial(h);
     if (rc) return rc;
     h->stdevs.clear();
@@ -807,9 +852,11 @@ int fsk_build_partial(fsk_handle* h) {
         h->d_Khat.clear();
     }
     CU(cudaStreamSynchronize(h->stream));
-    h->built = true;
     return FSK_OK;
 }
+}  // namespace
+
+extern "C" {
 
 int fsk_partial_buffer(fsk_handle* h, void** dev_ptr, int64_t* n_elems, int* dtype) {
     if (!h->uploaded) return fail(h, FSK_ESTATE, "nothing uploaded");
@@ -849,6 +896,12 @@ int fsk_synchronize(fsk_handle* h) {
     if (!h->stream) return FSK_OK;
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
+    if (h->uploaded) {
+        bool bad = false;
+        int rc = sort_was_unstable(h, &bad);
+        if (rc) return rc;
+        if (bad) return fail(h, FSK_ECUDA, "sort verification failed: records out of order after the optimistic ranking; set option safe_rank = 1");
+    }
     return FSK_OK;
 }
 

@@ -109,6 +109,23 @@ def test_random_exact_vs_oracle(FastSK, oracle_mod, case, acc_path):
     assert st["combos_done"] == len(queue) and st["kernel_launches"] > 0
 
 
+@pytest.mark.parametrize("case", [CASES[0], CASES[-3], CASES[-4]], ids=lambda c: c[0])
+def test_safe_ranking_path_gives_the_same_kernel(FastSK, case):
+    """onesweep's optimistic ranking (one shared atomic per key, verified by segment_kernel) and the match-mask
+    ranking it falls back to must produce the same integers."""
+    name, ntr, nte, alpha, (lo, hi), g, m, batch, lowc = case
+    rng = np.random.default_rng(7)
+    X = random_seqs(rng, ntr + nte, alpha, max(lo, g), hi, lowc)
+    queue = rng.permutation(comb(g, m))[:40].astype(np.int32)
+    out = []
+    for safe in (0, 1):
+        f = FastSK(g, m, combo_sequence=queue)
+        f.set_option("safe_rank", safe)
+        f.compute_train(X)
+        out.append(f.get_unnormalised())
+    assert np.array_equal(out[0], out[1])
+
+
 @pytest.mark.parametrize("alpha,g,m", [(4, 8, 4), (21, 6, 2), (57, 12, 6)])
 def test_per_combination_counts(FastSK, oracle_mod, alpha, g, m):
     """Integer partial kernel of every single combination (fastsk_kernel.cpp:224-241 for one work item)."""
