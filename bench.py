@@ -42,6 +42,9 @@ sys.path.insert(0, ROOT)
 
 G, M, N_SEQ, N_TRAIN, SEQ_LEN = 16, 8, 50000, 40000, 200
 METRIC, UNIT = "gkm_kernel_build_combinations_per_s", "combinations/s"
+# dram__bytes_read.sum + dram__bytes_write.sum of accumulate_rows_kernel per batch of 48 combinations, from the ncu --set full
+# capture summarised in profiles/ (None until captured for the current kernel)
+TRAFFIC_ACC = None
 
 
 def synthetic(n=N_SEQ):
@@ -278,23 +281,32 @@ def run_b200(args):
     peak, peak_src = measured_peak()
     n_pairs, nfeat, rec = st1["n_pairs"], st1["nfeat"], st1["record_bytes"]
     batches = max(1, -(-combos_rank // max(1, st1["batch"])))
-    # accumulate (dominant): every pair update streams one 4-byte (sequence, count) entry of a run prefix from HBM,
-    # and every batch reads and writes each touched 8-byte cell of the packed triangle once
-    acc_bytes = 4.0 * updates + 16.0 * n_pairs * batches
+    id_bytes = 2 if N_SEQ <= 65536 else 4
+    # accumulate (dominant kernel, launched in waves of rows; figures are per batch = one pass over all rows): every unit
+    # update streams one sequence id of a run prefix (2 B as u16) and every batch adds each 8-byte cell of the packed
+    # triangle once (RED = read + write)
+    acc_bytes = float(id_bytes) * updates + 16.0 * n_pairs * batches
     acc_s = d["ms_accumulate"] * 1e-3
     # pack + sort + segment: SURVEY 8(d) formula with the record width actually moved (4 B here, not 8)
     gw_bytes = 4 if G * st1["bits_per_char"] <= 32 else 8
-    sort_bytes = combos_rank * (nfeat * (gw_bytes + 4 + rec) + nfeat * 2 * rec * st1["sort_passes"] + nfeat * 2 * rec)
+    sort_bytes = combos_rank * nfeat * ((gw_bytes + 4 + rec) + 2 * rec * st1["sort_passes"] + (rec + id_bytes + 8))
     sort_s = (d["ms_pack"] + d["ms_sort"] + d["ms_segment"]) * 1e-3
-    roofline = {"kernel": "accumulate_rows_kernel (+seg_finish)", "bound": "hbm", "achieved": acc_bytes / acc_s / 1e9 if acc_s else None,
-                "peak": peak, "unit": "GB/s", "frac": (acc_bytes / acc_s / 1e9 / peak) if acc_s else None, "traffic": None,
+    roofline = {"kernel": "accumulate_rows_kernel", "bound": "hbm", "achieved": acc_bytes / acc_s / 1e9 if acc_s else None,
+                "peak": peak, "unit": "GB/s", "frac": (acc_bytes / acc_s / 1e9 / peak) if acc_s else None, "traffic": TRAFFIC_ACC,
                 "peak_source": peak_src, "share_of_step": d["ms_accumulate"] / d["ms_total"] if d["ms_total"] else None,
-                "algorithmic_bytes": "4 B x pair-updates (run-prefix entries) + 16 B x packed-triangle cells per batch",
+                "algorithmic_bytes": f"{id_bytes} B x unit pair-updates (ids of the run prefixes) + 16 B x packed-triangle cells per batch",
+                "launch": "one batch = all row waves of the kernel (launched in waves for L2 locality)",
+                "note": "shared-memory-atomic bound (ncu: l1tex 78 %, smem wavefronts 64 % of peak), not HBM bound",
                 "pair_updates_per_s": updates / acc_s if acc_s else None}
     roofline_sort = {"kernel": "pack_hist + onesweep passes + segment", "bound": "hbm", "achieved": sort_bytes / sort_s / 1e9 if sort_s else None,
                      "peak": peak, "unit": "GB/s", "frac": (sort_bytes / sort_s / 1e9 / peak) if sort_s else None,
                      "share_of_step": (d["ms_pack"] + d["ms_sort"] + d["ms_segment"]) / d["ms_total"] if d["ms_total"] else None,
-                     "algorithmic_bytes": f"per combination: nfeat x ({gw_bytes}+4+{rec}) pack + nfeat x 2 x {rec} x {st1['sort_passes']} passes + nfeat x 2 x {rec} segment"}
+                     "algorithmic_bytes": f"per combination and window: ({gw_bytes}+4+{rec}) pack + 2 x {rec} x {st1['sort_passes']} passes + "
+                                          f"({rec}+{id_bytes}+8) segment",
+                     "per_stage_gbs": {
+                         "pack": combos_rank * nfeat * (gw_bytes + 4 + rec) / (d["ms_pack"] * 1e-3) / 1e9 if d["ms_pack"] else None,
+                         "sort": combos_rank * nfeat * 2 * rec * st1["sort_passes"] / (d["ms_sort"] * 1e-3) / 1e9 if d["ms_sort"] else None,
+                         "segment": combos_rank * nfeat * (rec + id_bytes + 8) / (d["ms_segment"] * 1e-3) / 1e9 if d["ms_segment"] else None}}
     phase_ms = {k[3:]: d[k] / args.steps for k in d if k.startswith("ms_")}
     del f
     torch.cuda.empty_cache()
@@ -361,10 +373,10 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--combos-per-step", type=int, default=96)
+    ap.add_argument("--combos-per-step", type=int, default=192)
     ap.add_argument("--batch", type=int, default=0, help="combinations per launch group (0 = auto)")
     ap.add_argument("--acc-path", type=int, default=0, help="0 auto, 1 global RED, 2 shared-memory rows")
-    ap.add_argument("--wave", type=int, default=1, help="accumulate launch = wave x resident CTAs rows")
+    ap.add_argument("--wave", type=int, default=4, help="accumulate launch = wave x resident CTAs rows")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of reference CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

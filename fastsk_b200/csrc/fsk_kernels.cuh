@@ -25,7 +25,7 @@ constexpr int MAX_BATCH = 48;    // combinations per launch group (kernel-parame
 constexpr int MAX_PASS = 8;      // 64 key bits / 8
 constexpr int RADIX = 256;
 constexpr int SORT_THREADS = 256;
-constexpr int PACK_ITEMS = 8;
+constexpr int PACK_ITEMS = 64;   // windows per thread of pack_hist_kernel
 
 // The kept characters of a combination, as maximal stretches of consecutive kept positions inside one g-mer
 // word: seg = source bit position (word * 64 + shift) | (width in bits - 1) << 7.  The stretches are laid into
@@ -117,8 +117,10 @@ pack_hist_kernel(const GwT* __restrict__ gw0, const uint64_t* __restrict__ gw1, 
     for (int i = threadIdx.x; i < npass * RADIX; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const size_t sbase = (size_t)slot * nfeat;
+    // a CTA packs PACK_ITEMS x 256 consecutive windows: its 2 x 256 histogram counters go to the slot's global
+    // histogram once, so few CTAs per slot keep the same-address atomics on those few lines off the critical path
     const uint32_t tile0 = blockIdx.x * (256 * PACK_ITEMS);
-#pragma unroll 2
+#pragma unroll 4
     for (int it = 0; it < PACK_ITEMS; ++it) {
         const uint32_t w = tile0 + it * 256 + threadIdx.x;
         if (w < nfeat) {

@@ -45,7 +45,7 @@ struct fsk_handle {
     int opt_batch = 0;
     int opt_acc_path = 0;            // 0 auto, 1 global RED, 2 row-stationary shared memory
     bool safe_rank = false;          // onesweep ranking: false = one atomic per key, verified afterwards; true = match masks
-    int opt_wave = 1;                // accumulate launch = opt_wave x (CTAs resident on the chip) rows
+    int opt_wave = 4;                // accumulate launch = opt_wave x (CTAs resident on the chip) rows
     bool profile = false;
     std::string err;
 

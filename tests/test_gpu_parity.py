@@ -243,6 +243,47 @@ def test_full_size_properties(FastSK, oracle_mod):
     assert np.array_equal(np.diag(Kt), np.ones(N)) and np.array_equal(Kt, Kt.T)
 
 
+def test_c4_full_size_submatrix_and_additivity(FastSK, oracle_mod):
+    """BASELINE configs[3] at its full size (50 000 x 200 bp, g=16, m=8; the unmodified reference cannot index N > 46 341):
+    a few combinations through the whole pipeline with the production batch/wave settings.  K_ij depends only on
+    sequences i and j, so random sub-blocks must equal an oracle run on those sequences; partial kernels add up; the
+    diagonal is the count of matching window pairs of a sequence with itself (>= windows per combination)."""
+    import torch
+    N, L, g, m = 50000, 200, 16, 8
+    X = np.random.default_rng(0).integers(1, 5, size=(N, L), dtype=np.int32)
+    queue = np.random.default_rng(3).permutation(comb(g, m))[:6].astype(np.int32)
+    f = FastSK(g, m, combo_sequence=queue, distributed=False)
+    f.compute_kernel(X[:40000], X[40000:])
+    part = f.partial_tensor()                                 # int64 packed triangle on the device (10 GB): index it there
+    rng = np.random.default_rng(11)
+    idx = np.sort(np.concatenate([rng.choice(N, size=46, replace=False), [0, N - 1]]))
+    idx = np.unique(idx)
+    a, b = np.meshgrid(idx, idx, indexing="ij")
+    hi, lo = np.maximum(a, b).astype(np.int64), np.minimum(a, b).astype(np.int64)
+    flat = torch.from_numpy((hi * (hi + 1) // 2 + lo).ravel()).cuda()
+    sub = part[flat].cpu().numpy().reshape(len(idx), len(idx)).astype(np.uint64)
+    _, Ki, _ = oracle_mod.run("c", X[idx].tolist(), [], g, m, queue)
+    assert np.array_equal(sub, oracle_mod.unpack(Ki, len(idx)))
+    diag = part[torch.from_numpy(idx.astype(np.int64) * (idx.astype(np.int64) + 3) // 2).cuda()].cpu().numpy()
+    assert (diag >= len(queue) * (L - g + 1)).all()
+    # additivity over the combinations, checked on the same sub-block
+    f2 = FastSK(g, m, combo_sequence=queue[:2], distributed=False)
+    f2.compute_kernel(X[:40000], X[40000:])
+    s2 = f2.partial_tensor()[flat].cpu().numpy()
+    del f2
+    f3 = FastSK(g, m, combo_sequence=queue[2:], distributed=False)
+    f3.compute_kernel(X[:40000], X[40000:])
+    s3 = f3.partial_tensor()[flat].cpu().numpy()
+    assert np.array_equal((s2 + s3).reshape(sub.shape).astype(np.uint64), sub)
+    # normalised outputs: unit diagonal, train block symmetric (sampled), test rows within [0, 1]
+    Kt = f.get_train_kernel_tensor()
+    d = torch.diagonal(Kt)
+    assert bool((d == 1.0).all())
+    r = torch.from_numpy(rng.choice(40000, size=64, replace=False)).cuda()
+    blk = Kt[r][:, r]
+    assert bool((blk == blk.T).all()) and float(blk.max()) <= 1.0 and float(blk.min()) >= 0.0
+
+
 def test_errors_and_api_surface(FastSK, tmp_path):
     with pytest.raises(ValueError):
         FastSK(5, 5)
