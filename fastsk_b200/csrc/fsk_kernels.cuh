@@ -111,15 +111,40 @@ pack_hist_kernel(const GwT* __restrict__ gw0, const uint64_t* __restrict__ gw1, 
     // a 32-bit g-mer word holds a key of at most 32 bits: keep the arithmetic in 32 bits then
     using KeyT = typename std::conditional<sizeof(GwT) == 4, uint32_t, uint64_t>::type;
     __shared__ uint32_t sh[MAX_PASS * RADIX];
-    const int slot = blockIdx.y;
+    // grid = (slots, tiles): CTAs launched together read the same windows for different combinations, so the g-mer
+    // words come from HBM once per batch and from L2 for the other slots
+    const int slot = blockIdx.x;
     const int nseg = spec.nseg[slot];
     const int npass = plan.npass;
     for (int i = threadIdx.x; i < npass * RADIX; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const size_t sbase = (size_t)slot * nfeat;
+    // stretch and digit descriptors live in registers for the whole CTA (read once from parameter space; indexing the
+    // parameters inside the window loop made the kernel issue-bound on constant loads)
+    constexpr int SEGR = 8;
+    uint32_t sg_sh[SEGR], sg_dst[SEGR];
+    KeyT sg_mask[SEGR];
+    {
+        int dst = 0;
+#pragma unroll
+        for (int j = 0; j < SEGR; ++j) {
+            const uint32_t e = j < nseg ? spec.seg[slot][j] : 0u;
+            const int width = (int)(e >> 7) + 1;
+            sg_sh[j] = e & 127u;
+            sg_dst[j] = (uint32_t)dst;
+            sg_mask[j] = j < nseg ? (KeyT)((KeyT) ~(KeyT)0 >> ((int)sizeof(KeyT) * 8 - width)) : (KeyT)0;
+            dst += j < nseg ? width : 0;
+        }
+    }
+    uint32_t dg_sh[MAX_PASS], dg_mask[MAX_PASS];
+#pragma unroll
+    for (int p = 0; p < MAX_PASS; ++p) {
+        dg_sh[p] = p < npass ? plan.shift[p] : 0u;
+        dg_mask[p] = p < npass ? ((1u << plan.bits[p]) - 1u) : 0u;
+    }
     // a CTA packs PACK_ITEMS x 256 consecutive windows: its 2 x 256 histogram counters go to the slot's global
     // histogram once, so few CTAs per slot keep the same-address atomics on those few lines off the critical path
-    const uint32_t tile0 = blockIdx.x * (256 * PACK_ITEMS);
+    const uint32_t tile0 = blockIdx.y * (256 * PACK_ITEMS);
 #pragma unroll 4
     for (int it = 0; it < PACK_ITEMS; ++it) {
         const uint32_t w = tile0 + it * 256 + threadIdx.x;
@@ -128,17 +153,24 @@ pack_hist_kernel(const GwT* __restrict__ gw0, const uint64_t* __restrict__ gw1, 
             uint64_t hi = 0;
             if (NW == 2) hi = gw1[w];
             KeyT key = 0;
-            int dst = 0;
-            for (int j = 0; j < nseg; ++j) {
-                const uint32_t e = spec.seg[slot][j];
-                const int width = (int)(e >> 7) + 1;
-                if (NW == 2) {
-                    const uint64_t word = (e & 64u) ? hi : lo;
-                    key |= (KeyT)((word >> (e & 63u)) & (~0ull >> (64 - width))) << dst;
-                } else {
-                    key |= (KeyT)(((KeyT)lo >> (e & 63u)) & ((KeyT)~(KeyT)0 >> ((int)sizeof(KeyT) * 8 - width))) << dst;
+#pragma unroll
+            for (int j = 0; j < SEGR; ++j) {
+                if (j < nseg) {
+                    const KeyT word = (NW == 2 && (sg_sh[j] & 64u)) ? (KeyT)hi : (KeyT)lo;
+                    key |= ((word >> (sg_sh[j] & 63u)) & sg_mask[j]) << sg_dst[j];
                 }
-                dst += width;
+            }
+            if (nseg > SEGR) {                     // more than SEGR stretches (long k): the rest from parameter space
+                int dst = 0;
+                for (int j = 0; j < nseg; ++j) {
+                    const uint32_t e = spec.seg[slot][j];
+                    const int width = (int)(e >> 7) + 1;
+                    if (j >= SEGR) {
+                        const KeyT word = (NW == 2 && (e & 64u)) ? (KeyT)hi : (KeyT)lo;
+                        key |= ((word >> (e & 63u)) & ((KeyT) ~(KeyT)0 >> ((int)sizeof(KeyT) * 8 - width))) << dst;
+                    }
+                    dst += width;
+                }
             }
             const uint32_t seq = wseq[w];
             if (KV) {
@@ -147,10 +179,9 @@ pack_hist_kernel(const GwT* __restrict__ gw0, const uint64_t* __restrict__ gw1, 
             } else {
                 rec[sbase + w] = ((RecT)key << idbits) | (RecT)seq;
             }
-            for (int p = 0; p < npass; ++p) {
-                const uint32_t d = (uint32_t)(key >> plan.shift[p]) & ((1u << plan.bits[p]) - 1);
-                atomicAdd(&sh[p * RADIX + d], 1u);
-            }
+#pragma unroll
+            for (int p = 0; p < MAX_PASS; ++p)
+                if (p < npass) atomicAdd(&sh[p * RADIX + ((uint32_t)(key >> dg_sh[p]) & dg_mask[p])], 1u);
         }
     }
     __syncthreads();
@@ -166,7 +197,7 @@ pack_hist_kernel(const GwT* __restrict__ gw0, const uint64_t* __restrict__ gw1, 
 // ascending inside every run of equal k-mers (the property countAndUpdateTri relies on).
 // status word = flag (2 bits: 1 = tile aggregate, 2 = inclusive prefix) | count (30 bits).
 template <typename RecT, bool KV, int ITEMS, bool OPTIMISTIC>
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, (sizeof(RecT) == 4 ? 4 : 2))
 onesweep_kernel(const RecT* __restrict__ in, RecT* __restrict__ out, const uint32_t* __restrict__ vin,
                 uint32_t* __restrict__ vout, uint32_t n, uint32_t tiles_per_slot, uint32_t nslots, int shift, int bits,
                 const uint32_t* __restrict__ ghist /* [slot][MAX_PASS][RADIX], pre-offset to this pass */,
@@ -176,8 +207,7 @@ onesweep_kernel(const RecT* __restrict__ in, RecT* __restrict__ out, const uint3
     RecT* skeys = reinterpret_cast<RecT*>(smem_raw);
     uint32_t* svals = reinterpret_cast<uint32_t*>(smem_raw + sizeof(RecT) * TILE);
     uint32_t* warp_hist = svals + (KV ? TILE : 0);   // [8][RADIX]
-    uint32_t* digit_start = warp_hist + 8 * RADIX;    // [RADIX]
-    uint32_t* scatter_base = digit_start + RADIX;     // [RADIX]
+    uint32_t* scatter_base = warp_hist + 8 * RADIX;   // [RADIX]
     uint32_t* warp_sums = scatter_base + RADIX;       // [8]
     uint32_t* match_mask = warp_sums + 8;             // [8][RADIX]
     __shared__ uint32_t s_ticket;
@@ -196,7 +226,7 @@ onesweep_kernel(const RecT* __restrict__ in, RecT* __restrict__ out, const uint3
 
     RecT key[ITEMS];
     uint32_t val[ITEMS];
-    uint32_t rank[ITEMS];
+    uint32_t rank2[(ITEMS + 1) / 2];   // two 16-bit ranks per register (a rank is < TILE <= 4096)
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         const uint32_t idx = tile0 + warp * (32 * ITEMS) + j * 32 + lane;
@@ -222,8 +252,9 @@ onesweep_kernel(const RecT* __restrict__ in, RecT* __restrict__ out, const uint3
         const bool valid = idx < n;
         const uint32_t d = (uint32_t)(key[j] >> shift) & dmask;
         uint32_t* wh = warp_hist + warp * RADIX + d;
+        uint32_t rk;
         if (OPTIMISTIC) {
-            rank[j] = valid ? atomicAdd(wh, 1u) : 0u;
+            rk = valid ? atomicAdd(wh, 1u) : 0u;
         } else {
             uint32_t* mm = match_mask + warp * RADIX + d;
             if (valid) atomicOr(mm, 1u << lane);
@@ -234,18 +265,19 @@ onesweep_kernel(const RecT* __restrict__ in, RecT* __restrict__ out, const uint3
             const uint32_t lower = peers & lane_lt;
             if (valid && lower == 0) { *wh = prev + __popc(peers); *mm = 0; }
             __syncwarp();
-            rank[j] = prev + __popc(lower);
+            rk = prev + __popc(lower);
         }
+        if (j & 1) rank2[j >> 1] |= rk << 16;
+        else rank2[j >> 1] = rk;
     }
     __syncthreads();
 
-    // thread d owns digit d: exclusive scan over warps, tile total
-    uint32_t total = 0;
+    // thread d owns digit d: tile total, published at once as the tile's aggregate
+    uint32_t cw[8], total = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
-        const uint32_t c = warp_hist[w * RADIX + tid];
-        warp_hist[w * RADIX + tid] = total;
-        total += c;
+        cw[w] = warp_hist[w * RADIX + tid];
+        total += cw[w];
     }
     uint32_t* my_status = status + ((size_t)slot * tiles_per_slot + tile) * RADIX + tid;
     st_volatile_u32(my_status, total | (tile == 0 ? 0x80000000u : 0x40000000u));
@@ -253,9 +285,29 @@ onesweep_kernel(const RecT* __restrict__ in, RecT* __restrict__ out, const uint3
     uint32_t dummy;
     const uint32_t gexcl = block_excl_scan_256(ghist[(size_t)slot * MAX_PASS * RADIX + tid], warp_sums, dummy);
     const uint32_t dstart = block_excl_scan_256(total, warp_sums, dummy);
+    // position of a key inside the tile = (start of its digit + keys of the digit in earlier warps) + rank: one lookup
+    {
+        uint32_t run = dstart;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            warp_hist[w * RADIX + tid] = run;
+            run += cw[w];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const uint32_t idx = tile0 + warp * (32 * ITEMS) + j * 32 + lane;
+        if (idx < n) {
+            const uint32_t d = (uint32_t)(key[j] >> shift) & dmask;
+            const uint32_t pos = warp_hist[warp * RADIX + d] + ((rank2[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
+            skeys[pos] = key[j];
+            if (KV) svals[pos] = val[j];
+        }
+    }
 
-    // decoupled look-back, LOOK predecessors per step with independent loads in flight: the first wave of
-    // resident tiles has to walk back over every tile that started with it
+    // decoupled look-back (after the local scatter was issued, so its latency overlaps), LOOK predecessors per step
+    // with independent loads in flight
     uint32_t excl = 0;
     if (tile > 0) {
         constexpr int LOOK = 8;
@@ -277,20 +329,7 @@ onesweep_kernel(const RecT* __restrict__ in, RecT* __restrict__ out, const uint3
         }
         st_volatile_u32(my_status, (total + excl) | 0x80000000u);
     }
-    digit_start[tid] = dstart;
     scatter_base[tid] = gexcl + excl - dstart;
-    __syncthreads();
-
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-        const uint32_t idx = tile0 + warp * (32 * ITEMS) + j * 32 + lane;
-        if (idx < n) {
-            const uint32_t d = (uint32_t)(key[j] >> shift) & dmask;
-            const uint32_t pos = digit_start[d] + warp_hist[warp * RADIX + d] + rank[j];
-            skeys[pos] = key[j];
-            if (KV) svals[pos] = val[j];
-        }
-    }
     __syncthreads();
     const uint32_t count = min((uint32_t)TILE, n - tile0);
     for (uint32_t i = tid; i < count; i += SORT_THREADS) {
@@ -322,6 +361,12 @@ constexpr int SEG_ROWS = 16;
 constexpr int SEG_WARP_RECS = SEG_ROWS * 32;
 constexpr int SEG_TILE = (SEG_THREADS / 32) * SEG_WARP_RECS;
 
+// fill[slot][b] = woff[b]: where the next task of sequence b goes
+__global__ void init_fill_kernel(uint32_t* __restrict__ fill, const uint32_t* __restrict__ woff, uint32_t nseq) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nseq) fill[(size_t)blockIdx.y * nseq + b] = woff[b];
+}
+
 template <typename RecT, bool KV>
 struct RecOps {
     static __device__ __forceinline__ bool same_key(RecT a, RecT b, int idbits) { return KV ? a == b : ((a ^ b) >> idbits) == 0; }
@@ -331,7 +376,7 @@ struct RecOps {
 template <typename RecT, bool KV, typename IdT>
 __global__ void __launch_bounds__(SEG_THREADS, (sizeof(RecT) == 4 ? 3 : 2))
 segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, uint32_t n, size_t ids_stride, int idbits,
-               uint32_t nseq, const uint32_t* __restrict__ woff, uint32_t* __restrict__ fill, IdT* __restrict__ ids,
+               uint32_t nseq, uint32_t* __restrict__ fill, IdT* __restrict__ ids,
                uint2* __restrict__ task, uint32_t* __restrict__ unsorted_flag, unsigned long long* __restrict__ stat_counters) {
     using Ops = RecOps<RecT, KV>;
     const int slot = blockIdx.y;
@@ -461,22 +506,19 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
     constexpr int HALF = SEG_ROWS / 2;
 #pragma unroll
     for (int h0 = 0; h0 < SEG_ROWS; h0 += HALF) {
-        uint32_t pos[HALF], wo[HALF];
+        uint32_t pos[HALF];                      // fill[] starts at woff[seq]: the atomic returns the task's address
 #pragma unroll
         for (int k = 0; k < HALF; ++k) {
             const uint32_t i = seg0 + (h0 + k) * 32 + lane;
-            pos[k] = wo[k] = 0;
-            if (i < n) {
-                pos[k] = atomicAdd(&fill[(size_t)slot * nseq + sq[h0 + k]], 1u);
-                wo[k] = woff[sq[h0 + k]];
-            }
+            pos[k] = 0;
+            if (i < n) pos[k] = atomicAdd(&fill[(size_t)slot * nseq + sq[h0 + k]], 1u);
         }
 #pragma unroll
         for (int k = 0; k < HALF; ++k) {
             const uint32_t i = seg0 + (h0 + k) * 32 + lane;
             if (i < n) {
                 ids[(size_t)slot * ids_stride + i] = (IdT)sq[h0 + k];
-                task[sbase + wo[k] + pos[k]] = make_uint2(rs[h0 + k], len[h0 + k]);
+                task[sbase + pos[k]] = make_uint2(rs[h0 + k], len[h0 + k]);
                 updates += len[h0 + k];
             }
         }

@@ -148,8 +148,7 @@ void release_device(fsk_handle* h) {
     dev_free(h->d_recA); dev_free(h->d_recB); dev_free(h->d_valA); dev_free(h->d_valB);
     dev_free(h->d_zero);
     h->d_ghist = h->d_ticket = h->d_status = nullptr;
-    dev_free(h->d_woff32); dev_free(h->d_ids); dev_free(h->d_task);
-    h->d_fill = nullptr;
+    dev_free(h->d_woff32); dev_free(h->d_ids); dev_free(h->d_task); dev_free(h->d_fill);
     dev_free(h->d_Kint); dev_free(h->d_Kf);
     for (auto& p : h->d_Khat) dev_free(p);
     h->d_Khat.clear();
@@ -234,7 +233,7 @@ struct Span {
 // --- typed launch helpers ----------------------------------------------------------------------
 template <typename RecT, bool KV>
 int launch_pack(fsk_handle* h, int nb, const BatchSpec& spec) {
-    dim3 grid((unsigned)((h->nfeat + 256 * PACK_ITEMS - 1) / (256 * PACK_ITEMS)), nb);
+    dim3 grid(nb, (unsigned)((h->nfeat + 256 * PACK_ITEMS - 1) / (256 * PACK_ITEMS)));
     RecT* rec = (RecT*)h->d_recA;
     const uint32_t n = (uint32_t)h->nfeat;
     if (h->NW == 2)
@@ -253,7 +252,7 @@ int launch_pack(fsk_handle* h, int nb, const BatchSpec& spec) {
 
 template <typename RecT, bool KV, int ITEMS>
 size_t sort_smem() {
-    return sizeof(RecT) * SORT_THREADS * ITEMS + (KV ? 4 * SORT_THREADS * ITEMS : 0) + 4 * (8 * RADIX + 2 * RADIX + 8 + 8 * RADIX);
+    return sizeof(RecT) * SORT_THREADS * ITEMS + (KV ? 4 * SORT_THREADS * ITEMS : 0) + 4 * (8 * RADIX + RADIX + 8 + 8 * RADIX);
 }
 
 template <typename RecT, bool KV, int ITEMS>
@@ -282,13 +281,15 @@ int launch_segment(fsk_handle* h, int nb) {
     const uint32_t n = (uint32_t)h->nfeat;
     dim3 grid(h->seg_tiles, nb);
     unsigned long long* stat = h->profile ? h->d_counters : nullptr;
+    init_fill_kernel<<<dim3((unsigned)((h->N + 255) / 256), nb), 256, 0, h->stream>>>(h->d_fill, h->d_woff32, (uint32_t)h->N);
+    h->launches++;
     if (h->ids16)
         segment_kernel<RecT, KV, uint16_t><<<grid, SEG_THREADS, 0, h->stream>>>((const RecT*)h->d_recA, h->d_valA, n, h->ids_stride, h->idbits,
-                                                                                (uint32_t)h->N, h->d_woff32, h->d_fill, (uint16_t*)h->d_ids,
+                                                                                (uint32_t)h->N, h->d_fill, (uint16_t*)h->d_ids,
                                                                                 h->d_task, h->d_flag, stat);
     else
         segment_kernel<RecT, KV, uint32_t><<<grid, SEG_THREADS, 0, h->stream>>>((const RecT*)h->d_recA, h->d_valA, n, h->ids_stride, h->idbits,
-                                                                                (uint32_t)h->N, h->d_woff32, h->d_fill, (uint32_t*)h->d_ids,
+                                                                                (uint32_t)h->N, h->d_fill, (uint32_t*)h->d_ids,
                                                                                 h->d_task, h->d_flag, stat);
     h->launches++;
     CU(cudaGetLastError());
@@ -681,16 +682,16 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     if (h->mode == MODE_KV) { ALLOC(h->d_valA, bn); ALLOC(h->d_valB, bn); }
     const int B = h->B;
     const size_t ghist_words = (size_t)B * MAX_PASS * RADIX, ticket_words = 64;
-    const size_t rowcount_words = (size_t)B * (size_t)N;
+    const size_t rowcount_words = 0;
     const size_t status_words = (size_t)h->plan.npass * B * h->sort_tiles * RADIX;
     h->zero_bytes = 4 * (ghist_words + ticket_words + status_words + rowcount_words);
     ALLOC(h->d_zero, h->zero_bytes);
     h->d_ghist = (uint32_t*)h->d_zero;
     h->d_ticket = h->d_ghist + ghist_words;
     h->d_status = h->d_ticket + ticket_words;
-    h->d_fill = h->d_status + status_words;
     { unsigned char* p; ALLOC(p, (size_t)B * h->ids_stride * (h->ids16 ? 2 : 4)); h->d_ids = p; }
     ALLOC(h->d_task, bn);
+    ALLOC(h->d_fill, (size_t)B * (size_t)N);
     {
         std::vector<uint32_t> w32((size_t)N + 1);
         for (int64_t i = 0; i <= N; ++i) w32[(size_t)i] = (uint32_t)woff[(size_t)i];
