@@ -320,26 +320,28 @@ def run_b200(args):
     Xte_p = torch.from_numpy(Xte.copy()).pin_memory().numpy()
 
     def e2e_job(q):
+        t = [time.perf_counter()]
         fe = FastSK(G, M, combo_sequence=q, device=local)
         fe.set_option("batch", args.batch)
         fe.set_option("acc_path", args.acc_path)
         fe.set_option("wave", args.wave)
         fe.compute_kernel(Xtr_p, Xte_p)
+        t.append(time.perf_counter())
         if rank == 0:
             fe.get_train_kernel(out=out_tr)
             fe.get_test_kernel(out=out_te)
-        n_l = fe.stats()["kernel_launches"]
+        t.append(time.perf_counter())
         del fe
-        return n_l
+        return {"compute_kernel_s": t[1] - t[0], "get_kernels_d2h_s": t[2] - t[1]}
 
     e2e_job(job[:world * min(cps, 8)])        # warm-up: allocator, NCCL channels
     barrier()
     t0 = time.perf_counter()
-    e2e_job(job)
+    e2e_parts = e2e_job(job)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    e2e = {"value": len(job) / e2e_s, "unit": UNIT, "seconds": e2e_s, "combinations": int(len(job)),
+    e2e = {"value": len(job) / e2e_s, "unit": UNIT, "seconds": e2e_s, "combinations": int(len(job)), "parts_rank0": e2e_parts,
            "h2d_bytes_per_step": int(X.nbytes // args.steps), "d2h_bytes_per_step": int((out_tr.nbytes + out_te.nbytes) // args.steps) if rank == 0 else 0,
            "what": "FastSK(g,m,combo_sequence=<the timed region's combinations>).compute_kernel(Xtrain, Xtest) from pinned host int32 + "
                    "get_train_kernel/get_test_kernel into pinned host fp64 (one job = all steps; bytes are per-step shares)"}
@@ -373,7 +375,7 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--combos-per-step", type=int, default=192)
+    ap.add_argument("--combos-per-step", type=int, default=384)
     ap.add_argument("--batch", type=int, default=0, help="combinations per launch group (0 = auto)")
     ap.add_argument("--acc-path", type=int, default=0, help="0 auto, 1 global RED, 2 shared-memory rows")
     ap.add_argument("--wave", type=int, default=4, help="accumulate launch = wave x resident CTAs rows")

@@ -45,12 +45,20 @@ struct fsk_handle {
     int opt_batch = 0;
     int opt_acc_path = 0;            // 0 auto, 1 global RED, 2 row-stationary shared memory
     bool safe_rank = false;          // onesweep ranking: false = one atomic per key, verified afterwards; true = match masks
+    int opt_rows_threads = 0;        // threads per row CTA of the accumulate (0 = by N)
+    int opt_overlap = 0;             // 1 = pre-pass of the next batch on its own low-priority stream (measured: no gain, the
+                                     // row CTAs own the whole SM's shared memory; profiles/r01_overlap_experiment.txt)
     int opt_wave = 4;                // accumulate launch = opt_wave x (CTAs resident on the chip) rows
     bool profile = false;
     std::string err;
 
     // state
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // accumulate, Welford, normalisation, copies
+    cudaStream_t pre_stream = nullptr;   // pack / sort / segment of the NEXT batch, overlapping the accumulate of the current one
+    cudaStream_t ls = nullptr;           // stream the launch helpers and profiling spans currently target
+    cudaEvent_t ev_pre[2] = {nullptr, nullptr}, ev_acc[2] = {nullptr, nullptr}, ev_sync = nullptr;
+    int64_t batch_index = 0;
+    int buf = 0;
     bool uploaded = false, built = false, finalized = false;
     int64_t n_train = 0, n_test = 0, N = 0, nfeat = 0, n_pairs = 0, n_train_pairs = 0, ncomb = 0;
     int A = 0, b = 0, cpw = 0, NW = 1;
@@ -73,10 +81,10 @@ struct fsk_handle {
     size_t zero_bytes = 0;
     uint32_t *d_ghist = nullptr, *d_ticket = nullptr, *d_status = nullptr;
     uint32_t *d_woff32 = nullptr, *d_fill = nullptr;   // window offsets per sequence; tasks filed so far per (slot, sequence)
-    void* d_ids = nullptr;                             // sequence id of every sorted record (u16 when N <= 65536, else u32)
+    void* d_ids[2] = {nullptr, nullptr};               // sequence id of every sorted record (u16 when N <= 65536, else u32); double-buffered
     size_t ids_stride = 0;                             // per-slot stride of d_ids, a multiple of 64 elements
     bool ids16 = false;
-    uint2* d_task = nullptr;
+    uint2* d_task[2] = {nullptr, nullptr};
     bool rows_path = false;
     int rows_threads = 256;
     size_t rows_smem = 0;
@@ -143,12 +151,14 @@ void dev_free(T*& p) {
 }
 
 void release_device(fsk_handle* h) {
+    if (h->pre_stream) cudaStreamSynchronize(h->pre_stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
     dev_free(h->d_gw0); dev_free(h->d_gw1); dev_free(h->d_wseq);
     dev_free(h->d_recA); dev_free(h->d_recB); dev_free(h->d_valA); dev_free(h->d_valB);
     dev_free(h->d_zero);
     h->d_ghist = h->d_ticket = h->d_status = nullptr;
-    dev_free(h->d_woff32); dev_free(h->d_ids); dev_free(h->d_task); dev_free(h->d_fill);
+    dev_free(h->d_woff32); dev_free(h->d_fill);
+    for (int i = 0; i < 2; ++i) { dev_free(h->d_ids[i]); dev_free(h->d_task[i]); }
     dev_free(h->d_Kint); dev_free(h->d_Kf);
     for (auto& p : h->d_Khat) dev_free(p);
     h->d_Khat.clear();
@@ -203,6 +213,7 @@ cudaEvent_t get_event(fsk_handle* h) {
 }
 void resolve_spans(fsk_handle* h) {
     if (h->spans.empty()) return;
+    cudaStreamSynchronize(h->pre_stream);
     cudaStreamSynchronize(h->stream);
     for (auto& s : h->spans) {
         float ms = 0;
@@ -221,11 +232,11 @@ struct Span {
         s.cls = cls;
         s.a = get_event(h);
         s.b = get_event(h);
-        cudaEventRecord(s.a, h->stream);
+        cudaEventRecord(s.a, h->ls);
     }
     ~Span() {
         if (!on) return;
-        cudaEventRecord(s.b, h->stream);
+        cudaEventRecord(s.b, h->ls);
         h->spans.push_back(s);
     }
 };
@@ -237,13 +248,13 @@ int launch_pack(fsk_handle* h, int nb, const BatchSpec& spec) {
     RecT* rec = (RecT*)h->d_recA;
     const uint32_t n = (uint32_t)h->nfeat;
     if (h->NW == 2)
-        pack_hist_kernel<RecT, KV, uint64_t, 2><<<grid, 256, 0, h->stream>>>((const uint64_t*)h->d_gw0, h->d_gw1, h->d_wseq, n, rec,
+        pack_hist_kernel<RecT, KV, uint64_t, 2><<<grid, 256, 0, h->ls>>>((const uint64_t*)h->d_gw0, h->d_gw1, h->d_wseq, n, rec,
                                                                            h->d_valA, h->d_ghist, spec, h->plan, h->idbits);
     else if (h->gw32)
-        pack_hist_kernel<RecT, KV, uint32_t, 1><<<grid, 256, 0, h->stream>>>((const uint32_t*)h->d_gw0, nullptr, h->d_wseq, n, rec,
+        pack_hist_kernel<RecT, KV, uint32_t, 1><<<grid, 256, 0, h->ls>>>((const uint32_t*)h->d_gw0, nullptr, h->d_wseq, n, rec,
                                                                            h->d_valA, h->d_ghist, spec, h->plan, h->idbits);
     else
-        pack_hist_kernel<RecT, KV, uint64_t, 1><<<grid, 256, 0, h->stream>>>((const uint64_t*)h->d_gw0, nullptr, h->d_wseq, n, rec,
+        pack_hist_kernel<RecT, KV, uint64_t, 1><<<grid, 256, 0, h->ls>>>((const uint64_t*)h->d_gw0, nullptr, h->d_wseq, n, rec,
                                                                            h->d_valA, h->d_ghist, spec, h->plan, h->idbits);
     h->launches++;
     CU(cudaGetLastError());
@@ -265,7 +276,7 @@ int launch_sort(fsk_handle* h, int nb) {
     for (int p = 0; p < h->plan.npass; ++p) {
         const int shift = (KV ? 0 : h->idbits) + h->plan.shift[p];
         uint32_t* status = h->d_status + (size_t)p * h->B * h->sort_tiles * RADIX;
-        kernel<<<h->sort_tiles * nb, SORT_THREADS, smem, h->stream>>>(
+        kernel<<<h->sort_tiles * nb, SORT_THREADS, smem, h->ls>>>(
             (const RecT*)h->d_recA, (RecT*)h->d_recB, h->d_valA, h->d_valB, n, h->sort_tiles, (uint32_t)nb, shift, h->plan.bits[p],
             h->d_ghist + (size_t)p * RADIX, status, h->d_ticket + p);
         h->launches++;
@@ -281,16 +292,16 @@ int launch_segment(fsk_handle* h, int nb) {
     const uint32_t n = (uint32_t)h->nfeat;
     dim3 grid(h->seg_tiles, nb);
     unsigned long long* stat = h->profile ? h->d_counters : nullptr;
-    init_fill_kernel<<<dim3((unsigned)((h->N + 255) / 256), nb), 256, 0, h->stream>>>(h->d_fill, h->d_woff32, (uint32_t)h->N);
+    init_fill_kernel<<<dim3((unsigned)((h->N + 255) / 256), nb), 256, 0, h->ls>>>(h->d_fill, h->d_woff32, (uint32_t)h->N);
     h->launches++;
     if (h->ids16)
-        segment_kernel<RecT, KV, uint16_t><<<grid, SEG_THREADS, 0, h->stream>>>((const RecT*)h->d_recA, h->d_valA, n, h->ids_stride, h->idbits,
-                                                                                (uint32_t)h->N, h->d_fill, (uint16_t*)h->d_ids,
-                                                                                h->d_task, h->d_flag, stat);
+        segment_kernel<RecT, KV, uint16_t><<<grid, SEG_THREADS, 0, h->ls>>>((const RecT*)h->d_recA, h->d_valA, n, h->ids_stride, h->idbits,
+                                                                                (uint32_t)h->N, h->d_fill, (uint16_t*)h->d_ids[h->buf],
+                                                                                h->d_task[h->buf], h->d_flag, stat);
     else
-        segment_kernel<RecT, KV, uint32_t><<<grid, SEG_THREADS, 0, h->stream>>>((const RecT*)h->d_recA, h->d_valA, n, h->ids_stride, h->idbits,
-                                                                                (uint32_t)h->N, h->d_fill, (uint32_t*)h->d_ids,
-                                                                                h->d_task, h->d_flag, stat);
+        segment_kernel<RecT, KV, uint32_t><<<grid, SEG_THREADS, 0, h->ls>>>((const RecT*)h->d_recA, h->d_valA, n, h->ids_stride, h->idbits,
+                                                                                (uint32_t)h->N, h->d_fill, (uint32_t*)h->d_ids[h->buf],
+                                                                                h->d_task[h->buf], h->d_flag, stat);
     h->launches++;
     CU(cudaGetLastError());
     return FSK_OK;
@@ -299,20 +310,20 @@ int launch_segment(fsk_handle* h, int nb) {
 template <typename IdT>
 int launch_accumulate(fsk_handle* h, int nb, unsigned long long* K, size_t slot_stride) {
     const uint32_t n = (uint32_t)h->nfeat;
-    const IdT* ids = (const IdT*)h->d_ids;
+    const IdT* ids = (const IdT*)h->d_ids[h->buf];
     if (h->rows_path) {
         // slot_stride != 0 (variance mode): every slot adds into its own K; else all slots add into one K
         const int groups = slot_stride ? nb : 1, per_group = slot_stride ? 1 : nb;
         const int wave = std::max(1, h->wave_rows / groups);
         for (int64_t hi = h->N - 1; hi >= 0; hi -= wave) {
             dim3 grid((unsigned)std::min<int64_t>(wave, hi + 1), groups);
-            accumulate_rows_kernel<unsigned long long, IdT, 4><<<grid, h->rows_threads, h->rows_smem, h->stream>>>(
-                ids, h->ids_stride, h->d_task, h->d_woff32, n, (uint32_t)hi, per_group, K, slot_stride);
+            accumulate_rows_kernel<unsigned long long, IdT, 4><<<grid, h->rows_threads, h->rows_smem, h->ls>>>(
+                ids, h->ids_stride, h->d_task[h->buf], h->d_woff32, n, (uint32_t)hi, per_group, K, slot_stride);
             h->launches++;
         }
     } else {
         dim3 grid((unsigned)((h->nfeat + 255) / 256), nb);
-        accumulate_global_kernel<unsigned long long, IdT><<<grid, 256, 0, h->stream>>>(ids, h->ids_stride, h->d_task, h->d_wseq, n, K, slot_stride);
+        accumulate_global_kernel<unsigned long long, IdT><<<grid, 256, 0, h->ls>>>(ids, h->ids_stride, h->d_task[h->buf], h->d_wseq, n, K, slot_stride);
         h->launches++;
     }
     CU(cudaGetLastError());
@@ -337,7 +348,12 @@ int run_batch(fsk_handle* h, const int32_t* combos, int nb, unsigned long long* 
         }
         spec.nseg[s] = (uint8_t)nseg;
     }
-    CU(cudaMemsetAsync(h->d_zero, 0, h->zero_bytes, h->stream));
+    // The pack / sort / segment of this batch go to pre_stream and may overlap the accumulate of the previous batch on
+    // the main stream (they are HBM / L2 bound, the accumulate is shared-memory bound); ids/task are double-buffered.
+    h->buf = (int)(h->batch_index++ & 1);
+    h->ls = h->pre_stream;
+    CU(cudaStreamWaitEvent(h->pre_stream, h->ev_acc[h->buf], 0));
+    CU(cudaMemsetAsync(h->d_zero, 0, h->zero_bytes, h->ls));
     int rc;
     {
         Span sp(h, PC_PACK);
@@ -360,11 +376,15 @@ int run_batch(fsk_handle* h, const int32_t* combos, int nb, unsigned long long* 
         else rc = launch_segment<uint64_t, true>(h, nb);
         if (rc) return rc;
     }
+    CU(cudaEventRecord(h->ev_pre[h->buf], h->pre_stream));
+    h->ls = h->stream;
+    CU(cudaStreamWaitEvent(h->stream, h->ev_pre[h->buf], 0));
     {
         Span sp(h, PC_ACCUMULATE);
         rc = h->ids16 ? launch_accumulate<uint16_t>(h, nb, K, slot_stride) : launch_accumulate<uint32_t>(h, nb, K, slot_stride);
         if (rc) return rc;
     }
+    CU(cudaEventRecord(h->ev_acc[h->buf], h->stream));
     h->combos_done += nb;
     if (h->spans.size() > 2048) resolve_spans(h);
     return FSK_OK;
@@ -420,6 +440,7 @@ void shard_work(const fsk_handle* h, std::vector<int32_t>& out) {
 
 template <typename T>
 int finalize_typed(fsk_handle* h, const T* K) {
+    h->ls = h->stream;
     Span sp(h, PC_NORMALISE);
     diag_kernel<T><<<(unsigned)((h->N + 255) / 256), 256, 0, h->stream>>>(K, h->N, h->d_diag);
     dim3 gtrain((unsigned)((h->n_train + 31) / 32), (unsigned)((h->n_train + 31) / 32));
@@ -475,7 +496,12 @@ void fsk_destroy(fsk_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     release_device(h);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream) {
+        if (h->pre_stream != h->stream) cudaStreamDestroy(h->pre_stream);
+        cudaStreamDestroy(h->stream);
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_pre[i]); cudaEventDestroy(h->ev_acc[i]); }
+        cudaEventDestroy(h->ev_sync);
+    }
     delete h;
 }
 
@@ -505,6 +531,12 @@ int fsk_set_option(fsk_handle* h, const char* key, int64_t value) {
         h->opt_acc_path = (int)value;
     } else if (!strcmp(key, "safe_rank")) {
         h->safe_rank = value != 0;
+    } else if (!strcmp(key, "rows_threads")) {
+        if (value != 0 && (value < 32 || value > 1024 || value % 32)) return fail(h, FSK_EINVAL, "rows_threads must be 0 or a multiple of 32 up to 1024");
+        h->opt_rows_threads = (int)value;
+    } else if (!strcmp(key, "overlap")) {
+        if (h->stream) return fail(h, FSK_ESTATE, "overlap must be set before the first upload");
+        h->opt_overlap = value != 0;
     } else if (!strcmp(key, "wave")) {
         if (value < 1 || value > 1024) return fail(h, FSK_EINVAL, "wave must be in [1, 1024]");
         h->opt_wave = (int)value;
@@ -572,7 +604,19 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, h->device));
     if (prop.major < 10) return fail(h, FSK_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", h->device, prop.major, prop.minor);
-    if (!h->stream) CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    if (!h->stream) {
+        int prio_lo = 0, prio_hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CU(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi));        // accumulate CTAs are placed first
+        if (h->opt_overlap) CU(cudaStreamCreateWithPriority(&h->pre_stream, cudaStreamNonBlocking, prio_lo));
+        else h->pre_stream = h->stream;
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaEventCreateWithFlags(&h->ev_pre[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&h->ev_acc[i], cudaEventDisableTiming));
+        }
+        CU(cudaEventCreateWithFlags(&h->ev_sync, cudaEventDisableTiming));
+        h->ls = h->stream;
+    }
     release_device(h);
 
     h->n_train = n_train; h->n_test = n_test; h->N = N; h->nfeat = nfeat;
@@ -609,6 +653,7 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     h->rows_path = h->opt_acc_path == 2 || (h->opt_acc_path == 0 && rows_ok);
     h->rows_smem = (size_t)N * 4 + 128;   // + one dump word per lane for masked-off ids
     h->rows_threads = N >= 16384 ? 1024 : (N >= 4096 ? 512 : 256);
+    if (h->opt_rows_threads) h->rows_threads = h->opt_rows_threads;
     h->ids16 = N <= 65536;
     h->ids_stride = (size_t)((nfeat + 8 + 63) / 64 * 64);
     {
@@ -623,7 +668,7 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
 
     // batch: combinations per launch group.  The row path flushes every row of K once per batch, so it
     // wants the batch as large as memory allows; the u32 shared-memory accumulators bound it by 2^32 / maxwin^2.
-    const int64_t per_slot_bytes = nfeat * (2 * (h->mode == MODE_R32 ? 4 : 8) + (h->mode == MODE_KV ? 8 : 0) + 8 + (h->ids16 ? 2 : 4)) +
+    const int64_t per_slot_bytes = nfeat * (2 * (h->mode == MODE_R32 ? 4 : 8) + (h->mode == MODE_KV ? 8 : 0) + 2 * (8 + (h->ids16 ? 2 : 4))) +
                                    (int64_t)h->plan.npass * ((nfeat + 3071) / 3072) * RADIX * 4 + N * 4 + 4096;
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
@@ -689,8 +734,12 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     h->d_ghist = (uint32_t*)h->d_zero;
     h->d_ticket = h->d_ghist + ghist_words;
     h->d_status = h->d_ticket + ticket_words;
-    { unsigned char* p; ALLOC(p, (size_t)B * h->ids_stride * (h->ids16 ? 2 : 4)); h->d_ids = p; }
-    ALLOC(h->d_task, bn);
+    for (int i = 0; i < 2; ++i) {
+        unsigned char* p;
+        ALLOC(p, (size_t)B * h->ids_stride * (h->ids16 ? 2 : 4));
+        h->d_ids[i] = p;
+        ALLOC(h->d_task[i], bn);
+    }
     ALLOC(h->d_fill, (size_t)B * (size_t)N);
     {
         std::vector<uint32_t> w32((size_t)N + 1);
@@ -738,6 +787,8 @@ int fsk_accumulate_combos(fsk_handle* h, const int32_t* combos, int64_t n, int s
     if (!h->uploaded) return fail(h, FSK_ESTATE, "nothing uploaded");
     if (h->variance_mode) return fail(h, FSK_ESTATE, "fsk_accumulate_combos needs an integer mode (exact or skip_variance)");
     CU(cudaSetDevice(h->device));
+    CU(cudaEventRecord(h->ev_sync, h->stream));
+    CU(cudaStreamWaitEvent(h->pre_stream, h->ev_sync, 0));
     for (int64_t i = 0; i < n; i += h->B) {
         const int nb = (int)std::min<int64_t>(h->B, n - i);
         int rc = run_batch(h, combos + i, nb, h->d_Kint, 0);

@@ -4,6 +4,7 @@
         python tools/profile_step.py --batch 8
 """
 import argparse
+import time
 import os
 import sys
 from math import comb
@@ -22,7 +23,10 @@ ap.add_argument("--m", type=int, default=8)
 ap.add_argument("--alphabet", type=int, default=4)
 ap.add_argument("--acc-path", type=int, default=0)
 ap.add_argument("--reps", type=int, default=1)
-ap.add_argument("--wave", type=int, default=1)
+ap.add_argument("--batches-per-call", type=int, default=1)
+ap.add_argument("--wave", type=int, default=4)
+ap.add_argument("--overlap", type=int, default=0)
+ap.add_argument("--rows-threads", type=int, default=0)
 a = ap.parse_args()
 
 X = np.random.default_rng(0).integers(1, a.alphabet + 1, size=(a.n, a.len), dtype=np.int32)
@@ -31,15 +35,22 @@ f = FastSK(a.g, a.m, combo_sequence=order, distributed=False, profile=True)
 f.set_option("batch", a.batch)
 f.set_option("acc_path", a.acc_path)
 f.set_option("wave", a.wave)
+f.set_option("overlap", a.overlap)
+f.set_option("rows_threads", a.rows_threads)
 codes = np.ascontiguousarray(X.reshape(-1))
 offsets = np.arange(a.n + 1, dtype=np.int64) * a.len
 f._call("fsk_upload", codes.ctypes.data_as(_lib.c_i32p), offsets.ctypes.data_as(_lib.c_i64p), int(a.n * 0.8), a.n - int(a.n * 0.8))
 for r in range(1 + a.reps):
-    q = np.ascontiguousarray(order[r * a.batch:(r + 1) * a.batch])
+    per = a.batch * a.batches_per_call
+    q = np.ascontiguousarray(np.resize(order, (1 + a.reps) * per)[r * per:(r + 1) * per])
     f._call("fsk_accumulate_combos", q.ctypes.data_as(_lib.c_i32p), len(q), 1)
     if r == 0:
         s0 = f.stats()
+        t0 = time.perf_counter()
+wall_ms = (time.perf_counter() - t0) * 1e3
 s1 = f.stats()
 d = {k: s1[k] - s0[k] for k in s1 if k.startswith("ms_") or k in ("pair_updates", "entries", "runs", "combos_done", "kernel_launches")}
+d["wall_ms"] = wall_ms
+d["combos_per_s"] = d["combos_done"] / wall_ms * 1e3
 print({k: (round(v, 3) if isinstance(v, float) else v) for k, v in d.items()})
 print({k: s1[k] for k in ("nfeat", "n_pairs", "key_bits", "id_bits", "record_bytes", "sort_passes", "batch")})
