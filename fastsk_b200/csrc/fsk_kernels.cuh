@@ -554,7 +554,7 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
 // memory atomics; units that straddle a range end are masked.
 __device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
     uint4 v;
-    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
 
