@@ -352,8 +352,18 @@ onesweep_kernel(const RecT* __restrict__ in, RecT* __restrict__ out, const uint3
 // compaction pass: the sorted records themselves are the entry list (ids ascend inside a run because the
 // sort is stable).
 //
-// Outputs: ids[i] = seq(i) (IdT = u16 when N <= 65536, else u32), and the tasks filed by row:
-//   task[woff[b] + fill[b]++] = (rs, ge - rs + 1)          (a sequence has exactly as many tasks as windows).
+// Outputs:
+//   ids   the sequence id of every sorted record (IdT = u16 when N <= 65000, else u32), with every RUN
+//         ALIGNED: run q starts at X_q = sum over earlier runs of their length rounded up to the alignment
+//         (pad_mask + 1 ids: one 16-byte unit, or one 128-byte line when that costs little memory).  The cells
+//         between a run's end and the next run's start keep the 0xFF.. fill the host put there.  A task's
+//         prefix then starts on a unit boundary, and whatever follows its last id inside the last unit is
+//         either a larger id of the same run or fill: the accumulate needs no masks, only min(id, b + 1).
+//   task  filed by row: task[woff[b] + fill[b]++] = (X_run >> unit_shift, ge - rs + 1); a sequence has exactly
+//         as many tasks as windows.
+// X(i) = exclusive prefix sum, over sorted positions e < i, of [e is the last record of its run] x
+// roundup(run length): a warp scan, a CTA scan, and a decoupled look-back over the tiles of the slot (tiles
+// take tickets, slot-major, so that the task array being filled stays L2-resident).
 // A warp owns SEG_ROWS x 32 consecutive records; run heads / group tails are warp ballots, so the last
 // head at or before a record and the first tail at or after it are bit scans.
 constexpr int SEG_THREADS = 256;
@@ -375,17 +385,23 @@ struct RecOps {
 
 template <typename RecT, bool KV, typename IdT>
 __global__ void __launch_bounds__(SEG_THREADS, (sizeof(RecT) == 4 ? 3 : 2))
-segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, uint32_t n, size_t ids_stride, int idbits,
-               uint32_t nseq, uint32_t* __restrict__ fill, IdT* __restrict__ ids,
-               uint2* __restrict__ task, uint32_t* __restrict__ unsorted_flag, unsigned long long* __restrict__ stat_counters) {
+segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, uint32_t n, uint32_t tiles_per_slot,
+               size_t ids_stride, int idbits, uint32_t nseq, int unit_shift, uint32_t pad_mask, uint32_t* __restrict__ fill,
+               IdT* __restrict__ ids, uint2* __restrict__ task, uint32_t* __restrict__ scan_status /* [slot][tile] */,
+               uint32_t* __restrict__ ticket, uint32_t* __restrict__ unsorted_flag,
+               unsigned long long* __restrict__ stat_counters) {
     using Ops = RecOps<RecT, KV>;
-    const int slot = blockIdx.y;
+    __shared__ uint32_t s_ticket, s_tile_base, s_warp_tot[SEG_THREADS / 32];
+    if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t slot = s_ticket / tiles_per_slot;
+    const uint32_t tile = s_ticket - slot * tiles_per_slot;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t sbase = (size_t)slot * n;
     const RecT* __restrict__ R = rec + sbase;
     const uint32_t* __restrict__ V = KV ? val + sbase : nullptr;
-    const uint32_t seg0 = blockIdx.x * SEG_TILE + warp * SEG_WARP_RECS;
-    if (seg0 >= n) return;
+    const uint32_t seg0 = tile * SEG_TILE + warp * SEG_WARP_RECS;
+    const bool live = seg0 < n;                              // the last tile's trailing warps own no records
     const RecT idmask = KV ? (RecT)0 : (((RecT)1 << idbits) - 1);
 
     RecT r[SEG_ROWS];
@@ -403,11 +419,11 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
     // the records just outside the warp's segment
     RecT r_before = 0, r_after = 0;
     uint32_t s_before = 0, s_after = 0;
-    const uint32_t seg_end = min(seg0 + SEG_WARP_RECS, n);   // exclusive
-    if (seg0 > 0) { r_before = R[seg0 - 1]; if (KV) s_before = V[seg0 - 1]; }
-    if (seg_end < n) { r_after = R[seg_end]; if (KV) s_after = V[seg_end]; }
+    const uint32_t seg_end = live ? min(seg0 + SEG_WARP_RECS, n) : seg0;   // exclusive
+    if (live && seg0 > 0) { r_before = R[seg0 - 1]; if (KV) s_before = V[seg0 - 1]; }
+    if (live && seg_end < n) { r_after = R[seg_end]; if (KV) s_after = V[seg_end]; }
 
-    uint32_t hm[SEG_ROWS], tm[SEG_ROWS];   // run-head / group-tail ballots (warp-uniform)
+    uint32_t hm[SEG_ROWS], tm[SEG_ROWS], rtm[SEG_ROWS];   // run-head / group-tail / run-tail ballots (warp-uniform)
     uint32_t n_groups = 0;
 #pragma unroll
     for (int k = 0; k < SEG_ROWS; ++k) {
@@ -427,31 +443,32 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
         const bool head = valid && (i == 0 || !Ops::same_key(pr, r[k], idbits));
         const bool ghead = valid && (i == 0 || pr != r[k] || (KV && ps != sq[k]));
         const bool tail = valid && (i + 1 >= n || nr != r[k] || (KV && ns != sq[k]));
+        const bool rtail = valid && (i + 1 >= n || !Ops::same_key(nr, r[k], idbits));
         // the sort must have left the records non-decreasing (key, then sequence id): see onesweep_kernel
         if (valid && i > 0 && (KV ? (pr > r[k] || (pr == r[k] && ps > sq[k])) : pr > r[k])) *unsorted_flag = 1u;
         hm[k] = __ballot_sync(0xffffffffu, head);
         tm[k] = __ballot_sync(0xffffffffu, tail);
+        rtm[k] = __ballot_sync(0xffffffffu, rtail);
         n_groups += __popc(__ballot_sync(0xffffffffu, ghead));
     }
 
     // run start of the segment's first record when its run began before the segment: walk back in blocks of 32
     // (typical runs are short), then lower_bound over the sorted records for very long runs
     uint32_t carry_head = seg0;
-    if (seg0 > 0 && !(hm[0] & 1u)) {
+    if (live && seg0 > 0 && !(hm[0] & 1u)) {
         const RecT r_first = __shfl_sync(0xffffffffu, r[0], 0);
-        uint32_t lo_known = 0;              // a position known to be <= the run start
         bool found = false;
         uint32_t p = seg0;                  // records [p, seg0) all have the key of r_first
         for (int step = 0; step < 8 && p > 0 && !found; ++step) {
             const uint32_t j = p - 1 - lane;               // may wrap below 0
-            const bool inb = lane < p;
+            const bool inb = (uint32_t)lane < p;
             const bool differs = inb && !Ops::same_key(R[inb ? j : 0], r_first, idbits);
             const uint32_t dm = __ballot_sync(0xffffffffu, differs);
             if (dm) { p = p - (__ffs(dm) - 1); found = true; }      // first differing record going backwards is at p-1-l
             else p = p > 32 ? p - 32 : 0;
         }
-        if (!found && p > 0) {              // lower_bound of the key in [lo_known, p)
-            uint32_t lo = lo_known, hi = p;
+        if (!found && p > 0) {              // lower_bound of the key in [0, p)
+            uint32_t lo = 0, hi = p;
             while (lo < hi) {
                 const uint32_t mid = lo + ((hi - lo) >> 1);
                 if (Ops::key_less(R[mid], r_first, idbits)) lo = mid + 1;
@@ -502,8 +519,42 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
             }
         }
     }
-    // file the tasks: all the atomics of half the rows in flight before the first dependent store
+
+    // aligned position of every record's run: exclusive scan of the rounded-up lengths of the runs that END before it
+    uint32_t xs[SEG_ROWS];
+    uint32_t wtot = 0;                      // warp-uniform running total
+#pragma unroll
+    for (int k = 0; k < SEG_ROWS; ++k) {
+        xs[k] = wtot;
+        if (rtm[k]) {                       // warp-uniform: most rows of long runs hold no run end
+            const uint32_t i = seg0 + k * 32 + lane;
+            const uint32_t c = ((rtm[k] >> lane) & 1u) ? ((i - rs[k] + 1 + pad_mask) & ~pad_mask) : 0u;
+            uint32_t inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            xs[k] += inc - c;
+            wtot += __shfl_sync(0xffffffffu, inc, 31);
+        }
+    }
+    if (lane == 0) s_warp_tot[warp] = wtot;
+    __syncthreads();
+    uint32_t wbase = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < SEG_THREADS / 32; ++w) {
+        const uint32_t t = s_warp_tot[w];
+        if (w < warp) wbase += t;
+        tile_total += t;
+    }
+    uint32_t* __restrict__ st = scan_status + (size_t)slot * tiles_per_slot;
+    if (threadIdx.x == 0 && tile > 0) st_volatile_u32(st + tile, tile_total | 0x40000000u);
+
+    // file the tasks: all the atomics of half the rows in flight before the first dependent store; the look-back of
+    // the tile's base runs under the first half's atomics
     constexpr int HALF = SEG_ROWS / 2;
+    uint32_t base = 0;
 #pragma unroll
     for (int h0 = 0; h0 < SEG_ROWS; h0 += HALF) {
         uint32_t pos[HALF];                      // fill[] starts at woff[seq]: the atomic returns the task's address
@@ -513,12 +564,39 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
             pos[k] = 0;
             if (i < n) pos[k] = atomicAdd(&fill[(size_t)slot * nseq + sq[h0 + k]], 1u);
         }
+        if (h0 == 0) {
+            if (warp == 0) {
+                uint32_t excl = 0;
+                if (tile > 0) {
+                    int64_t pt = (int64_t)tile - 1;
+                    while (true) {
+                        const int64_t mine = pt - lane;
+                        uint32_t v = 0x80000000u;            // before the slot's first tile: inclusive 0
+                        if (mine >= 0) {
+                            do { v = ld_volatile_u32(st + mine); } while ((v >> 30) == 0);
+                        }
+                        const uint32_t inclusive = __ballot_sync(0xffffffffu, (v >> 31) != 0);
+                        const bool take = inclusive == 0 || lane <= __ffs(inclusive) - 1;
+                        excl += __reduce_add_sync(0xffffffffu, take ? (v & 0x3fffffffu) : 0u);
+                        if (inclusive) break;
+                        pt -= 32;
+                    }
+                }
+                if (lane == 0) {
+                    s_tile_base = excl;
+                    st_volatile_u32(st + tile, (excl + tile_total) | 0x80000000u);
+                }
+            }
+            __syncthreads();
+            base = s_tile_base + wbase;
+        }
 #pragma unroll
         for (int k = 0; k < HALF; ++k) {
             const uint32_t i = seg0 + (h0 + k) * 32 + lane;
             if (i < n) {
-                ids[(size_t)slot * ids_stride + i] = (IdT)sq[h0 + k];
-                task[sbase + pos[k]] = make_uint2(rs[h0 + k], len[h0 + k]);
+                const uint32_t X = base + xs[h0 + k];
+                ids[(size_t)slot * ids_stride + X + (i - rs[h0 + k])] = (IdT)sq[h0 + k];
+                task[sbase + pos[k]] = make_uint2(X >> unit_shift, len[h0 + k]);
                 updates += len[h0 + k];
             }
         }
@@ -538,8 +616,8 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
 }
 
 // ------------------------------------------------------------------------------------------
-// accumulate (shared.cpp:316-327): K[b][ids[j]] += 1 for every task (rs, len) of row b and every j in
-// [rs, rs + len).
+// accumulate (shared.cpp:316-327): K[b][ids[j]] += 1 for every task (first unit u, length len) of row b
+// and every j in [u * PER, u * PER + len).
 //
 // Measured on B200 (profiles/r01_atomic_microbench.txt): scattered RED into the 10 GB packed triangle
 // runs at 20 G updates/s (DRAM sector read-modify-write), L2-resident at 210 G/s, shared-memory atomics
@@ -547,39 +625,46 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
 // combinations, keeps it in shared memory (4 B x (b+1) <= 227 KB), streams the id ranges of its tasks and
 // adds the row to HBM once per batch.
 //
-// The id ranges are read in aligned 16-byte units (8 u16 ids).  A warp takes 32 tasks (one coalesced
+// The id ranges are read in aligned 16-byte units (PER = 8 u16 ids).  A warp takes 32 tasks (one coalesced
 // load), cuts their ranges into units, and deals the concatenated units over its lanes 32 at a time
 // (load-balanced expansion: the task owning position i is the number of task starts at or before i), so
-// every load instruction is 32 x 16 B in a handful of cache lines and every lane then issues 8 shared-
-// memory atomics; units that straddle a range end are masked.
+// every load instruction is 32 x 16 B in a handful of cache lines and every lane then issues PER shared-
+// memory atomics.  Runs start on unit boundaries (segment_kernel), so only the LAST unit of a task can hold
+// ids that are not part of it, and those are larger than b (later sequences of the run, or the 0xFF.. fill):
+// min(id, b + 1 + lane) sends them to one of 32 dump words behind the row -- no masks, no branches.
+// HINT: L2 prefetch size attached to the streaming load (0 = 64 B, 1 = none, 2 = 128 B) -- an experiment knob
+template <int HINT>
 __device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
     uint4 v;
-    asm("ld.global.nc.L1::no_allocate.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    if (HINT == 0) asm("ld.global.nc.L1::no_allocate.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    else if (HINT == 1) asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    else asm("ld.global.nc.L1::no_allocate.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
 
-// masked-off ids (outside the task's range) go to a per-lane dump word behind the row instead of branching
+__device__ __forceinline__ void smem_inc(uint32_t* row, uint32_t byte_off) {
+    atomicAdd(reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(row) + byte_off), 1u);
+}
+
 template <typename IdT>
-__device__ __forceinline__ void apply_unit(uint32_t* row, const uint4 v, const uint32_t msk, const uint32_t dump) {
+__device__ __forceinline__ void apply_unit(uint32_t* row, const uint4 v, const uint32_t dump) {
     if (sizeof(IdT) == 2) {
-        const uint32_t i0 = (msk & 1u) ? (v.x & 0xffffu) : dump, i1 = (msk & 2u) ? (v.x >> 16) : dump;
-        const uint32_t i2 = (msk & 4u) ? (v.y & 0xffffu) : dump, i3 = (msk & 8u) ? (v.y >> 16) : dump;
-        const uint32_t i4 = (msk & 16u) ? (v.z & 0xffffu) : dump, i5 = (msk & 32u) ? (v.z >> 16) : dump;
-        const uint32_t i6 = (msk & 64u) ? (v.w & 0xffffu) : dump, i7 = (msk & 128u) ? (v.w >> 16) : dump;
-        atomicAdd(&row[i0], 1u); atomicAdd(&row[i1], 1u); atomicAdd(&row[i2], 1u); atomicAdd(&row[i3], 1u);
-        atomicAdd(&row[i4], 1u); atomicAdd(&row[i5], 1u); atomicAdd(&row[i6], 1u); atomicAdd(&row[i7], 1u);
+        const uint32_t d2 = dump | (dump << 16);           // dump <= 0xffff whenever ids are 16-bit
+        const uint32_t a = __vminu2(v.x, d2), b = __vminu2(v.y, d2), c = __vminu2(v.z, d2), d = __vminu2(v.w, d2);
+        smem_inc(row, (a << 2) & 0x3fffcu); smem_inc(row, (a >> 14) & 0x3fffcu);
+        smem_inc(row, (b << 2) & 0x3fffcu); smem_inc(row, (b >> 14) & 0x3fffcu);
+        smem_inc(row, (c << 2) & 0x3fffcu); smem_inc(row, (c >> 14) & 0x3fffcu);
+        smem_inc(row, (d << 2) & 0x3fffcu); smem_inc(row, (d >> 14) & 0x3fffcu);
     } else {
-        const uint32_t i0 = (msk & 1u) ? v.x : dump, i1 = (msk & 2u) ? v.y : dump;
-        const uint32_t i2 = (msk & 4u) ? v.z : dump, i3 = (msk & 8u) ? v.w : dump;
-        atomicAdd(&row[i0], 1u); atomicAdd(&row[i1], 1u); atomicAdd(&row[i2], 1u); atomicAdd(&row[i3], 1u);
+        atomicAdd(&row[min(v.x, dump)], 1u); atomicAdd(&row[min(v.y, dump)], 1u);
+        atomicAdd(&row[min(v.z, dump)], 1u); atomicAdd(&row[min(v.w, dump)], 1u);
     }
 }
 
 // grid = (rows of this wave, groups): CTA x owns row b = row_hi - x; the slots [group * slots_per_group,
 // +slots_per_group) add into the same K.  The host launches the rows in waves of a few CTAs per SM, longest
-// rows first: the CTAs of a wave walk the slots in the same order at the same pace, so the id arrays of only
-// a few slots are live in L2 at any time and every id is fetched from HBM about once per wave, not once per row.
-template <typename AccT, typename IdT, int UNROLL>
+// rows first.
+template <typename AccT, typename IdT, int UNROLL, int HINT>
 __global__ void __launch_bounds__(1024)
 accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uint2* __restrict__ task,
                        const uint32_t* __restrict__ woff, uint32_t n, uint32_t row_hi, int slots_per_group,
@@ -595,7 +680,7 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
     const uint32_t cps = (nw + 31) >> 5;                     // chunks of 32 tasks per slot
     const uint32_t nchunks = cps * (uint32_t)slots_per_group;
     if (threadIdx.x == 0) next_chunk = 0;
-    for (uint32_t i = threadIdx.x; i <= b; i += blockDim.x) row[i] = 0;
+    for (uint32_t i = threadIdx.x; i <= b + 32; i += blockDim.x) row[i] = 0;
     __syncthreads();
     const uint32_t lane_le = 0xffffffffu >> (31 - lane);
     const uint32_t dump = b + 1 + lane;                      // 32 words behind the row
@@ -607,11 +692,10 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
         const uint32_t s = c / cps;
         const uint32_t t = ((c - s * cps) << 5) + lane;
         const size_t slot = (size_t)group * slots_per_group + s;
-        const IdT* __restrict__ ip = ids + slot * ids_stride;
+        const uint4* __restrict__ ip = reinterpret_cast<const uint4*>(ids + slot * ids_stride);   // ids_stride is a multiple of 64
         uint2 q = make_uint2(0, 0);
         if (t < nw) q = task[slot * n + wb + t];
-        const uint32_t rs = q.x, end = q.x + q.y;
-        const uint32_t my_units = q.y ? ((end + PER - 1) >> SH) - (rs >> SH) : 0u;
+        const uint32_t my_units = (q.y + PER - 1) >> SH;
         uint32_t incl = my_units;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -620,11 +704,10 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
         }
         const uint32_t P = incl - my_units;                 // first position of this lane's task in the concatenation
         const uint32_t W = __shfl_sync(0xffffffffu, incl, 31);
-        const uint32_t u0 = (rs >> SH) - P;                  // unit index = u0[owner] + position
+        const uint32_t u0 = q.x - P;                         // unit index = u0[owner] + position
         uint32_t started = 0;
         for (uint32_t base = 0; base < W; base += 32 * UNROLL) {
             uint4 v[UNROLL];
-            uint32_t msk[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const uint32_t wbase = base + 32 * u;
@@ -632,20 +715,12 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
                 const uint32_t m = __reduce_or_sync(0xffffffffu, (rel < 32u && my_units) ? (1u << rel) : 0u);
                 const uint32_t j = (started + __popc(m & lane_le) - 1) & 31;
                 started += __popc(m);
-                const uint32_t a = (__shfl_sync(0xffffffffu, u0, j) + wbase + lane) << SH;   // first id of the unit
-                const uint32_t trs = __shfl_sync(0xffffffffu, rs, j);
-                const uint32_t tend = __shfl_sync(0xffffffffu, end, j);
-                msk[u] = 0;
-                v[u] = make_uint4(0, 0, 0, 0);
-                if (wbase + lane < W) {
-                    v[u] = ldg_stream_u4(ip + a);
-                    const uint32_t lo = max(trs, a) - a, hi = min(tend, a + PER) - a;
-                    msk[u] = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
-                }
+                const uint32_t unit = __shfl_sync(0xffffffffu, u0, j) + wbase + lane;
+                if (wbase + lane < W) v[u] = ldg_stream_u4<HINT>(ip + unit);
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u)
-                if (base + 32 * u < W) apply_unit<IdT>(row, v[u], msk[u], dump);   // warp-uniform skip of empty tail windows
+                if (base + 32 * u + lane < W) apply_unit<IdT>(row, v[u], dump);
         }
     }
     __syncthreads();
@@ -663,6 +738,7 @@ template <typename AccT, typename IdT>
 __global__ void __launch_bounds__(256)
 accumulate_global_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uint2* __restrict__ task,
                          const uint32_t* __restrict__ wseq, uint32_t n, AccT* __restrict__ K, size_t k_slot_stride) {
+    constexpr int PER = 16 / sizeof(IdT);
     const int slot = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const uint32_t t0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 32;
@@ -672,7 +748,7 @@ accumulate_global_kernel(const IdT* __restrict__ ids, size_t ids_stride, const u
         const uint2 q = task[(size_t)slot * n + t];
         const size_t b = wseq[t];
         AccT* __restrict__ Krow = Ks + (b * (b + 1) >> 1);
-        for (uint32_t a = lane; a < q.y; a += 32) atomicAdd(&Krow[ip[q.x + a]], (AccT)1);
+        for (uint32_t a = lane; a < q.y; a += 32) atomicAdd(&Krow[ip[(size_t)q.x * PER + a]], (AccT)1);
     }
 }
 

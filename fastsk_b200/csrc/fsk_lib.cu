@@ -22,6 +22,7 @@ namespace {
 std::string g_create_error;
 
 enum RecMode { MODE_R32 = 0, MODE_R64 = 1, MODE_KV = 2 };
+constexpr int SEG_TICKET = 16;   // d_ticket[0 .. MAX_PASS) belong to the sort passes
 enum ProfClass { PC_PACK = 0, PC_SORT, PC_SEGMENT, PC_ACCUMULATE, PC_WELFORD, PC_NORMALISE, PC_COUNT };
 
 struct ProfSpan {
@@ -48,6 +49,8 @@ struct fsk_handle {
     int opt_rows_threads = 0;        // threads per row CTA of the accumulate (0 = by N)
     int opt_overlap = 0;             // 1 = pre-pass of the next batch on its own low-priority stream (measured: no gain, the
                                      // row CTAs own the whole SM's shared memory; profiles/r01_overlap_experiment.txt)
+    int opt_ld_hint = 0;             // experiment: L2 prefetch hint of the accumulate's id loads (0 = 64 B, 1 = none, 2 = 128 B)
+    int opt_l2_fetch = 0;            // experiment: cudaLimitMaxL2FetchGranularity (0 = leave alone)
     int opt_wave = 4;                // accumulate launch = opt_wave x (CTAs resident on the chip) rows
     bool profile = false;
     std::string err;
@@ -79,10 +82,12 @@ struct fsk_handle {
     uint32_t *d_valA = nullptr, *d_valB = nullptr;
     unsigned char* d_zero = nullptr;   // [ghist | tickets | status] cleared once per batch
     size_t zero_bytes = 0;
-    uint32_t *d_ghist = nullptr, *d_ticket = nullptr, *d_status = nullptr;
+    uint32_t *d_ghist = nullptr, *d_ticket = nullptr, *d_status = nullptr, *d_seg_status = nullptr;
     uint32_t *d_woff32 = nullptr, *d_fill = nullptr;   // window offsets per sequence; tasks filed so far per (slot, sequence)
     void* d_ids[2] = {nullptr, nullptr};               // sequence id of every sorted record (u16 when N <= 65536, else u32); double-buffered
     size_t ids_stride = 0;                             // per-slot stride of d_ids, a multiple of 64 elements
+    uint32_t pad_mask = 7;                             // runs start on multiples of pad_mask + 1 ids in d_ids (a 16-byte unit or a 128-byte line)
+    int opt_pad = 0;                                   // 0 auto, 1 unit, 2 line
     bool ids16 = false;
     uint2* d_task[2] = {nullptr, nullptr};
     bool rows_path = false;
@@ -156,7 +161,7 @@ void release_device(fsk_handle* h) {
     dev_free(h->d_gw0); dev_free(h->d_gw1); dev_free(h->d_wseq);
     dev_free(h->d_recA); dev_free(h->d_recB); dev_free(h->d_valA); dev_free(h->d_valB);
     dev_free(h->d_zero);
-    h->d_ghist = h->d_ticket = h->d_status = nullptr;
+    h->d_ghist = h->d_ticket = h->d_status = h->d_seg_status = nullptr;
     dev_free(h->d_woff32); dev_free(h->d_fill);
     for (int i = 0; i < 2; ++i) { dev_free(h->d_ids[i]); dev_free(h->d_task[i]); }
     dev_free(h->d_Kint); dev_free(h->d_Kf);
@@ -290,18 +295,21 @@ int launch_sort(fsk_handle* h, int nb) {
 template <typename RecT, bool KV>
 int launch_segment(fsk_handle* h, int nb) {
     const uint32_t n = (uint32_t)h->nfeat;
-    dim3 grid(h->seg_tiles, nb);
     unsigned long long* stat = h->profile ? h->d_counters : nullptr;
     init_fill_kernel<<<dim3((unsigned)((h->N + 255) / 256), nb), 256, 0, h->ls>>>(h->d_fill, h->d_woff32, (uint32_t)h->N);
     h->launches++;
+    // the gaps between the aligned runs must read as "no sequence": 0xFF.. clamps to the dump word in the accumulate
+    CU(cudaMemsetAsync(h->d_ids[h->buf], 0xff, (size_t)nb * h->ids_stride * (h->ids16 ? 2 : 4), h->ls));
+    const unsigned grid = h->seg_tiles * (unsigned)nb;
+    const int ush = h->ids16 ? 3 : 2;
     if (h->ids16)
-        segment_kernel<RecT, KV, uint16_t><<<grid, SEG_THREADS, 0, h->ls>>>((const RecT*)h->d_recA, h->d_valA, n, h->ids_stride, h->idbits,
-                                                                                (uint32_t)h->N, h->d_fill, (uint16_t*)h->d_ids[h->buf],
-                                                                                h->d_task[h->buf], h->d_flag, stat);
+        segment_kernel<RecT, KV, uint16_t><<<grid, SEG_THREADS, 0, h->ls>>>((const RecT*)h->d_recA, h->d_valA, n, h->seg_tiles, h->ids_stride, h->idbits,
+                                                                                (uint32_t)h->N, ush, h->pad_mask, h->d_fill, (uint16_t*)h->d_ids[h->buf],
+                                                                                h->d_task[h->buf], h->d_seg_status, h->d_ticket + SEG_TICKET, h->d_flag, stat);
     else
-        segment_kernel<RecT, KV, uint32_t><<<grid, SEG_THREADS, 0, h->ls>>>((const RecT*)h->d_recA, h->d_valA, n, h->ids_stride, h->idbits,
-                                                                                (uint32_t)h->N, h->d_fill, (uint32_t*)h->d_ids[h->buf],
-                                                                                h->d_task[h->buf], h->d_flag, stat);
+        segment_kernel<RecT, KV, uint32_t><<<grid, SEG_THREADS, 0, h->ls>>>((const RecT*)h->d_recA, h->d_valA, n, h->seg_tiles, h->ids_stride, h->idbits,
+                                                                                (uint32_t)h->N, ush, h->pad_mask, h->d_fill, (uint32_t*)h->d_ids[h->buf],
+                                                                                h->d_task[h->buf], h->d_seg_status, h->d_ticket + SEG_TICKET, h->d_flag, stat);
     h->launches++;
     CU(cudaGetLastError());
     return FSK_OK;
@@ -317,7 +325,10 @@ int launch_accumulate(fsk_handle* h, int nb, unsigned long long* K, size_t slot_
         const int wave = std::max(1, h->wave_rows / groups);
         for (int64_t hi = h->N - 1; hi >= 0; hi -= wave) {
             dim3 grid((unsigned)std::min<int64_t>(wave, hi + 1), groups);
-            accumulate_rows_kernel<unsigned long long, IdT, 4><<<grid, h->rows_threads, h->rows_smem, h->ls>>>(
+            auto kern = h->opt_ld_hint == 1 ? accumulate_rows_kernel<unsigned long long, IdT, 4, 1>
+                        : h->opt_ld_hint == 2 ? accumulate_rows_kernel<unsigned long long, IdT, 4, 2>
+                                              : accumulate_rows_kernel<unsigned long long, IdT, 4, 0>;
+            kern<<<grid, h->rows_threads, h->rows_smem, h->ls>>>(
                 ids, h->ids_stride, h->d_task[h->buf], h->d_woff32, n, (uint32_t)hi, per_group, K, slot_stride);
             h->launches++;
         }
@@ -540,6 +551,13 @@ int fsk_set_option(fsk_handle* h, const char* key, int64_t value) {
     } else if (!strcmp(key, "wave")) {
         if (value < 1 || value > 1024) return fail(h, FSK_EINVAL, "wave must be in [1, 1024]");
         h->opt_wave = (int)value;
+    } else if (!strcmp(key, "pad")) {
+        if (value < 0 || value > 2) return fail(h, FSK_EINVAL, "pad must be 0 (auto), 1 (16-byte units) or 2 (128-byte lines)");
+        h->opt_pad = (int)value;
+    } else if (!strcmp(key, "ld_hint")) {
+        h->opt_ld_hint = (int)value;
+    } else if (!strcmp(key, "l2_fetch")) {
+        h->opt_l2_fetch = (int)value;
     } else if (!strcmp(key, "profile")) {
         h->profile = value != 0;
     } else {
@@ -654,21 +672,41 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     h->rows_smem = (size_t)N * 4 + 128;   // + one dump word per lane for masked-off ids
     h->rows_threads = N >= 16384 ? 1024 : (N >= 4096 ? 512 : 256);
     if (h->opt_rows_threads) h->rows_threads = h->opt_rows_threads;
-    h->ids16 = N <= 65536;
-    h->ids_stride = (size_t)((nfeat + 8 + 63) / 64 * 64);
+    h->ids16 = N <= 65000;   // u16 ids leave room for the 32 dump words b + 1 + lane (packed 16-bit min in the accumulate)
+    {
+        // runs of the id stream are aligned (segment_kernel): to one 16-byte unit always, to a 128-byte line when the
+        // padding costs at most half of the stream again (few, long runs -- the HBM fetches whole lines either way)
+        const int64_t unit = h->ids16 ? 8 : 4, line = unit * 8;
+        const int64_t max_runs = h->keybits >= 31 ? nfeat : std::min<int64_t>(nfeat, (int64_t)1 << h->keybits);
+        const bool line_ok = (line - 1) * max_runs <= nfeat / 2;
+        const int64_t align = h->opt_pad == 1 ? unit : (h->opt_pad == 2 ? line : (line_ok ? line : unit));
+        h->pad_mask = (uint32_t)(align - 1);
+        const int64_t cap = nfeat + (align - 1) * max_runs + 64;
+        if (cap >= (1LL << 30)) return fail(h, FSK_EINVAL, "too many g-mers (%lld) for the aligned id stream", (long long)nfeat);
+        h->ids_stride = (size_t)((cap + 63) / 64 * 64);
+    }
     {
         // rows per accumulate launch: the CTAs resident at once, times opt_wave (default 1)
         const int per_sm = std::max(1, std::min(2048 / h->rows_threads, (int)((size_t)(max_smem + 1024) / (h->rows_smem + 1024))));
         h->wave_rows = n_sm * per_sm * std::max(1, h->opt_wave);
     }
     if (h->rows_path) {
-        if (h->ids16) CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-        else CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
+        if (h->ids16) {
+            CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
+            CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
+            CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
+        } else {
+            CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
+            CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
+            CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
+        }
+        if (h->opt_l2_fetch) CU(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)h->opt_l2_fetch));
     }
 
     // batch: combinations per launch group.  The row path flushes every row of K once per batch, so it
     // wants the batch as large as memory allows; the u32 shared-memory accumulators bound it by 2^32 / maxwin^2.
-    const int64_t per_slot_bytes = nfeat * (2 * (h->mode == MODE_R32 ? 4 : 8) + (h->mode == MODE_KV ? 8 : 0) + 2 * (8 + (h->ids16 ? 2 : 4))) +
+    const int64_t per_slot_bytes = nfeat * (2 * (h->mode == MODE_R32 ? 4 : 8) + (h->mode == MODE_KV ? 8 : 0) + 2 * 8) +
+                                   2 * (int64_t)h->ids_stride * (h->ids16 ? 2 : 4) +
                                    (int64_t)h->plan.npass * ((nfeat + 3071) / 3072) * RADIX * 4 + N * 4 + 4096;
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
@@ -729,11 +767,13 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     const size_t ghist_words = (size_t)B * MAX_PASS * RADIX, ticket_words = 64;
     const size_t rowcount_words = 0;
     const size_t status_words = (size_t)h->plan.npass * B * h->sort_tiles * RADIX;
-    h->zero_bytes = 4 * (ghist_words + ticket_words + status_words + rowcount_words);
+    const size_t seg_status_words = (size_t)B * h->seg_tiles;
+    h->zero_bytes = 4 * (ghist_words + ticket_words + status_words + seg_status_words + rowcount_words);
     ALLOC(h->d_zero, h->zero_bytes);
     h->d_ghist = (uint32_t*)h->d_zero;
     h->d_ticket = h->d_ghist + ghist_words;
     h->d_status = h->d_ticket + ticket_words;
+    h->d_seg_status = h->d_status + status_words;
     for (int i = 0; i < 2; ++i) {
         unsigned char* p;
         ALLOC(p, (size_t)B * h->ids_stride * (h->ids16 ? 2 : 4));

@@ -27,6 +27,9 @@ ap.add_argument("--batches-per-call", type=int, default=1)
 ap.add_argument("--wave", type=int, default=4)
 ap.add_argument("--overlap", type=int, default=0)
 ap.add_argument("--rows-threads", type=int, default=0)
+ap.add_argument("--ld-hint", type=int, default=0)
+ap.add_argument("--pad", type=int, default=0)
+ap.add_argument("--l2-fetch", type=int, default=0)
 a = ap.parse_args()
 
 X = np.random.default_rng(0).integers(1, a.alphabet + 1, size=(a.n, a.len), dtype=np.int32)
@@ -37,6 +40,9 @@ f.set_option("acc_path", a.acc_path)
 f.set_option("wave", a.wave)
 f.set_option("overlap", a.overlap)
 f.set_option("rows_threads", a.rows_threads)
+f.set_option("ld_hint", a.ld_hint)
+f.set_option("pad", a.pad)
+f.set_option("l2_fetch", a.l2_fetch)
 codes = np.ascontiguousarray(X.reshape(-1))
 offsets = np.arange(a.n + 1, dtype=np.int64) * a.len
 f._call("fsk_upload", codes.ctypes.data_as(_lib.c_i32p), offsets.ctypes.data_as(_lib.c_i64p), int(a.n * 0.8), a.n - int(a.n * 0.8))
