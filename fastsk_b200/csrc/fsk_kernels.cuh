@@ -21,7 +21,7 @@
 namespace fsk {
 
 constexpr int MAX_K = 32;        // kept positions per combination
-constexpr int MAX_BATCH = 48;    // combinations per launch group (kernel-parameter budget)
+constexpr int MAX_BATCH = 96;    // combinations per launch group (BatchSpec travels in kernel-parameter space: 6.2 KB of the 32 KB)
 constexpr int MAX_PASS = 8;      // 64 key bits / 8
 constexpr int RADIX = 256;
 constexpr int SORT_THREADS = 256;
@@ -102,7 +102,22 @@ __global__ void build_gwords_kernel(const uint8_t* __restrict__ codes, const int
 }
 
 // ------------------------------------------------------------------------------------------
-// pack + histogram.  grid = (tiles, slots).
+// pack + histogram.  grid = (slots, tiles): CTAs launched together read the same windows for different
+// combinations, so the g-mer words come from HBM once per batch and from L2 for the other slots.
+//
+// A stretch of kept characters moves from bit `src` of the g-mer word to bit `dst` of the key: one rotate and
+// one masked OR (key |= rotr(word, src - dst) & (mask << dst)).  A thread packs PACK_SUB windows at a time: the
+// stretch and digit descriptors are read from parameter space once per sub-batch (uniform loads), the inner
+// loops run on registers only, and PACK_SUB loads per array are in flight.
+constexpr int PACK_SUB = 8;
+
+template <typename KeyT>
+__device__ __forceinline__ KeyT rotr_key(KeyT x, uint32_t r) {
+    if (sizeof(KeyT) == 4) return (KeyT)__funnelshift_r((uint32_t)x, (uint32_t)x, r);
+    r &= 63u;
+    return r ? (KeyT)(((uint64_t)x >> r) | ((uint64_t)x << (64u - r))) : x;
+}
+
 template <typename RecT, bool KV, typename GwT, int NW>
 __global__ void __launch_bounds__(256)
 pack_hist_kernel(const GwT* __restrict__ gw0, const uint64_t* __restrict__ gw1, const uint32_t* __restrict__ wseq,
@@ -110,78 +125,68 @@ pack_hist_kernel(const GwT* __restrict__ gw0, const uint64_t* __restrict__ gw1, 
                  const __grid_constant__ BatchSpec spec, const __grid_constant__ SortPlan plan, int idbits) {
     // a 32-bit g-mer word holds a key of at most 32 bits: keep the arithmetic in 32 bits then
     using KeyT = typename std::conditional<sizeof(GwT) == 4, uint32_t, uint64_t>::type;
+    constexpr uint32_t KB = sizeof(KeyT) * 8;
     __shared__ uint32_t sh[MAX_PASS * RADIX];
-    // grid = (slots, tiles): CTAs launched together read the same windows for different combinations, so the g-mer
-    // words come from HBM once per batch and from L2 for the other slots
     const int slot = blockIdx.x;
     const int nseg = spec.nseg[slot];
     const int npass = plan.npass;
     for (int i = threadIdx.x; i < npass * RADIX; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const size_t sbase = (size_t)slot * nfeat;
-    // stretch and digit descriptors live in registers for the whole CTA (read once from parameter space; indexing the
-    // parameters inside the window loop made the kernel issue-bound on constant loads)
-    constexpr int SEGR = 8;
-    uint32_t sg_sh[SEGR], sg_dst[SEGR];
-    KeyT sg_mask[SEGR];
-    {
-        int dst = 0;
-#pragma unroll
-        for (int j = 0; j < SEGR; ++j) {
-            const uint32_t e = j < nseg ? spec.seg[slot][j] : 0u;
-            const int width = (int)(e >> 7) + 1;
-            sg_sh[j] = e & 127u;
-            sg_dst[j] = (uint32_t)dst;
-            sg_mask[j] = j < nseg ? (KeyT)((KeyT) ~(KeyT)0 >> ((int)sizeof(KeyT) * 8 - width)) : (KeyT)0;
-            dst += j < nseg ? width : 0;
-        }
-    }
-    uint32_t dg_sh[MAX_PASS], dg_mask[MAX_PASS];
-#pragma unroll
-    for (int p = 0; p < MAX_PASS; ++p) {
-        dg_sh[p] = p < npass ? plan.shift[p] : 0u;
-        dg_mask[p] = p < npass ? ((1u << plan.bits[p]) - 1u) : 0u;
-    }
-    // a CTA packs PACK_ITEMS x 256 consecutive windows: its 2 x 256 histogram counters go to the slot's global
+    // a CTA packs PACK_ITEMS x 256 consecutive windows: its npass x 256 histogram counters go to the slot's global
     // histogram once, so few CTAs per slot keep the same-address atomics on those few lines off the critical path
     const uint32_t tile0 = blockIdx.y * (256 * PACK_ITEMS);
-#pragma unroll 4
-    for (int it = 0; it < PACK_ITEMS; ++it) {
-        const uint32_t w = tile0 + it * 256 + threadIdx.x;
-        if (w < nfeat) {
-            const uint64_t lo = gw0[w];
-            uint64_t hi = 0;
-            if (NW == 2) hi = gw1[w];
-            KeyT key = 0;
+    for (int it = 0; it < PACK_ITEMS; it += PACK_SUB) {
+        const uint32_t w0 = tile0 + it * 256 + threadIdx.x;
+        if (tile0 + it * 256 >= nfeat) break;
+        KeyT lo[PACK_SUB], hi[NW == 2 ? PACK_SUB : 1], key[PACK_SUB];
+        uint32_t seq[PACK_SUB];
 #pragma unroll
-            for (int j = 0; j < SEGR; ++j) {
-                if (j < nseg) {
-                    const KeyT word = (NW == 2 && (sg_sh[j] & 64u)) ? (KeyT)hi : (KeyT)lo;
-                    key |= ((word >> (sg_sh[j] & 63u)) & sg_mask[j]) << sg_dst[j];
-                }
+        for (int i = 0; i < PACK_SUB; ++i) {
+            const uint32_t w = w0 + i * 256;
+            lo[i] = 0;
+            seq[i] = 0;
+            if (NW == 2) hi[i] = 0;
+            if (w < nfeat) {
+                lo[i] = (KeyT)gw0[w];
+                if (NW == 2) hi[i] = (KeyT)gw1[w];
+                seq[i] = wseq[w];
             }
-            if (nseg > SEGR) {                     // more than SEGR stretches (long k): the rest from parameter space
-                int dst = 0;
-                for (int j = 0; j < nseg; ++j) {
-                    const uint32_t e = spec.seg[slot][j];
-                    const int width = (int)(e >> 7) + 1;
-                    if (j >= SEGR) {
-                        const KeyT word = (NW == 2 && (e & 64u)) ? (KeyT)hi : (KeyT)lo;
-                        key |= ((word >> (e & 63u)) & ((KeyT) ~(KeyT)0 >> ((int)sizeof(KeyT) * 8 - width))) << dst;
-                    }
-                    dst += width;
-                }
-            }
-            const uint32_t seq = wseq[w];
-            if (KV) {
-                rec[sbase + w] = (RecT)key;
-                val[sbase + w] = seq;
+            key[i] = 0;
+        }
+        uint32_t dst = 0;
+        for (int j = 0; j < nseg; ++j) {
+            const uint32_t e = spec.seg[slot][j];
+            const uint32_t src = e & 63u, width = (e >> 7) + 1u;
+            const KeyT m = (KeyT)((KeyT) ~(KeyT)0 >> (KB - width)) << dst;
+            const uint32_t r = (src - dst) & (KB - 1u);
+            if (NW == 2 && (e & 64u)) {
+#pragma unroll
+                for (int i = 0; i < PACK_SUB; ++i) key[i] |= rotr_key<KeyT>(hi[i], r) & m;
             } else {
-                rec[sbase + w] = ((RecT)key << idbits) | (RecT)seq;
-            }
 #pragma unroll
-            for (int p = 0; p < MAX_PASS; ++p)
-                if (p < npass) atomicAdd(&sh[p * RADIX + ((uint32_t)(key >> dg_sh[p]) & dg_mask[p])], 1u);
+                for (int i = 0; i < PACK_SUB; ++i) key[i] |= rotr_key<KeyT>(lo[i], r) & m;
+            }
+            dst += width;
+        }
+#pragma unroll
+        for (int i = 0; i < PACK_SUB; ++i) {
+            const uint32_t w = w0 + i * 256;
+            if (w < nfeat) {
+                if (KV) {
+                    rec[sbase + w] = (RecT)key[i];
+                    val[sbase + w] = seq[i];
+                } else {
+                    rec[sbase + w] = ((RecT)key[i] << idbits) | (RecT)seq[i];
+                }
+            }
+        }
+        for (int p = 0; p < npass; ++p) {
+            const uint32_t dsh = plan.shift[p], dmask = (1u << plan.bits[p]) - 1u;
+            uint32_t* hp = sh + p * RADIX;
+#pragma unroll
+            for (int i = 0; i < PACK_SUB; ++i)
+                if (w0 + i * 256 < nfeat) atomicAdd(&hp[(uint32_t)(key[i] >> dsh) & dmask], 1u);
         }
     }
     __syncthreads();
@@ -367,9 +372,8 @@ onesweep_kernel(const RecT* __restrict__ in, RecT* __restrict__ out, const uint3
 // A warp owns SEG_ROWS x 32 consecutive records; run heads / group tails are warp ballots, so the last
 // head at or before a record and the first tail at or after it are bit scans.
 constexpr int SEG_THREADS = 256;
-constexpr int SEG_ROWS = 16;
-constexpr int SEG_WARP_RECS = SEG_ROWS * 32;
-constexpr int SEG_TILE = (SEG_THREADS / 32) * SEG_WARP_RECS;
+constexpr int SEG_ROWS_DEFAULT = 16;
+__host__ __device__ constexpr int seg_tile_records(int rows) { return (SEG_THREADS / 32) * rows * 32; }
 
 // fill[slot][b] = woff[b]: where the next task of sequence b goes
 __global__ void init_fill_kernel(uint32_t* __restrict__ fill, const uint32_t* __restrict__ woff, uint32_t nseq) {
@@ -383,14 +387,17 @@ struct RecOps {
     static __device__ __forceinline__ bool key_less(RecT a, RecT b, int idbits) { return KV ? a < b : (a >> idbits) < (b >> idbits); }
 };
 
-template <typename RecT, bool KV, typename IdT>
-__global__ void __launch_bounds__(SEG_THREADS, (sizeof(RecT) == 4 ? 3 : 2))
+template <typename RecT, bool KV, typename IdT, int ROWS = SEG_ROWS_DEFAULT, int MINB = (sizeof(RecT) == 4 ? 3 : 2)>
+__global__ void __launch_bounds__(SEG_THREADS, MINB)
 segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, uint32_t n, uint32_t tiles_per_slot,
                size_t ids_stride, int idbits, uint32_t nseq, int unit_shift, uint32_t pad_mask, uint32_t* __restrict__ fill,
                IdT* __restrict__ ids, uint2* __restrict__ task, uint32_t* __restrict__ scan_status /* [slot][tile] */,
                uint32_t* __restrict__ ticket, uint32_t* __restrict__ unsorted_flag,
-               unsigned long long* __restrict__ stat_counters) {
+               unsigned long long* __restrict__ stat_counters, int exp /* timing experiments only: 1-3 file tasks wrongly */) {
     using Ops = RecOps<RecT, KV>;
+    constexpr int SEG_ROWS = ROWS;
+    constexpr int SEG_WARP_RECS = SEG_ROWS * 32;
+    constexpr int SEG_TILE = seg_tile_records(ROWS);
     __shared__ uint32_t s_ticket, s_tile_base, s_warp_tot[SEG_THREADS / 32];
     if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
     __syncthreads();
@@ -562,7 +569,11 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
         for (int k = 0; k < HALF; ++k) {
             const uint32_t i = seg0 + (h0 + k) * 32 + lane;
             pos[k] = 0;
-            if (i < n) pos[k] = atomicAdd(&fill[(size_t)slot * nseq + sq[h0 + k]], 1u);
+            if (i < n) {
+                if (exp == 1) pos[k] = i;                                              // no atomic, coalesced store
+                else if (exp == 3) pos[k] = (uint32_t)(((uint64_t)i * 2654435761u) % n);   // no atomic, scattered store
+                else pos[k] = atomicAdd(&fill[(size_t)slot * nseq + sq[h0 + k]], 1u);
+            }
         }
         if (h0 == 0) {
             if (warp == 0) {
@@ -596,7 +607,7 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
             if (i < n) {
                 const uint32_t X = base + xs[h0 + k];
                 ids[(size_t)slot * ids_stride + X + (i - rs[h0 + k])] = (IdT)sq[h0 + k];
-                task[sbase + pos[k]] = make_uint2(X >> unit_shift, len[h0 + k]);
+                task[sbase + (exp == 2 ? i : pos[k])] = make_uint2(X >> unit_shift, len[h0 + k]);
                 updates += len[h0 + k];
             }
         }
@@ -664,7 +675,7 @@ __device__ __forceinline__ void apply_unit(uint32_t* row, const uint4 v, const u
 // grid = (rows of this wave, groups): CTA x owns row b = row_hi - x; the slots [group * slots_per_group,
 // +slots_per_group) add into the same K.  The host launches the rows in waves of a few CTAs per SM, longest
 // rows first.
-template <typename AccT, typename IdT, int UNROLL, int HINT>
+template <typename AccT, typename IdT, int UNROLL, int HINT, bool PIPE = false>
 __global__ void __launch_bounds__(1024)
 accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uint2* __restrict__ task,
                        const uint32_t* __restrict__ woff, uint32_t n, uint32_t row_hi, int slots_per_group,
@@ -684,17 +695,34 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
     __syncthreads();
     const uint32_t lane_le = 0xffffffffu >> (31 - lane);
     const uint32_t dump = b + 1 + lane;                      // 32 words behind the row
-    while (true) {
+    const uint2* __restrict__ task_g = task + (size_t)group * slots_per_group * n + wb;
+    const IdT* __restrict__ ids_g = ids + (size_t)group * slots_per_group * ids_stride;
+    // chunk c -> (slot, first task); the task of this lane, or an empty one
+    auto grab = [&]() -> uint32_t {
         uint32_t c = 0;
         if (lane == 0) c = atomicAdd(&next_chunk, 1u);
-        c = __shfl_sync(0xffffffffu, c, 0);
-        if (c >= nchunks) break;
-        const uint32_t s = c / cps;
-        const uint32_t t = ((c - s * cps) << 5) + lane;
-        const size_t slot = (size_t)group * slots_per_group + s;
-        const uint4* __restrict__ ip = reinterpret_cast<const uint4*>(ids + slot * ids_stride);   // ids_stride is a multiple of 64
+        return __shfl_sync(0xffffffffu, c, 0);
+    };
+    auto load_task = [&](uint32_t c) -> uint2 {
         uint2 q = make_uint2(0, 0);
-        if (t < nw) q = task[slot * n + wb + t];
+        if (c < nchunks) {
+            const uint32_t s = c / cps;
+            const uint32_t t = ((c - s * cps) << 5) + lane;
+            if (t < nw) q = task_g[(size_t)s * n + t];
+        }
+        return q;
+    };
+    uint32_t c = grab();
+    uint2 q = load_task(c);
+    while (c < nchunks) {
+        const uint32_t s = c / cps;
+        const uint4* __restrict__ ip = reinterpret_cast<const uint4*>(ids_g + (size_t)s * ids_stride);   // ids_stride is a multiple of 64
+        uint32_t c_next = 0;
+        uint2 q_next = make_uint2(0, 0);
+        if (PIPE) {                                          // the next chunk's tasks travel while this chunk is applied
+            c_next = grab();
+            q_next = load_task(c_next);
+        }
         const uint32_t my_units = (q.y + PER - 1) >> SH;
         uint32_t incl = my_units;
 #pragma unroll
@@ -706,8 +734,8 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
         const uint32_t W = __shfl_sync(0xffffffffu, incl, 31);
         const uint32_t u0 = q.x - P;                         // unit index = u0[owner] + position
         uint32_t started = 0;
-        for (uint32_t base = 0; base < W; base += 32 * UNROLL) {
-            uint4 v[UNROLL];
+        // loads of one step: UNROLL x 32 consecutive positions of the concatenation
+        auto issue = [&](uint32_t base, uint4 (&v)[UNROLL]) {
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const uint32_t wbase = base + 32 * u;
@@ -718,9 +746,33 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
                 const uint32_t unit = __shfl_sync(0xffffffffu, u0, j) + wbase + lane;
                 if (wbase + lane < W) v[u] = ldg_stream_u4<HINT>(ip + unit);
             }
+        };
+        auto apply = [&](uint32_t base, const uint4 (&v)[UNROLL]) {
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u)
                 if (base + 32 * u + lane < W) apply_unit<IdT>(row, v[u], dump);
+        };
+        if (PIPE) {
+            uint4 va[UNROLL], vb[UNROLL];
+            issue(0, va);
+            for (uint32_t base = 0; base < W; base += 64 * UNROLL) {   // two steps per trip: the buffers swap by name
+                if (base + 32 * UNROLL < W) issue(base + 32 * UNROLL, vb);
+                apply(base, va);
+                if (base + 32 * UNROLL < W) {
+                    if (base + 64 * UNROLL < W) issue(base + 64 * UNROLL, va);
+                    apply(base + 32 * UNROLL, vb);
+                }
+            }
+            c = c_next;
+            q = q_next;
+        } else {
+            for (uint32_t base = 0; base < W; base += 32 * UNROLL) {
+                uint4 v[UNROLL];
+                issue(base, v);
+                apply(base, v);
+            }
+            c = grab();
+            q = load_task(c);
         }
     }
     __syncthreads();
