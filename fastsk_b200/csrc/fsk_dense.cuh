@@ -1,0 +1,249 @@
+// Dense regime of the accumulate (regime 2): when a combination has few distinct k-mers
+// (alphabet^k at most a few thousand: DNA with k = g - m <= 6, the TFBS configurations of the reference) the
+// count matrix C[sequence][k-mer] is dense and countAndUpdateTri's K[i][j] += c_i * c_j (shared.cpp:304-327)
+// is the contraction K += C * C^T.  Then neither the sort nor the run segmentation is needed:
+//
+//   dense_count_kernel   C[seq][slot * nks + key] = number of windows of `seq` whose kept characters pack to `key`
+//                        (the gather of fastsk_kernel.cpp:224-228 + the counting of shared.cpp:304-315), fp16
+//   syrk_tc_kernel       lower-triangle tiles of C * C^T on the 5th-generation tensor cores: TMA (128-byte swizzle)
+//                        -> shared memory -> tcgen05.mma kind::f16 with fp32 accumulators in TMEM -> tcgen05.ld ->
+//                        integer RED into the packed int64 triangle.  All slots of a batch are one GEMM: the
+//                        contraction dimension is (slots x k-mers).
+//
+// Exactness: counts are integers <= maxwin <= 2048 (exact in fp16), products < 2^22, and the host cuts the
+// contraction dimension so that no fp32 accumulator can exceed 2^24 (slots per GEMM <= 2^24 / maxwin^2): every
+// intermediate is an exactly representable integer, so the result is bit-identical to the integer sum.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include "fsk_kernels.cuh"
+
+namespace fsk {
+
+constexpr int DG_TILE = 128;                                     // output tile: 128 x 128 pairs of sequences
+constexpr int DG_BK = 64;                                        // fp16 elements per k-block = one 128-byte swizzle row
+constexpr int DG_STAGES = 3;                                     // 3 x 32 KB: two CTAs per SM, one's epilogue under the other's MMAs
+constexpr int DG_THREADS = 192;                                  // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr uint32_t DG_TILE_BYTES = DG_TILE * DG_BK * 2;          // 16 KB
+constexpr uint32_t DG_STAGE_BYTES = 2 * DG_TILE_BYTES;           // A rows + B rows
+constexpr uint32_t DG_TMEM_COLS = 128;                           // 128 lanes x 128 fp32 columns
+constexpr size_t DG_SMEM = (size_t)DG_STAGES * DG_STAGE_BYTES + 1024 /* 1024-byte alignment of the swizzle atom */ + 128;
+constexpr int DENSE_MAX_KEYS = 4096;
+
+// ------------------------------------------------------------------------------------------
+// C = per-sequence k-mer counts of every slot.  grid = (sequences, slot lanes); a CTA walks the windows of one
+// sequence once per slot with a shared-memory histogram and writes the slot's row segment (padding columns zero).
+template <typename GwT, int NW>
+__global__ void __launch_bounds__(128)
+dense_count_kernel(const GwT* __restrict__ gw0, const uint64_t* __restrict__ gw1, const uint32_t* __restrict__ woff,
+                   uint32_t nks, size_t ld, int nb, __half* __restrict__ C, const __grid_constant__ BatchSpec spec) {
+    using KeyT = typename std::conditional<sizeof(GwT) == 4, uint32_t, uint64_t>::type;
+    constexpr uint32_t KB = sizeof(KeyT) * 8;
+    extern __shared__ uint32_t hist[];
+    const uint32_t seq = blockIdx.x;
+    const uint32_t w0 = woff[seq], nw = woff[seq + 1] - w0;
+    for (int slot = blockIdx.y; slot < nb; slot += gridDim.y) {
+        for (uint32_t i = threadIdx.x; i < nks; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        const int nseg = spec.nseg[slot];
+        for (uint32_t p = threadIdx.x; p < nw; p += blockDim.x) {
+            const KeyT lo = (KeyT)gw0[w0 + p];
+            const KeyT hi = NW == 2 ? (KeyT)gw1[w0 + p] : (KeyT)0;
+            KeyT key = 0;
+            uint32_t dst = 0;
+            for (int j = 0; j < nseg; ++j) {          // same stretch packing as pack_hist_kernel
+                const uint32_t e = spec.seg[slot][j];
+                const uint32_t src = e & 63u, width = (e >> 7) + 1u;
+                const KeyT m = (KeyT)((KeyT) ~(KeyT)0 >> (KB - width)) << dst;
+                const uint32_t r = (src - dst) & (KB - 1u);
+                key |= rotr_key<KeyT>((NW == 2 && (e & 64u)) ? hi : lo, r) & m;
+                dst += width;
+            }
+            atomicAdd(&hist[(uint32_t)key], 1u);
+        }
+        __syncthreads();
+        __half2* __restrict__ out = reinterpret_cast<__half2*>(C + (size_t)seq * ld + (size_t)slot * nks);
+        for (uint32_t i = threadIdx.x; i < nks / 2; i += blockDim.x)
+            out[i] = __halves2half2(__uint2half_rn(hist[2 * i]), __uint2half_rn(hist[2 * i + 1]));
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a): mbarrier, TMA, tcgen05
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol error must end in a trap (an error code at the next synchronise), never in a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t it = 0;; ++it) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (it > (1u << 22)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(x), "r"(y)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {   // arrives on `bar` when every MMA issued so far has completed
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets row (lane base + t)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor of a K-major operand tile staged by TMA with 128-byte swizzle: rows of 128 bytes,
+// 8-row groups 1024 bytes apart (stride byte offset), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);   // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                       // leading byte offset: unused for swizzled K-major layouts
+    d |= (uint64_t)(1024u >> 4) << 32;            // stride byte offset
+    d |= (uint64_t)1 << 46;                       // version
+    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D = fp32, A = B = fp16, both K-major, N at bit 17 (>> 3), M at bit 24 (>> 4)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// grid = (lower-triangle tiles T (T + 1) / 2, groups).  Group `g` contracts the columns [k_begin + g * k_group,
+// + klen) of C and adds into K + g * out_group_stride (integer modes: one group; variance mode: one per slot).
+__global__ void __launch_bounds__(DG_THREADS)
+syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t nseq, uint32_t k_begin, uint32_t k_group, uint32_t klen,
+               unsigned long long* __restrict__ K, size_t out_group_stride) {
+    extern __shared__ uint8_t dg_smem_raw[];
+    const uint32_t raw = smem_u32(dg_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;                 // swizzle atoms need 1024-byte alignment
+    const uint32_t bars = base + DG_STAGES * DG_STAGE_BYTES;      // full[S], empty[S], tmem_full, tmem slot
+    const uint32_t full0 = bars, empty0 = bars + 8 * DG_STAGES, tmem_full = bars + 16 * DG_STAGES, tmem_slot = tmem_full + 8;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(dg_smem_raw + (tmem_slot - raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // tile index -> (I, J), J <= I
+    const uint32_t t = blockIdx.x;
+    uint32_t I = (uint32_t)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while ((uint64_t)(I + 1) * (I + 2) / 2 <= t) ++I;
+    while ((uint64_t)I * (I + 1) / 2 > t) --I;
+    const uint32_t J = t - (uint32_t)((uint64_t)I * (I + 1) / 2);
+    const bool diag = I == J;
+    const uint32_t kx0 = k_begin + blockIdx.y * k_group;
+    const uint32_t nkb = klen / DG_BK;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < DG_STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {   // one warp allocates (and later frees) the accumulator columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(DG_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+            const uint32_t tx = diag ? DG_TILE_BYTES : DG_STAGE_BYTES;
+            for (uint32_t kb = 0; kb < nkb; ++kb) {
+                const uint32_t s = kb % DG_STAGES, ph = (kb / DG_STAGES) & 1u;
+                mbar_wait(empty0 + 8 * s, ph ^ 1u);                           // the MMAs that read this stage have completed
+                mbar_arrive_expect_tx(full0 + 8 * s, tx);
+                const uint32_t a = base + s * DG_STAGE_BYTES;
+                const int x = (int)(kx0 + kb * DG_BK);
+                tma_load_2d(a, &tmap, full0 + 8 * s, x, (int)(I * DG_TILE));
+                if (!diag) tma_load_2d(a + DG_TILE_BYTES, &tmap, full0 + 8 * s, x, (int)(J * DG_TILE));
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(DG_TILE, DG_TILE);
+            for (uint32_t kb = 0; kb < nkb; ++kb) {
+                const uint32_t s = kb % DG_STAGES, ph = (kb / DG_STAGES) & 1u;
+                mbar_wait(full0 + 8 * s, ph);                                 // TMA has landed this stage
+                tc_fence_after();
+                const uint32_t a = base + s * DG_STAGE_BYTES;
+                const uint64_t adesc = umma_desc_sw128(a);
+                const uint64_t bdesc = umma_desc_sw128(diag ? a : a + DG_TILE_BYTES);
+#pragma unroll
+                for (uint32_t k = 0; k < DG_BK / 16; ++k)                     // UMMA_K = 16 fp16 = 32 bytes along the swizzled row
+                    tc_mma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0u);
+                tc_commit(empty0 + 8 * s);                                    // frees the stage once these MMAs are done
+            }
+            tc_commit(tmem_full);                                             // accumulator complete
+        }
+        __syncwarp();
+    } else {
+        const uint32_t q = (uint32_t)warp & 3u;                               // the TMEM lane quarter this warp can read
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int64_t i = (int64_t)I * DG_TILE + q * 32 + lane;
+        unsigned long long* __restrict__ Krow = K + (size_t)blockIdx.y * out_group_stride + (size_t)(i * (i + 1) / 2);
+        const int64_t j0 = (int64_t)J * DG_TILE;
+#pragma unroll 1
+        for (int c0 = 0; c0 < DG_TILE; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + (uint32_t)c0, v);
+            if (i < nseq) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const int64_t j = j0 + c0 + c;
+                    const uint32_t u = __float2uint_rn(__uint_as_float(v[c]));
+                    if (j <= i && u) atomicAdd(&Krow[j], (unsigned long long)u);   // RED.ADD.64: the tile is owned by this CTA
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(DG_TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace fsk

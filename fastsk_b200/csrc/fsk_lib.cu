@@ -4,6 +4,7 @@
 // kernel_build_parallel (fastsk_kernel.cpp:24-106, 145-322) without any CPU compute path.
 #include "../../include/fastsk_b200.h"
 #include "fsk_kernels.cuh"
+#include "fsk_dense.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -44,7 +45,7 @@ struct fsk_handle {
     uint64_t seed = 0;
     std::vector<int32_t> user_queue;
     int opt_batch = 0;
-    int opt_acc_path = 0;            // 0 auto, 1 global RED, 2 row-stationary shared memory
+    int opt_acc_path = 0;            // 0 auto, 1 global RED, 2 row-stationary shared memory, 3 dense tensor-core contraction
     bool safe_rank = false;          // onesweep ranking: false = one atomic per key, verified afterwards; true = match masks
     int opt_rows_threads = 0;        // threads per row CTA of the accumulate (0 = by N)
     int opt_overlap = 0;             // 1 = pre-pass of the next batch on its own low-priority stream (measured: no gain, the
@@ -100,6 +101,13 @@ struct fsk_handle {
     size_t rows_smem = 0;
     int wave_rows = 148;                               // rows per accumulate launch
     int64_t maxwin = 0;
+    // dense regime (fsk_dense.cuh): per-sequence k-mer counts of a batch, contracted on the tensor cores
+    bool dense_path = false;
+    uint32_t nks = 0;                                  // k-mer columns per slot, padded to a multiple of DG_BK
+    size_t dense_ld = 0;                               // fp16 elements per row of d_C (= B * nks)
+    int dense_chunk = 1;                               // slots per GEMM: keeps every fp32 accumulator below 2^24
+    __half* d_C = nullptr;
+    CUtensorMap tmap_C;
     unsigned long long* d_Kint = nullptr;   // integer partial (exact / skip_variance), or per-slot Ks in variance mode
     int ks_slots = 1;
     std::vector<double*> d_Khat;            // one per local virtual stream
@@ -167,7 +175,7 @@ void release_device(fsk_handle* h) {
     dev_free(h->d_recA); dev_free(h->d_recB); dev_free(h->d_valA); dev_free(h->d_valB);
     dev_free(h->d_zero);
     h->d_ghist = h->d_ticket = h->d_status = h->d_seg_status = nullptr;
-    dev_free(h->d_woff32); dev_free(h->d_fill);
+    dev_free(h->d_woff32); dev_free(h->d_fill); dev_free(h->d_C);
     for (int i = 0; i < 2; ++i) { dev_free(h->d_ids[i]); dev_free(h->d_task[i]); }
     dev_free(h->d_Kint); dev_free(h->d_Kf);
     for (auto& p : h->d_Khat) dev_free(p);
@@ -358,6 +366,43 @@ int launch_accumulate(fsk_handle* h, int nb, unsigned long long* K, size_t slot_
     return FSK_OK;
 }
 
+// Dense regime: per-sequence k-mer counts of every slot, then K += C C^T on the tensor cores (fsk_dense.cuh).
+int run_batch_dense(fsk_handle* h, int nb, const BatchSpec& spec, unsigned long long* K, size_t slot_stride) {
+    h->ls = h->stream;
+    {
+        Span sp(h, PC_PACK);
+        dim3 grid((unsigned)h->N, (unsigned)std::min(nb, 8));
+        const size_t smem = (size_t)h->nks * 4;
+        if (h->NW == 2)
+            dense_count_kernel<uint64_t, 2><<<grid, 128, smem, h->ls>>>((const uint64_t*)h->d_gw0, h->d_gw1, h->d_woff32, h->nks, h->dense_ld, nb, h->d_C, spec);
+        else if (h->gw32)
+            dense_count_kernel<uint32_t, 1><<<grid, 128, smem, h->ls>>>((const uint32_t*)h->d_gw0, nullptr, h->d_woff32, h->nks, h->dense_ld, nb, h->d_C, spec);
+        else
+            dense_count_kernel<uint64_t, 1><<<grid, 128, smem, h->ls>>>((const uint64_t*)h->d_gw0, nullptr, h->d_woff32, h->nks, h->dense_ld, nb, h->d_C, spec);
+        h->launches++;
+        CU(cudaGetLastError());
+    }
+    {
+        Span sp(h, PC_ACCUMULATE);
+        const unsigned T = (unsigned)((h->N + DG_TILE - 1) / DG_TILE);
+        const unsigned tiles = T * (T + 1) / 2;
+        if (slot_stride) {   // variance mode: every slot contracts its own k-mer columns into its own Ks
+            syrk_tc_kernel<<<dim3(tiles, (unsigned)nb), DG_THREADS, DG_SMEM, h->ls>>>(h->tmap_C, h->N, 0u, h->nks, h->nks, K, slot_stride);
+            h->launches++;
+        } else {
+            for (int c0 = 0; c0 < nb; c0 += h->dense_chunk) {
+                const int cs = std::min(h->dense_chunk, nb - c0);
+                syrk_tc_kernel<<<dim3(tiles, 1), DG_THREADS, DG_SMEM, h->ls>>>(h->tmap_C, h->N, (uint32_t)c0 * h->nks, 0u, (uint32_t)cs * h->nks, K, 0);
+                h->launches++;
+            }
+        }
+        CU(cudaGetLastError());
+    }
+    h->combos_done += nb;
+    if (h->spans.size() > 2048) resolve_spans(h);
+    return FSK_OK;
+}
+
 // One batch of combinations: partial kernels added into K (+ slot * slot_stride).
 int run_batch(fsk_handle* h, const int32_t* combos, int nb, unsigned long long* K, size_t slot_stride) {
     BatchSpec spec;
@@ -376,6 +421,7 @@ int run_batch(fsk_handle* h, const int32_t* combos, int nb, unsigned long long* 
         }
         spec.nseg[s] = (uint8_t)nseg;
     }
+    if (h->dense_path) return run_batch_dense(h, nb, spec, K, slot_stride);
     // The pack / sort / segment of this batch go to pre_stream and may overlap the accumulate of the previous batch on
     // the main stream (they are HBM / L2 bound, the accumulate is shared-memory bound); ids/task are double-buffered.
     h->buf = (int)(h->batch_index++ & 1);
@@ -555,7 +601,7 @@ int fsk_set_option(fsk_handle* h, const char* key, int64_t value) {
         if (value < 0 || value > MAX_BATCH) return fail(h, FSK_EINVAL, "batch must be in [0, %d]", MAX_BATCH);
         h->opt_batch = (int)value;
     } else if (!strcmp(key, "acc_path")) {
-        if (value < 0 || value > 2) return fail(h, FSK_EINVAL, "acc_path must be 0 (auto), 1 (global RED) or 2 (shared-memory rows)");
+        if (value < 0 || value > 3) return fail(h, FSK_EINVAL, "acc_path must be 0 (auto), 1 (global RED), 2 (shared-memory rows) or 3 (dense tensor-core contraction)");
         h->opt_acc_path = (int)value;
     } else if (!strcmp(key, "safe_rank")) {
         h->safe_rank = value != 0;
@@ -695,6 +741,22 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     const bool rows_ok = (size_t)N * 4 + 128 + 1024 <= (size_t)max_smem && (double)maxwin * (double)maxwin < 4294967296.0;
     if (h->opt_acc_path == 2 && !rows_ok) return fail(h, FSK_EINVAL, "acc_path = 2 needs N * 4 B <= %d B of shared memory", max_smem);
     h->rows_path = h->opt_acc_path == 2 || (h->opt_acc_path == 0 && rows_ok);
+    {
+        // dense regime: few distinct k-mers per combination, so K += C C^T on the tensor cores beats the sort + sparse
+        // update.  Cost model per combination: N^2 / 2 x nks MACs at an effective 5e14 MAC/s against
+        // nfeat^2 / (2 keys) shared-memory updates at 1.2e12 /s plus 2.7e-11 s per window of sort + segmentation.
+        const bool dense_ok = h->keybits <= 12 && maxwin <= 2048;
+        const uint32_t nks = dense_ok ? (uint32_t)(((1u << h->keybits) + DG_BK - 1) / DG_BK * DG_BK) : 0;
+        double keys = 1;
+        for (int i = 0; i < h->k; ++i) keys *= A;
+        const double t_dense = 0.5 * (double)N * (double)N * nks / 5e14 + (double)N * nks * 2 / 3e12 + 5e-6;
+        const double t_sparse = (double)nfeat * (double)nfeat / (2.0 * keys) / 1.2e12 + (double)nfeat * 2.7e-11 + 5e-6;
+        if (h->opt_acc_path == 3 && !dense_ok)
+            return fail(h, FSK_EINVAL, "acc_path = 3 needs at most 12 key bits and 2048 windows per sequence (key bits = %d, windows = %lld)", h->keybits, (long long)maxwin);
+        h->dense_path = h->opt_acc_path == 3 || (h->opt_acc_path == 0 && dense_ok && t_dense < t_sparse);
+        h->nks = nks;
+        if (h->dense_path) h->rows_path = false;
+    }
     h->rows_smem = (size_t)N * 4 + 128;   // + one dump word per lane for masked-off ids
     h->rows_threads = N >= 16384 ? 1024 : (N >= 4096 ? 512 : 256);
     if (h->opt_rows_threads) h->rows_threads = h->opt_rows_threads;
@@ -763,6 +825,15 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         const int T = effective_streams(h, nq);
         Bsel = std::min<int64_t>(Bsel, std::max(1, (T + h->world - 1) / h->world));
     }
+    if (h->dense_path) {
+        if (h->opt_batch == 0) Bsel = std::min<int64_t>(MAX_BATCH, std::max<int64_t>(1, h->user_queue.empty() ? h->ncomb : (int64_t)h->user_queue.size()));
+        if (h->variance_mode) {
+            const int64_t nq = h->user_queue.empty() ? h->ncomb : (int64_t)h->user_queue.size();
+            Bsel = std::min<int64_t>(Bsel, std::max(1, (effective_streams(h, nq) + h->world - 1) / h->world));
+        }
+        Bsel = std::min<int64_t>(Bsel, std::max<int64_t>(1, (4LL << 30) / (N * (int64_t)h->nks * 2)));   // C stays below 4 GB
+        h->dense_chunk = (int)std::max<int64_t>(1, std::min<int64_t>(Bsel, 16777215 / std::max<int64_t>(1, maxwin * maxwin)));
+    }
     h->B = (int)Bsel;
     h->sort_tiles = (uint32_t)((nfeat + SORT_THREADS * h->sort_items - 1) / (SORT_THREADS * h->sort_items));
     h->seg_rows = (h->opt_seg_occ >= 1 && h->opt_seg_occ <= 3 && h->ids16 && h->mode == MODE_R32) ? 8 : SEG_ROWS_DEFAULT;
@@ -825,6 +896,28 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         for (int64_t i = 0; i <= N; ++i) w32[(size_t)i] = (uint32_t)woff[(size_t)i];
         ALLOC(h->d_woff32, N + 1);
         CU(cudaMemcpy(h->d_woff32, w32.data(), sizeof(uint32_t) * (size_t)(N + 1), cudaMemcpyHostToDevice));
+    }
+    if (h->dense_path) {
+        h->dense_ld = (size_t)B * h->nks;
+        ALLOC(h->d_C, (size_t)N * h->dense_ld);
+        // TMA descriptor of C: [N rows][dense_ld fp16], boxes of 128 rows x 64 columns landing with the 128-byte swizzle the
+        // UMMA descriptors of syrk_tc_kernel expect; rows past N read as zero
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return fail(h, FSK_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+        const cuuint64_t gdim[2] = {(cuuint64_t)h->dense_ld, (cuuint64_t)N};
+        const cuuint64_t gstride[1] = {(cuuint64_t)h->dense_ld * 2};
+        const cuuint32_t box[2] = {(cuuint32_t)DG_BK, (cuuint32_t)DG_TILE};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult cr = ((EncodeFn)fn)(&h->tmap_C, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)h->d_C, gdim, gstride, box, estr,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return fail(h, FSK_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+        CU(cudaFuncSetAttribute(syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DG_SMEM));
     }
     ALLOC(h->d_counters, 4);
     CU(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), h->stream));
@@ -1163,6 +1256,7 @@ int fsk_get_stats(fsk_handle* h, fsk_stats* out) {
     out->kernel_launches = h->launches;
     out->key_bits = h->keybits; out->id_bits = h->idbits; out->record_bytes = h->rec_bytes; out->sort_passes = h->plan.npass;
     out->alphabet = h->A; out->bits_per_char = h->b; out->batch = h->B; out->acc_bytes = 8;
+    out->acc_path = h->dense_path ? 3 : (h->rows_path ? 2 : 1);
     if (h->uploaded) {
         CU(cudaSetDevice(h->device));
         resolve_spans(h);

@@ -63,8 +63,10 @@ int fsk_set_combo_sequence(fsk_handle* h, const int32_t* combos, int64_t n);
 int fsk_set_shard(fsk_handle* h, int rank, int world);
 /* tuning / diagnostics: "batch" (combinations per launch group, 0 = auto), "profile" (1 = time
  * every kernel class with CUDA events and count entries / runs / pair updates), "acc_path" (0 = auto,
- * 1 = global RED on the packed triangle, 2 = row-stationary shared-memory accumulate); unknown keys
- * give FSK_EINVAL */
+ * 1 = global RED on the packed triangle, 2 = row-stationary shared-memory accumulate, 3 = dense regime:
+ * per-sequence k-mer counts contracted as K += C C^T by tcgen05 tensor-core MMAs, no sort; needs at most
+ * 12 key bits and 2048 windows per sequence, chosen automatically when its cost model wins); unknown
+ * keys give FSK_EINVAL */
 int fsk_set_option(fsk_handle* h, const char* key, int64_t value);
 
 /* ---- compute ---------------------------------------------------------------------------- */
@@ -128,6 +130,8 @@ typedef struct fsk_stats {
     int32_t key_bits, id_bits, record_bytes, sort_passes, alphabet, bits_per_char, batch, acc_bytes;
     /* per kernel class, milliseconds on the handle's stream ("profile" only) */
     double ms_pack, ms_sort, ms_segment, ms_accumulate, ms_welford, ms_normalise, ms_total;
+    /* accumulate path in use: 1 global RED, 2 shared-memory rows, 3 dense tensor-core contraction (no sort) */
+    int32_t acc_path, reserved0;
 } fsk_stats;
 int fsk_get_stats(fsk_handle* h, fsk_stats* out);
 

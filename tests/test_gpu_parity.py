@@ -85,10 +85,17 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("acc_path", [0, 1], ids=["rows", "global_red"])
+def dense_eligible(alpha, g, m):
+    """acc_path 3 (tensor-core contraction) takes at most 12 key bits: (g - m) x ceil(log2(alphabet))."""
+    return (g - m) * max(1, int(np.ceil(np.log2(alpha)))) <= 12
+
+
+@pytest.mark.parametrize("acc_path", [0, 1, 2, 3], ids=["auto", "global_red", "rows", "dense_tc"])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_random_exact_vs_oracle(FastSK, oracle_mod, case, acc_path):
     name, ntr, nte, alpha, (lo, hi), g, m, batch, lowc = case
+    if acc_path == 3 and not dense_eligible(alpha, g, m):
+        pytest.skip("key space too large for the dense path")
     rng = np.random.default_rng(abs(hash(name)) % (2 ** 31))
     X = random_seqs(rng, ntr + nte, alpha, max(lo, g), hi, lowc)
     if name == "wide_alphabet_ids":
@@ -107,6 +114,8 @@ def test_random_exact_vs_oracle(FastSK, oracle_mod, case, acc_path):
     assert np.array_equal(f.get_kernel_packed(), oracle_mod.normalise(K, ntr + nte))
     st = f.stats()
     assert st["combos_done"] == len(queue) and st["kernel_launches"] > 0
+    if acc_path:
+        assert st["acc_path"] == acc_path
 
 
 @pytest.mark.parametrize("case", [CASES[0], CASES[-3], CASES[-4]], ids=lambda c: c[0])
@@ -147,12 +156,14 @@ def test_per_combination_counts(FastSK, oracle_mod, alpha, g, m):
 
 @pytest.mark.parametrize("T,max_iters,skip,delta", [(1, 12, False, 0.025), (3, 8, False, 0.025), (5, 4, True, 0.025),
                                                     (2, -1, False, 3.0), (-1, 3, False, 0.025), (4, -1, True, 0.025)])
-def test_approx_modes_vs_oracle(FastSK, oracle_mod, T, max_iters, skip, delta):
+@pytest.mark.parametrize("acc_path", [2, 3], ids=["rows", "dense_tc"])
+def test_approx_modes_vs_oracle(FastSK, oracle_mod, T, max_iters, skip, delta, acc_path):
     rng = np.random.default_rng(42 + (T % 7) + 3 * max_iters)
     g, m = 9, 5
     X = random_seqs(rng, 36, 4, 20, 70)
     queue = rng.permutation(comb(g, m)).astype(np.int32)
     f = FastSK(g, m, T, True, delta, max_iters, skip, combo_sequence=queue)
+    f.set_option("acc_path", acc_path)
     f.compute_kernel(X[:24], X[24:])
     K, Ki, sd = oracle_mod.run("c", X[:24], X[24:], g, m, queue, T=T, approx=True, delta=delta, max_iters=max_iters,
                                skip_variance=skip)
@@ -167,6 +178,40 @@ def test_approx_modes_vs_oracle(FastSK, oracle_mod, T, max_iters, skip, delta):
         assert len(f.get_stdevs()) == len(sd)
         np.testing.assert_allclose(f.get_stdevs(), sd, rtol=RTOL, atol=0)
         assert f.get_stdevs()[0] == 3162.2775020544923
+
+
+def test_dense_tensor_core_path_multi_tile_and_chunked(FastSK, oracle_mod):
+    """acc_path 3 (K += C C^T with tcgen05 MMAs): several 128-row tiles incl. off-diagonal ones and a ragged last tile;
+    long low-complexity sequences whose counts force the contraction to be cut into chunks of slots so that every fp32
+    accumulator stays an exact integer; and the automatic choice on an EP300-shaped input."""
+    rng = np.random.default_rng(11)
+    g, m = 10, 6                                              # 4 kept characters x 2 bits: 256 k-mers
+    X = random_seqs(rng, 333, 4, 60, 100)
+    queue = rng.permutation(comb(g, m))[:100].astype(np.int32)   # 100 combinations: a full batch of 96 and a rest
+    f = FastSK(g, m, combo_sequence=queue)
+    f.compute_kernel(X[:250], X[250:])
+    st = f.stats()
+    assert st["acc_path"] == 3, "the cost model should pick the dense path for 256 k-mers x 333 sequences"
+    _, Ki, _ = oracle_mod.run("c", X[:250], X[250:], g, m, queue)
+    assert np.array_equal(f.get_unnormalised().astype(np.uint64), Ki)
+
+    g, m = 8, 4
+    X = random_seqs(rng, 14, 4, 900, 1100, True)             # homopolymers: counts up to 1093, products above 2^20
+    queue = rng.permutation(comb(g, m))[:40].astype(np.int32)
+    out = []
+    for path in (2, 3):
+        f = FastSK(g, m, combo_sequence=queue)
+        f.set_option("acc_path", path)
+        f.compute_train(X)
+        out.append(f.get_unnormalised())
+    assert np.array_equal(out[0], out[1])
+    _, Ki, _ = oracle_mod.run("c", X, [], g, m, queue)
+    assert np.array_equal(out[1].astype(np.uint64), Ki)
+
+    f = FastSK(12, 4, combo_sequence=queue[:4])              # 8 x 2 = 16 key bits: not eligible
+    f.set_option("acc_path", 3)
+    with pytest.raises(ValueError):
+        f.compute_train(random_seqs(rng, 5, 4, 20, 30))
 
 
 def test_seeded_shuffle_is_reproducible_and_exact_is_order_invariant(FastSK):
