@@ -31,41 +31,53 @@ constexpr size_t DG_SMEM = (size_t)DG_STAGES * DG_STAGE_BYTES + 1024 /* 1024-byt
 constexpr int DENSE_MAX_KEYS = 4096;
 
 // ------------------------------------------------------------------------------------------
-// C = per-sequence k-mer counts of every slot.  grid = (sequences, slot lanes); a CTA walks the windows of one
-// sequence once per slot with a shared-memory histogram and writes the slot's row segment (padding columns zero).
+// C = per-sequence k-mer counts of every slot.  One CTA per sequence, one warp per (sequence, slot): the warp counts
+// the sequence's windows into its own shared-memory histogram (two 16-bit counters per word: counts are at most
+// maxwin <= 2048) and writes the slot's row segment as fp16 (padding columns zero).  Warp-level synchronisation only.
+constexpr int DENSE_COUNT_WARPS = 8;
+constexpr int DENSE_MAX_SEG = 12;          // at most 12 key bits, so at most 12 stretches of kept characters
 template <typename GwT, int NW>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(DENSE_COUNT_WARPS * 32)
 dense_count_kernel(const GwT* __restrict__ gw0, const uint64_t* __restrict__ gw1, const uint32_t* __restrict__ woff,
                    uint32_t nks, size_t ld, int nb, __half* __restrict__ C, const __grid_constant__ BatchSpec spec) {
     using KeyT = typename std::conditional<sizeof(GwT) == 4, uint32_t, uint64_t>::type;
     constexpr uint32_t KB = sizeof(KeyT) * 8;
-    extern __shared__ uint32_t hist[];
+    extern __shared__ uint32_t hist_all[];
+    __shared__ uint32_t seg_all[DENSE_COUNT_WARPS][DENSE_MAX_SEG];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* __restrict__ seg = seg_all[warp];
+    const uint32_t words = nks >> 1;
+    uint32_t* __restrict__ hist = hist_all + (size_t)warp * words;
     const uint32_t seq = blockIdx.x;
     const uint32_t w0 = woff[seq], nw = woff[seq + 1] - w0;
-    for (int slot = blockIdx.y; slot < nb; slot += gridDim.y) {
-        for (uint32_t i = threadIdx.x; i < nks; i += blockDim.x) hist[i] = 0;
-        __syncthreads();
+    for (int slot = warp; slot < nb; slot += DENSE_COUNT_WARPS) {
+        for (uint32_t i = lane; i < words; i += 32) hist[i] = 0;
         const int nseg = spec.nseg[slot];
-        for (uint32_t p = threadIdx.x; p < nw; p += blockDim.x) {
+        if (lane < nseg) seg[lane] = spec.seg[slot][lane];     // the slot's stretch descriptors: broadcast reads below
+        __syncwarp();
+        for (uint32_t p = lane; p < nw; p += 32) {
             const KeyT lo = (KeyT)gw0[w0 + p];
             const KeyT hi = NW == 2 ? (KeyT)gw1[w0 + p] : (KeyT)0;
             KeyT key = 0;
             uint32_t dst = 0;
-            for (int j = 0; j < nseg; ++j) {          // same stretch packing as pack_hist_kernel
-                const uint32_t e = spec.seg[slot][j];
+            for (int j = 0; j < nseg; ++j) {            // same stretch packing as pack_hist_kernel
+                const uint32_t e = seg[j];
                 const uint32_t src = e & 63u, width = (e >> 7) + 1u;
                 const KeyT m = (KeyT)((KeyT) ~(KeyT)0 >> (KB - width)) << dst;
                 const uint32_t r = (src - dst) & (KB - 1u);
                 key |= rotr_key<KeyT>((NW == 2 && (e & 64u)) ? hi : lo, r) & m;
                 dst += width;
             }
-            atomicAdd(&hist[(uint32_t)key], 1u);
+            const uint32_t kk = (uint32_t)key;
+            atomicAdd(&hist[kk >> 1], 1u << ((kk & 1u) << 4));
         }
-        __syncthreads();
+        __syncwarp();
         __half2* __restrict__ out = reinterpret_cast<__half2*>(C + (size_t)seq * ld + (size_t)slot * nks);
-        for (uint32_t i = threadIdx.x; i < nks / 2; i += blockDim.x)
-            out[i] = __halves2half2(__uint2half_rn(hist[2 * i]), __uint2half_rn(hist[2 * i + 1]));
-        __syncthreads();
+        for (uint32_t i = lane; i < words; i += 32) {
+            const uint32_t w = hist[i];
+            out[i] = __halves2half2(__ushort2half_rn((unsigned short)(w & 0xffffu)), __ushort2half_rn((unsigned short)(w >> 16)));
+        }
+        __syncwarp();
     }
 }
 
@@ -143,11 +155,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// grid = (lower-triangle tiles T (T + 1) / 2, groups).  Group `g` contracts the columns [k_begin + g * k_group,
+// grid = (lower-triangle tiles T (T + 1) / 2 in tile_order, groups).  Group `g` contracts the columns [k_begin + g * k_group,
 // + klen) of C and adds into K + g * out_group_stride (integer modes: one group; variance mode: one per slot).
 __global__ void __launch_bounds__(DG_THREADS)
-syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t nseq, uint32_t k_begin, uint32_t k_group, uint32_t klen,
-               unsigned long long* __restrict__ K, size_t out_group_stride) {
+syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restrict__ tile_order, int64_t nseq, uint32_t k_begin,
+               uint32_t k_group, uint32_t klen, unsigned long long* __restrict__ K, size_t out_group_stride) {
     extern __shared__ uint8_t dg_smem_raw[];
     const uint32_t raw = smem_u32(dg_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                 // swizzle atoms need 1024-byte alignment
@@ -156,12 +168,10 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t nseq, uint32_t 
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(dg_smem_raw + (tmem_slot - raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // tile index -> (I, J), J <= I
-    const uint32_t t = blockIdx.x;
-    uint32_t I = (uint32_t)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-    while ((uint64_t)(I + 1) * (I + 2) / 2 <= t) ++I;
-    while ((uint64_t)I * (I + 1) / 2 > t) --I;
-    const uint32_t J = t - (uint32_t)((uint64_t)I * (I + 1) / 2);
+    // tile (I, J), J <= I, in the host's rasterised order: the CTAs resident at once cover a band of 16 tile rows by as
+    // many tile columns, so every operand slice TMA fetches is shared by ~16 CTAs through L2
+    const uint32_t ij = tile_order[blockIdx.x];
+    const uint32_t I = ij >> 16, J = ij & 0xffffu;
     const bool diag = I == J;
     const uint32_t kx0 = k_begin + blockIdx.y * k_group;
     const uint32_t nkb = klen / DG_BK;

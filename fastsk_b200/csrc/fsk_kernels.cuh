@@ -879,7 +879,28 @@ welford_kernel(AccT* __restrict__ Ks, double* __restrict__ K_hat, int64_t n_pair
     __shared__ double ws[8];
     const double diter = (double)iter;
     double acc = 0.0;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += (int64_t)gridDim.x * blockDim.x) {
+    // four independent element loads per array in flight per thread; a thread still visits its elements in increasing
+    // order, so the per-thread partial sums (and the result) do not depend on the unrolling
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; p + 3 * stride < n_pairs; p += 4 * stride) {
+        double ks[4], kh[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            ks[u] = (double)Ks[p + u * stride];
+            kh[u] = K_hat[p + u * stride];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t q = p + u * stride;
+            Ks[q] = 0;
+            const double delta = __dsub_rn(ks[u], kh[u]);
+            const double nh = __dadd_rn(kh[u], __ddiv_rn(delta, diter));
+            K_hat[q] = nh;
+            if (q < n_train_pairs) acc = __dadd_rn(acc, __dmul_rn(delta, __dsub_rn(ks[u], nh)));
+        }
+    }
+    for (; p < n_pairs; p += stride) {
         const double ks = (double)Ks[p];
         Ks[p] = 0;
         double kh = K_hat[p];

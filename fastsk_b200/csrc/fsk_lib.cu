@@ -107,6 +107,7 @@ struct fsk_handle {
     size_t dense_ld = 0;                               // fp16 elements per row of d_C (= B * nks)
     int dense_chunk = 1;                               // slots per GEMM: keeps every fp32 accumulator below 2^24
     __half* d_C = nullptr;
+    uint32_t* d_tile_order = nullptr;                  // lower-triangle tiles (I << 16 | J) in L2-friendly launch order
     CUtensorMap tmap_C;
     unsigned long long* d_Kint = nullptr;   // integer partial (exact / skip_variance), or per-slot Ks in variance mode
     int ks_slots = 1;
@@ -175,7 +176,7 @@ void release_device(fsk_handle* h) {
     dev_free(h->d_recA); dev_free(h->d_recB); dev_free(h->d_valA); dev_free(h->d_valB);
     dev_free(h->d_zero);
     h->d_ghist = h->d_ticket = h->d_status = h->d_seg_status = nullptr;
-    dev_free(h->d_woff32); dev_free(h->d_fill); dev_free(h->d_C);
+    dev_free(h->d_woff32); dev_free(h->d_fill); dev_free(h->d_C); dev_free(h->d_tile_order);
     for (int i = 0; i < 2; ++i) { dev_free(h->d_ids[i]); dev_free(h->d_task[i]); }
     dev_free(h->d_Kint); dev_free(h->d_Kf);
     for (auto& p : h->d_Khat) dev_free(p);
@@ -371,14 +372,15 @@ int run_batch_dense(fsk_handle* h, int nb, const BatchSpec& spec, unsigned long 
     h->ls = h->stream;
     {
         Span sp(h, PC_PACK);
-        dim3 grid((unsigned)h->N, (unsigned)std::min(nb, 8));
-        const size_t smem = (size_t)h->nks * 4;
+        dim3 grid((unsigned)h->N);
+        const size_t smem = (size_t)DENSE_COUNT_WARPS * h->nks * 2;
+        constexpr int CT = DENSE_COUNT_WARPS * 32;
         if (h->NW == 2)
-            dense_count_kernel<uint64_t, 2><<<grid, 128, smem, h->ls>>>((const uint64_t*)h->d_gw0, h->d_gw1, h->d_woff32, h->nks, h->dense_ld, nb, h->d_C, spec);
+            dense_count_kernel<uint64_t, 2><<<grid, CT, smem, h->ls>>>((const uint64_t*)h->d_gw0, h->d_gw1, h->d_woff32, h->nks, h->dense_ld, nb, h->d_C, spec);
         else if (h->gw32)
-            dense_count_kernel<uint32_t, 1><<<grid, 128, smem, h->ls>>>((const uint32_t*)h->d_gw0, nullptr, h->d_woff32, h->nks, h->dense_ld, nb, h->d_C, spec);
+            dense_count_kernel<uint32_t, 1><<<grid, CT, smem, h->ls>>>((const uint32_t*)h->d_gw0, nullptr, h->d_woff32, h->nks, h->dense_ld, nb, h->d_C, spec);
         else
-            dense_count_kernel<uint64_t, 1><<<grid, 128, smem, h->ls>>>((const uint64_t*)h->d_gw0, nullptr, h->d_woff32, h->nks, h->dense_ld, nb, h->d_C, spec);
+            dense_count_kernel<uint64_t, 1><<<grid, CT, smem, h->ls>>>((const uint64_t*)h->d_gw0, nullptr, h->d_woff32, h->nks, h->dense_ld, nb, h->d_C, spec);
         h->launches++;
         CU(cudaGetLastError());
     }
@@ -387,12 +389,12 @@ int run_batch_dense(fsk_handle* h, int nb, const BatchSpec& spec, unsigned long 
         const unsigned T = (unsigned)((h->N + DG_TILE - 1) / DG_TILE);
         const unsigned tiles = T * (T + 1) / 2;
         if (slot_stride) {   // variance mode: every slot contracts its own k-mer columns into its own Ks
-            syrk_tc_kernel<<<dim3(tiles, (unsigned)nb), DG_THREADS, DG_SMEM, h->ls>>>(h->tmap_C, h->N, 0u, h->nks, h->nks, K, slot_stride);
+            syrk_tc_kernel<<<dim3(tiles, (unsigned)nb), DG_THREADS, DG_SMEM, h->ls>>>(h->tmap_C, h->d_tile_order, h->N, 0u, h->nks, h->nks, K, slot_stride);
             h->launches++;
         } else {
             for (int c0 = 0; c0 < nb; c0 += h->dense_chunk) {
                 const int cs = std::min(h->dense_chunk, nb - c0);
-                syrk_tc_kernel<<<dim3(tiles, 1), DG_THREADS, DG_SMEM, h->ls>>>(h->tmap_C, h->N, (uint32_t)c0 * h->nks, 0u, (uint32_t)cs * h->nks, K, 0);
+                syrk_tc_kernel<<<dim3(tiles, 1), DG_THREADS, DG_SMEM, h->ls>>>(h->tmap_C, h->d_tile_order, h->N, (uint32_t)c0 * h->nks, 0u, (uint32_t)cs * h->nks, K, 0);
                 h->launches++;
             }
         }
@@ -868,8 +870,9 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         CU(cudaGetLastError());
     }
 
-    // scratch for B slots
-    const size_t bn = (size_t)h->B * (size_t)nfeat;
+    // scratch for B slots (the dense path sorts nothing: one record keeps the pointers valid)
+    const size_t bn = h->dense_path ? 1 : (size_t)h->B * (size_t)nfeat;
+    if (h->dense_path) { h->sort_tiles = h->seg_tiles = 1; h->ids_stride = 64; }
     { unsigned char* p; ALLOC(p, bn * (h->mode == MODE_R32 ? 4 : 8)); h->d_recA = p; }
     { unsigned char* p; ALLOC(p, bn * (h->mode == MODE_R32 ? 4 : 8)); h->d_recB = p; }
     if (h->mode == MODE_KV) { ALLOC(h->d_valA, bn); ALLOC(h->d_valB, bn); }
@@ -890,7 +893,7 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         h->d_ids[i] = p;
         ALLOC(h->d_task[i], bn);
     }
-    ALLOC(h->d_fill, (size_t)B * (size_t)N);
+    ALLOC(h->d_fill, h->dense_path ? 1 : (size_t)B * (size_t)N);
     {
         std::vector<uint32_t> w32((size_t)N + 1);
         for (int64_t i = 0; i <= N; ++i) w32[(size_t)i] = (uint32_t)woff[(size_t)i];
@@ -918,6 +921,22 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return fail(h, FSK_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
         CU(cudaFuncSetAttribute(syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DG_SMEM));
+        const int count_smem = DENSE_COUNT_WARPS * (int)h->nks * 2;
+        CU(cudaFuncSetAttribute(dense_count_kernel<uint64_t, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, count_smem));
+        CU(cudaFuncSetAttribute(dense_count_kernel<uint64_t, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, count_smem));
+        CU(cudaFuncSetAttribute(dense_count_kernel<uint32_t, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, count_smem));
+        // launch order of the output tiles: bands of 16 tile rows, column by column inside a band
+        const int64_t T = (N + DG_TILE - 1) / DG_TILE;
+        if (T > 65535) return fail(h, FSK_EINVAL, "too many sequences for the dense path");
+        std::vector<uint32_t> order;
+        order.reserve((size_t)(T * (T + 1) / 2));
+        for (int64_t b0 = 0; b0 < T; b0 += 16) {
+            const int64_t b1 = std::min<int64_t>(T, b0 + 16);
+            for (int64_t J = 0; J < b1; ++J)
+                for (int64_t I = std::max(b0, J); I < b1; ++I) order.push_back((uint32_t)(I << 16 | J));
+        }
+        ALLOC(h->d_tile_order, order.size());
+        CU(cudaMemcpy(h->d_tile_order, order.data(), order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
     ALLOC(h->d_counters, 4);
     CU(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), h->stream));
