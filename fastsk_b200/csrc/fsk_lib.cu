@@ -5,6 +5,7 @@
 #include "../../include/fastsk_b200.h"
 #include "fsk_kernels.cuh"
 #include "fsk_dense.cuh"
+#include "fsk_bucket.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -54,6 +55,9 @@ struct fsk_handle {
     int opt_l2_fetch = 0;            // experiment: cudaLimitMaxL2FetchGranularity (0 = leave alone)
     int opt_seg_occ = 0;             // experiment: segment_kernel variant (0 = 16 rows per warp, 3 CTAs/SM; 1-3 = 8 rows, 4/5/6 CTAs/SM)
     int seg_rows = SEG_ROWS_DEFAULT;
+    int opt_seg_fused = 0;           // 0 auto, 1 off, 2 on: fused last sort pass + segmentation (fsk_bucket.cuh) for two-digit keys
+    bool fused_seg = false;
+    uint32_t image_cap = 0;          // ids in the shared-memory image of a bucket
     int opt_seg_exp = 0;             // timing experiments on segment_kernel (results are wrong when != 0; the accumulate is skipped)
     int opt_acc_pipe = 0;            // 1 = double-buffered id loads + next chunk's tasks prefetched
     int opt_acc_unroll = 2;          // id units in flight per lane of the accumulate (2, 4, 6 or 8)
@@ -292,7 +296,8 @@ int launch_sort(fsk_handle* h, int nb) {
     // opt in to more than 48 KB of dynamic shared memory (per device, so not cached across handles)
     auto kernel = h->safe_rank ? onesweep_kernel<RecT, KV, ITEMS, false> : onesweep_kernel<RecT, KV, ITEMS, true>;
     CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    for (int p = 0; p < h->plan.npass; ++p) {
+    const bool fused = h->fused_seg && !h->safe_rank;     // fused: partition by the high digit only (bucket_segment_kernel does the rest)
+    for (int p = fused ? h->plan.npass - 1 : 0; p < h->plan.npass; ++p) {
         const int shift = (KV ? 0 : h->idbits) + h->plan.shift[p];
         uint32_t* status = h->d_status + (size_t)p * h->B * h->sort_tiles * RADIX;
         kernel<<<h->sort_tiles * nb, SORT_THREADS, smem, h->ls>>>(
@@ -312,6 +317,21 @@ int launch_segment(fsk_handle* h, int nb) {
     unsigned long long* stat = h->profile ? h->d_counters : nullptr;
     init_fill_kernel<<<dim3((unsigned)((h->N + 255) / 256), nb), 256, 0, h->ls>>>(h->d_fill, h->d_woff32, (uint32_t)h->N);
     h->launches++;
+    if (h->fused_seg && !h->safe_rank) {
+        if (!std::is_same<RecT, uint32_t>::value || KV) return fail(h, FSK_ESTATE, "fused segmentation needs 32-bit records");
+        const int lo_bits = h->plan.bits[0], hi_bits = h->plan.bits[1];
+        dim3 grid(1u << hi_bits, (unsigned)nb);
+        const size_t smem = bucket_smem_bytes(h->image_cap);
+        const uint32_t* gh = h->d_ghist + (size_t)(h->plan.npass - 1) * RADIX;
+#define BK_ARGS (const uint32_t*)h->d_recA, n, gh, h->idbits, h->idbits + h->plan.shift[0], lo_bits, (uint32_t)h->N, h->ids_stride, h->pad_mask, \
+                h->image_cap, h->d_fill, (uint16_t*)h->d_ids[h->buf], h->d_task[h->buf], h->d_flag, stat
+        if (stat) bucket_segment_kernel<true><<<grid, BK_THREADS, smem, h->ls>>>(BK_ARGS);
+        else bucket_segment_kernel<false><<<grid, BK_THREADS, smem, h->ls>>>(BK_ARGS);
+#undef BK_ARGS
+        h->launches++;
+        CU(cudaGetLastError());
+        return FSK_OK;
+    }
     // the gaps between the aligned runs must read as "no sequence": 0xFF.. clamps to the dump word in the accumulate
     CU(cudaMemsetAsync(h->d_ids[h->buf], 0xff, (size_t)nb * h->ids_stride * (h->ids16 ? 2 : 4), h->ls));
     const unsigned grid = h->seg_tiles * (unsigned)nb;
@@ -621,6 +641,9 @@ int fsk_set_option(fsk_handle* h, const char* key, int64_t value) {
         h->opt_pad = (int)value;
     } else if (!strcmp(key, "seg_occ")) {
         h->opt_seg_occ = (int)value;
+    } else if (!strcmp(key, "seg_fused")) {
+        if (value < 0 || value > 2) return fail(h, FSK_EINVAL, "seg_fused must be 0 (auto), 1 (off) or 2 (on)");
+        h->opt_seg_fused = (int)value;
     } else if (!strcmp(key, "seg_exp")) {
         h->opt_seg_exp = (int)value;
     } else if (!strcmp(key, "acc_unroll")) {
@@ -774,6 +797,21 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         const int64_t cap = nfeat + (align - 1) * max_runs + 64;
         if (cap >= (1LL << 30)) return fail(h, FSK_EINVAL, "too many g-mers (%lld) for the aligned id stream", (long long)nfeat);
         h->ids_stride = (size_t)((cap + 63) / 64 * 64);
+        // fused last pass + segmentation: two radix digits, 32-bit records, 16-bit ids, row-stationary accumulate
+        const bool fused_ok = h->plan.npass == 2 && h->mode == MODE_R32 && h->ids16 && h->rows_path;
+        if (h->opt_seg_fused == 2 && !fused_ok)
+            return fail(h, FSK_EINVAL, "seg_fused = 2 needs keys of two radix digits (9..16 bits), 32-bit records and 16-bit ids");
+        h->fused_seg = fused_ok && h->opt_seg_fused != 1;
+        if (h->fused_seg) {
+            const int lo_bits = h->plan.bits[0], hi_bits = h->plan.bits[1];
+            const int64_t cap2 = ((nfeat + 63) / 64 * 64) + ((int64_t)1 << hi_bits) * (int64_t)bucket_id_stride(lo_bits) + 64;
+            if (cap2 >= (1LL << 30)) return fail(h, FSK_EINVAL, "too many g-mers (%lld) for the aligned id stream", (long long)nfeat);
+            h->ids_stride = std::max(h->ids_stride, (size_t)((cap2 + 63) / 64 * 64));
+            const int64_t cap_max = (((int64_t)max_smem - 1024 - (int64_t)bucket_smem_bytes(0)) / 2) & ~7LL;
+            h->image_cap = (uint32_t)std::max<int64_t>(64, std::min<int64_t>(cap_max, (nfeat + 64 * ((int64_t)1 << lo_bits) + 64) & ~7LL));
+            CU(cudaFuncSetAttribute(bucket_segment_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bucket_smem_bytes(h->image_cap)));
+            CU(cudaFuncSetAttribute(bucket_segment_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bucket_smem_bytes(h->image_cap)));
+        }
     }
     {
         // rows per accumulate launch: the CTAs resident at once, times opt_wave (default 1)

@@ -214,6 +214,44 @@ def test_dense_tensor_core_path_multi_tile_and_chunked(FastSK, oracle_mod):
         f.compute_train(random_seqs(rng, 5, 4, 20, 30))
 
 
+FUSED_CASES = [
+    # name, n, alphabet, len range, g, m, low complexity, batch
+    ("dna_14bit", 120, 4, (40, 160), 12, 5, False, 0),          # 7 + 7 bits: 128 buckets x 128 runs
+    ("dna_10bit_lowcomplex", 90, 4, (30, 120), 11, 6, True, 3),  # 5 + 5 bits, homopolymers: one group fills a run
+    ("protein_15bit", 70, 21, (20, 140), 8, 5, False, 0),        # 3 x 5 bits: 8 + 7
+    ("dna_16bit", 200, 4, (150, 150), 16, 8, False, 5),          # the C4 shape
+    ("dna_16bit_one_seq", 1, 4, (400, 400), 12, 4, False, 0),
+    ("binary_9bit", 60, 2, (40, 90), 14, 5, True, 0),            # 9 x 1 bits: 5 + 4
+]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES, ids=[c[0] for c in FUSED_CASES])
+def test_fused_bucket_segmentation_vs_oracle(FastSK, oracle_mod, case):
+    """seg_fused 2 (one onesweep pass on the high digit + bucket_segment_kernel) against the two-pass sort +
+    segment_kernel (seg_fused 1) and against the oracle: same integers, same statistics."""
+    name, n, alpha, (lo, hi), g, m, lowc, batch = case
+    rng = np.random.default_rng(abs(hash(name)) % (2 ** 31))
+    X = random_seqs(rng, n, alpha, max(lo, g), hi, lowc)
+    nc = comb(g, m)
+    queue = rng.permutation(nc)[:min(nc, 20)].astype(np.int32)
+    out, stats = [], []
+    for fused in (1, 2):
+        f = FastSK(g, m, combo_sequence=queue, profile=True)
+        f.set_option("acc_path", 2)
+        f.set_option("seg_fused", fused)
+        if batch:
+            f.set_option("batch", batch)
+        f.compute_train(X)
+        out.append(f.get_unnormalised())
+        stats.append(f.stats())
+    assert np.array_equal(out[0], out[1])
+    for k in ("pair_updates", "entries", "runs"):
+        assert stats[0][k] == stats[1][k], k
+    assert stats[1]["kernel_launches"] < stats[0]["kernel_launches"]
+    _, Ki, _ = oracle_mod.run("c", X, [], g, m, queue)
+    assert np.array_equal(out[1].astype(np.uint64), Ki)
+
+
 def test_seeded_shuffle_is_reproducible_and_exact_is_order_invariant(FastSK):
     rng = np.random.default_rng(3)
     X = random_seqs(rng, 30, 4, 15, 60)

@@ -32,6 +32,7 @@ ap.add_argument("--pad", type=int, default=0)
 ap.add_argument("--l2-fetch", type=int, default=0)
 ap.add_argument("--seg-exp", type=int, default=0)
 ap.add_argument("--seg-occ", type=int, default=0)
+ap.add_argument("--seg-fused", type=int, default=0)
 ap.add_argument("--acc-unroll", type=int, default=2)
 ap.add_argument("--acc-pipe", type=int, default=0)
 a = ap.parse_args()
@@ -49,6 +50,7 @@ f.set_option("pad", a.pad)
 f.set_option("l2_fetch", a.l2_fetch)
 f.set_option("seg_exp", a.seg_exp)
 f.set_option("seg_occ", a.seg_occ)
+f.set_option("seg_fused", a.seg_fused)
 f.set_option("acc_unroll", a.acc_unroll)
 f.set_option("acc_pipe", a.acc_pipe)
 codes = np.ascontiguousarray(X.reshape(-1))
