@@ -23,20 +23,21 @@
 
 namespace fsk {
 
-constexpr int BK_THREADS = 1024;
+constexpr int BK_THREADS = 512;              // two CTAs per SM: one bucket's phases overlap the other's
 constexpr int BK_WARPS = BK_THREADS / 32;
-constexpr int BK_BIG_RUN = 4096;            // runs longer than this are walked by the whole CTA, not by one warp
-constexpr int BK_ILP = 8;                   // record loads in flight per lane in the two streaming phases
+constexpr int BK_ILP = 16;
+constexpr int BK_DILP = 16;                 // records (= task-slot atomics in flight) per thread in the filing phase                  // record loads in flight per lane in the two streaming phases
 
 // id-stream cells between the ranges of consecutive buckets beyond the bucket's own records: 63 pad cells for each of its
 // 2^lo_bits runs at most, + 63 for rounding the bucket's start up to a 128-byte line
 __host__ __device__ constexpr size_t bucket_id_stride(int lo_bits) { return ((size_t)64 << lo_bits) + 64; }
+// shared memory: warp histograms, run tables, the image, and the run number of every 64-id block of the image
 __host__ __device__ constexpr size_t bucket_smem_bytes(uint32_t image_ids) {
-    return (size_t)BK_WARPS * RADIX * 4 + 3 * RADIX * 4 + (size_t)image_ids * 2 + 64;
+    return (size_t)BK_WARPS * RADIX * 4 + 3 * RADIX * 4 + (size_t)image_ids * 2 + ((size_t)(image_ids / 32 + 8) * 2 + 15) / 16 * 16 + 64;
 }
 
 template <bool STATS>
-__global__ void __launch_bounds__(BK_THREADS, 1)
+__global__ void __launch_bounds__(BK_THREADS, 2)
 bucket_segment_kernel(const uint32_t* __restrict__ rec, uint32_t n, const uint32_t* __restrict__ ghist_hi /* [slot][MAX_PASS][RADIX], pre-offset to the high digit */,
                       int idbits, int lo_shift, int lo_bits, uint32_t nseq, size_t ids_stride, uint32_t pad_mask,
                       uint32_t image_cap /* ids that fit the shared-memory image */, uint32_t* __restrict__ fill,
@@ -48,6 +49,7 @@ bucket_segment_kernel(const uint32_t* __restrict__ rec, uint32_t n, const uint32
     uint32_t* runX = runS + RADIX;                                    // aligned start of run d inside the bucket's id range
     uint32_t* runL = runX + RADIX;                                    // length of run d
     uint16_t* image = reinterpret_cast<uint16_t*>(runL + RADIX);      // the bucket's id stream (16-byte aligned)
+    uint16_t* block_run = image + image_cap;                          // run that owns the i-th block of pad_mask + 1 ids of the image
     __shared__ uint32_t s_start, s_warp_tot[2][8], s_total_x;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -120,90 +122,128 @@ bucket_segment_kernel(const uint32_t* __restrict__ rec, uint32_t n, const uint32
         }
     }
     __syncthreads();
-    if (tid < (int)DL) {
-        const uint32_t s = runS[tid];
-#pragma unroll 8
-        for (int w = 0; w < BK_WARPS; ++w) hist[w * RADIX + tid] += s;
-    }
     const uint32_t total_x = s_total_x;
+    if (tid < (int)DL) {
+        const uint32_t s0 = runS[tid];
+#pragma unroll 8
+        for (int w = 0; w < BK_WARPS; ++w) hist[w * RADIX + tid] += s0;
+    }
     // id-stream range of this bucket (multiple of 64 ids: 128-byte aligned)
     const size_t xbase = (size_t)((start + 63u) & ~63u) + (size_t)bucket * bucket_id_stride(lo_bits);
     uint16_t* __restrict__ gids = ids + (size_t)slot * ids_stride + xbase;
-    const bool staged = total_x <= image_cap;
-    uint16_t* sid = staged ? image : gids;          // generic pointer: shared-memory image, or HBM for an oversized bucket
-    __syncthreads();
-
-    // C: sequence ids to their sorted, aligned places
-    for (uint32_t i0 = c0; i0 < c1; i0 += 32 * BK_ILP) {
-        uint32_t r[BK_ILP];
-#pragma unroll
-        for (int u = 0; u < BK_ILP; ++u) {
-            const uint32_t i = i0 + u * 32 + lane;
-            r[u] = i < c1 ? R[i] : 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < BK_ILP; ++u) {                            // in record order: the ranks must follow the input order
-            if (i0 + u * 32 + lane < c1) {
-                const uint32_t d = (r[u] >> lo_shift) & dmask;
-                const uint32_t p = atomicAdd(&wh[d], 1u);             // lanes with equal d are served in lane order (verified in D)
-                sid[runX[d] + (p - runS[d])] = (uint16_t)(r[u] & idmask);
-            }
-        }
-    }
-    __syncthreads();
-
-    // D: tasks.  One warp per run (the whole CTA for very long runs); record j of a run of sequence b adds the prefix
-    // [run start, last record of b's group].
     const uint32_t xunit0 = (uint32_t)(xbase >> 3);
+    const uint32_t blk_shift = 31 - __clz(pad_mask + 1u);              // runs start on multiples of pad_mask + 1 = 2^blk_shift ids
     unsigned long long updates = 0;
     uint32_t groups = 0;
-    // four records per thread and step: their lookups, then their four atomics, then their four stores
-    auto do_run = [&](uint32_t X, uint32_t Lr, uint32_t first, uint32_t step) {
-        for (uint32_t j0 = first; j0 < Lr; j0 += 4 * step) {
-            uint32_t id[4], ln[4], pos[4];
+    auto run_end = [&](uint32_t d) -> uint32_t { return d + 1 < DL ? runX[d + 1] : total_x; };   // runX is the scan of the padded lengths
+
+    // The runs [d0, d1) whose padded ids fit the shared-memory image are built together: for the synthetic workload that is
+    // the whole bucket at once; a skewed bucket takes several rounds (its records are read again from L2 in each), and a
+    // single run longer than the image is built directly in HBM.
+    uint32_t d0 = 0;
+    while (d0 < DL) {
+        const uint32_t base = runX[d0];
+        uint32_t d1;
+        if (total_x - base <= image_cap) {
+            d1 = DL;
+        } else {                                                     // largest d1 with run_end(d1 - 1) - base <= image_cap
+            uint32_t lo = d0, hi = DL;                               // invariant: runs [d0, lo) fit, run hi - 1 ... may not
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (run_end(mid) - base <= image_cap) lo = mid + 1;
+                else hi = mid;
+            }
+            d1 = lo;
+        }
+        const bool in_hbm = d1 == d0;                                // run d0 alone exceeds the image
+        if (in_hbm) d1 = d0 + 1;
+        const uint32_t span = run_end(d1 - 1) - base;
+        uint16_t* sid = in_hbm ? gids + base : image;                // generic pointer
+        if (!in_hbm && tid >= (int)d0 && tid < (int)d1) {
+            const uint32_t X = runX[tid] - base, Xe = run_end(tid) - base;
+            for (uint32_t blk = X >> blk_shift; blk < Xe >> blk_shift; ++blk) block_run[blk] = (uint16_t)tid;
+        }
+        __syncthreads();
+
+        // C: sequence ids of the round's runs to their sorted, aligned places
+        for (uint32_t i0 = c0; i0 < c1; i0 += 32 * BK_ILP) {
+            uint32_t r[BK_ILP];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t j = j0 + u * step;
-                id[u] = 0;
-                ln[u] = 0;
-                if (j < Lr) {
-                    id[u] = sid[X + j];
-                    uint32_t e = j;
-                    while (e + 1 < Lr && sid[X + e + 1] == id[u]) ++e;
-                    if (e + 1 < Lr && sid[X + e + 1] < id[u]) *unsorted_flag = 1u;
-                    ln[u] = e + 1;
-                    if (STATS) { updates += e + 1; groups += (e == j); }
-                }
+            for (int u = 0; u < BK_ILP; ++u) {
+                const uint32_t i = i0 + u * 32 + lane;
+                r[u] = i < c1 ? R[i] : 0u;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (ln[u]) pos[u] = atomicAdd(&fill[(size_t)slot * nseq + id[u]], 1u);
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (ln[u]) task[(size_t)slot * n + pos[u]] = make_uint2(xunit0 + (X >> 3), ln[u]);
+            for (int u = 0; u < BK_ILP; ++u) {                        // in record order: the ranks must follow the input order
+                const uint32_t d = (r[u] >> lo_shift) & dmask;
+                if (i0 + u * 32 + lane < c1 && d >= d0 && d < d1) {
+                    const uint32_t p = atomicAdd(&wh[d], 1u);         // lanes with equal d are served in lane order (verified in D)
+                    sid[runX[d] - base + (p - runS[d])] = (uint16_t)(r[u] & idmask);
+                }
+            }
         }
-    };
-    for (uint32_t d = warp; d < DL; d += BK_WARPS) {
-        const uint32_t Lr = runL[d], X = runX[d];
-        if (Lr == 0 || Lr > BK_BIG_RUN) continue;
-        do_run(X, Lr, lane, 32);
-        // the rest of the run's last 16-byte unit reads as "no sequence"
-        const uint32_t pend = (Lr + 7u) & ~7u;
-        if (Lr + lane < pend) sid[X + Lr + lane] = 0xffffu;
-    }
-    for (uint32_t d = 0; d < DL; ++d) {
-        const uint32_t Lr = runL[d], X = runX[d];
-        if (Lr <= BK_BIG_RUN) continue;
-        do_run(X, Lr, tid, BK_THREADS);
-        const uint32_t pend = (Lr + 7u) & ~7u;
-        if (Lr + tid < pend) sid[X + Lr + tid] = 0xffffu;
-    }
-    __syncthreads();
-    if (staged) {   // image -> HBM, 16 bytes per thread and step (xbase and the padded run starts are multiples of 8 ids)
-        const uint4* __restrict__ src = reinterpret_cast<const uint4*>(image);
-        uint4* __restrict__ dst = reinterpret_cast<uint4*>(gids);
-        const uint32_t nvec = (total_x + 7u) >> 3;
-        for (uint32_t i = tid; i < nvec; i += BK_THREADS) dst[i] = src[i];
+        __syncthreads();
+
+        // D: tasks.  Record j of a run of sequence b adds the prefix [run start, last record of b's group].
+        if (!in_hbm) {
+            // every thread walks the image (load balanced): position a belongs to run block_run[a >> blk_shift].  BK_DILP records
+            // per thread and step: the global atomics that hand out the task slots are the long-latency part, so all of a step's
+            // atomics are in flight together (pv = sequence id before, task slot after)
+            for (uint32_t a0 = tid; a0 < span; a0 += BK_DILP * BK_THREADS) {
+                uint32_t pv[BK_DILP], ln[BK_DILP];
+#pragma unroll
+                for (int u = 0; u < BK_DILP; ++u) {
+                    const uint32_t a = a0 + u * BK_THREADS;
+                    ln[u] = 0;
+                    pv[u] = 0;
+                    if (a < span) {
+                        const uint32_t d = block_run[a >> blk_shift];
+                        const uint32_t X = runX[d] - base, Lr = runL[d], j = a - X;
+                        if (j < Lr) {
+                            const uint32_t id = image[a];
+                            uint32_t e = j;
+                            while (e + 1 < Lr && image[X + e + 1] == id) ++e;
+                            if (e + 1 < Lr && image[X + e + 1] < id) *unsorted_flag = 1u;
+                            ln[u] = e + 1;
+                            pv[u] = id;
+                            if (STATS) { updates += e + 1; groups += (e == j); }
+                        } else if (j < ((Lr + 7u) & ~7u)) {
+                            image[a] = 0xffffu;      // the rest of the run's last 16-byte unit reads as "no sequence"
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < BK_DILP; ++u)
+                    if (ln[u]) pv[u] = atomicAdd(&fill[(size_t)slot * nseq + pv[u]], 1u);
+#pragma unroll
+                for (int u = 0; u < BK_DILP; ++u)
+                    if (ln[u]) {
+                        const uint32_t X = runX[block_run[(a0 + u * BK_THREADS) >> blk_shift]];
+                        task[(size_t)slot * n + pv[u]] = make_uint2(xunit0 + (X >> 3), ln[u]);
+                    }
+            }
+            __syncthreads();
+            // image -> HBM, 16 bytes per thread and step (xbase and the padded run starts are multiples of 8 ids)
+            const uint4* __restrict__ src = reinterpret_cast<const uint4*>(image);
+            uint4* __restrict__ dst = reinterpret_cast<uint4*>(gids + base);
+            const uint32_t nvec = (span + 7u) >> 3;
+            for (uint32_t i = tid; i < nvec; i += BK_THREADS) dst[i] = src[i];
+        } else {
+            const uint32_t Lr = runL[d0];
+            for (uint32_t j = tid; j < Lr; j += BK_THREADS) {
+                const uint32_t id = sid[j];
+                uint32_t e = j;
+                while (e + 1 < Lr && sid[e + 1] == id) ++e;
+                if (e + 1 < Lr && sid[e + 1] < id) *unsorted_flag = 1u;
+                const uint32_t pos = atomicAdd(&fill[(size_t)slot * nseq + id], 1u);
+                task[(size_t)slot * n + pos] = make_uint2(xunit0 + (base >> 3), e + 1);
+                if (STATS) { updates += e + 1; groups += (e == j); }
+            }
+            const uint32_t pend = (Lr + 7u) & ~7u;
+            if (Lr + tid < pend) sid[Lr + tid] = 0xffffu;
+        }
+        __syncthreads();                                             // the next round reuses the image and block_run
+        d0 = d1;
     }
     if (STATS) {
         uint32_t nruns = (tid < (int)DL && runL[tid] > 0) ? 1u : 0u;

@@ -55,7 +55,7 @@ struct fsk_handle {
     int opt_l2_fetch = 0;            // experiment: cudaLimitMaxL2FetchGranularity (0 = leave alone)
     int opt_seg_occ = 0;             // experiment: segment_kernel variant (0 = 16 rows per warp, 3 CTAs/SM; 1-3 = 8 rows, 4/5/6 CTAs/SM)
     int seg_rows = SEG_ROWS_DEFAULT;
-    int opt_seg_fused = 0;           // 0 auto, 1 off, 2 on: fused last sort pass + segmentation (fsk_bucket.cuh) for two-digit keys
+    int opt_seg_fused = 0;           // 0 auto (= off), 1 off, 2 on: fused last sort pass + segmentation (fsk_bucket.cuh) for two-digit keys
     bool fused_seg = false;
     uint32_t image_cap = 0;          // ids in the shared-memory image of a bucket
     int opt_seg_exp = 0;             // timing experiments on segment_kernel (results are wrong when != 0; the accumulate is skipped)
@@ -801,14 +801,21 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         const bool fused_ok = h->plan.npass == 2 && h->mode == MODE_R32 && h->ids16 && h->rows_path;
         if (h->opt_seg_fused == 2 && !fused_ok)
             return fail(h, FSK_EINVAL, "seg_fused = 2 needs keys of two radix digits (9..16 bits), 32-bit records and 16-bit ids");
-        h->fused_seg = fused_ok && h->opt_seg_fused != 1;
+        // measured on B200 (profiles/r01_fused_bucket_experiment.txt): the fused kernel halves the sort time but its task
+        // filing (global atomics with return + scattered 8-byte stores) is no faster than segment_kernel's, and the 64-byte run
+        // alignment it needs costs the accumulate 4 %: 1280 against 1346 combinations/s on configs[3].  Opt-in only.
+        h->fused_seg = fused_ok && h->opt_seg_fused == 2;
         if (h->fused_seg) {
             const int lo_bits = h->plan.bits[0], hi_bits = h->plan.bits[1];
             const int64_t cap2 = ((nfeat + 63) / 64 * 64) + ((int64_t)1 << hi_bits) * (int64_t)bucket_id_stride(lo_bits) + 64;
             if (cap2 >= (1LL << 30)) return fail(h, FSK_EINVAL, "too many g-mers (%lld) for the aligned id stream", (long long)nfeat);
             h->ids_stride = std::max(h->ids_stride, (size_t)((cap2 + 63) / 64 * 64));
-            const int64_t cap_max = (((int64_t)max_smem - 1024 - (int64_t)bucket_smem_bytes(0)) / 2) & ~7LL;
-            h->image_cap = (uint32_t)std::max<int64_t>(64, std::min<int64_t>(cap_max, (nfeat + 64 * ((int64_t)1 << lo_bits) + 64) & ~7LL));
+            // two CTAs per SM: each may take half of the SM's shared memory less the 1 KB the system reserves per CTA
+            h->pad_mask = 31;   // runs start on 64-byte boundaries (the DRAM access granularity); the kernel maps image positions
+                                // to runs by 32-id blocks.  128-byte lines would cost 51 pad ids per 141-id run of configs[3].
+            const int64_t per_cta = ((int64_t)max_smem + 1024) / 2 - 1024 - 512;
+            const int64_t cap_max = ((per_cta - (int64_t)bucket_smem_bytes(0)) * 32 / 66) & ~63LL;
+            h->image_cap = (uint32_t)std::max<int64_t>(64, std::min<int64_t>(cap_max, (nfeat + 64 * ((int64_t)1 << lo_bits) + 127) & ~63LL));
             CU(cudaFuncSetAttribute(bucket_segment_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bucket_smem_bytes(h->image_cap)));
             CU(cudaFuncSetAttribute(bucket_segment_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bucket_smem_bytes(h->image_cap)));
         }
