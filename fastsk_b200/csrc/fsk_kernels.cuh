@@ -873,7 +873,7 @@ __global__ void to_f64_kernel(const T* __restrict__ in, double* __restrict__ out
 // fixed order, so a run is reproducible.
 constexpr int WELFORD_BLOCKS = 592;   // 4 x 148 SMs
 template <typename AccT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)     // 4 CTAs per SM: the 592 blocks are one full wave
 welford_kernel(AccT* __restrict__ Ks, double* __restrict__ K_hat, int64_t n_pairs, int64_t n_train_pairs, int iter,
                double* __restrict__ block_sums) {
     __shared__ double ws[8];
