@@ -159,7 +159,8 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
 // + klen) of C and adds into K + g * out_group_stride (integer modes: one group; variance mode: one per slot).
 __global__ void __launch_bounds__(DG_THREADS)
 syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restrict__ tile_order, int64_t nseq, uint32_t k_begin,
-               uint32_t k_group, uint32_t klen, unsigned long long* __restrict__ K, size_t out_group_stride) {
+               uint32_t k_group, uint32_t klen, unsigned long long* __restrict__ K, size_t out_group_stride,
+               const WelfordSpec* __restrict__ wf) {
     extern __shared__ uint8_t dg_smem_raw[];
     const uint32_t raw = smem_u32(dg_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                 // swizzle atoms need 1024-byte alignment
@@ -231,21 +232,64 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restr
         const uint32_t q = (uint32_t)warp & 3u;                               // the TMEM lane quarter this warp can read
         mbar_wait(tmem_full, 0);
         tc_fence_after();
-        const int64_t i = (int64_t)I * DG_TILE + q * 32 + lane;
-        unsigned long long* __restrict__ Krow = K + (size_t)blockIdx.y * out_group_stride + (size_t)(i * (i + 1) / 2);
+        // The accumulator comes out of TMEM one row per thread; it goes through a padded shared-memory transpose (the pipeline
+        // stages are free by now: every MMA has completed) so that the 32 lanes of a warp touch 32 CONSECUTIVE cells of one
+        // row of the packed triangle: coalesced 256-byte accesses instead of 32 rows x 8 bytes.
+        float* __restrict__ ts = reinterpret_cast<float*>(dg_smem_raw + (base - raw)) + (warp - 2) * (32 * 33);
+        const int64_t ibase = (int64_t)I * DG_TILE + q * 32;
         const int64_t j0 = (int64_t)J * DG_TILE;
+        const bool variance = wf != nullptr;
+        double* __restrict__ kh = variance ? wf->khat[blockIdx.y] : nullptr;
+        const double diter = variance ? (double)wf->iter[blockIdx.y] : 1.0;
+        const int64_t n_train = variance ? wf->n_train : 0;
+        unsigned long long* __restrict__ Kg = K + (size_t)blockIdx.y * out_group_stride;
+        double acc = 0.0;
 #pragma unroll 1
         for (int c0 = 0; c0 < DG_TILE; c0 += 32) {
             uint32_t v[32];
             tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + (uint32_t)c0, v);
-            if (i < nseq) {
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const int64_t j = j0 + c0 + c;
-                    const uint32_t u = __float2uint_rn(__uint_as_float(v[c]));
-                    if (j <= i && u) atomicAdd(&Krow[j], (unsigned long long)u);   // RED.ADD.64: the tile is owned by this CTA
+            for (int c = 0; c < 32; ++c) ts[lane * 33 + c] = __uint_as_float(v[c]);
+            __syncwarp();
+            const int64_t j = j0 + c0 + lane;
+#pragma unroll 1
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+                if (variance) {
+                    // variance mode: the tile is this iteration's partial kernel of the slot's stream; the Welford step on the
+                    // stream's running mean happens here (fastsk_kernel.cpp:121-135), eight rows' loads in flight
+                    double k0[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int64_t i = ibase + r0 + u;
+                        k0[u] = (i < nseq && j <= i) ? kh[(size_t)(i * (i + 1) / 2 + j)] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int64_t i = ibase + r0 + u;
+                        if (i < nseq && j <= i) {
+                            const double ks = (double)__float2uint_rn(ts[(r0 + u) * 33 + lane]);
+                            const double delta = __dsub_rn(ks, k0[u]);
+                            const double nh = __dadd_rn(k0[u], __ddiv_rn(delta, diter));
+                            kh[(size_t)(i * (i + 1) / 2 + j)] = nh;
+                            if (i < n_train) acc = __dadd_rn(acc, __dmul_rn(delta, __dsub_rn(ks, nh)));
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int64_t i = ibase + r0 + u;
+                        const uint32_t cnt = __float2uint_rn(ts[(r0 + u) * 33 + lane]);
+                        if (i < nseq && j <= i && cnt)
+                            atomicAdd(&Kg[(size_t)(i * (i + 1) / 2 + j)], (unsigned long long)cnt);   // RED.ADD.64: the tile is owned by this CTA
+                    }
                 }
             }
+            __syncwarp();
+        }
+        if (variance) {   // one partial sum of delta * delta2 per epilogue warp, added up in a fixed order by welford_final_kernel
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+            if (lane == 0) wf->sums[(size_t)blockIdx.y * wf->sums_stride + (size_t)blockIdx.x * 4 + q] = acc;
         }
     }
     tc_fence_before();

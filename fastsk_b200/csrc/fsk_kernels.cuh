@@ -40,6 +40,17 @@ struct SortPlan {
     uint8_t bits[MAX_PASS];
 };
 
+// Variance mode with the Welford step fused into the accumulate's flush (fastsk_kernel.cpp:108-143): the running mean of
+// the virtual stream that owns each slot, its iteration number, and where the per-CTA sums of delta * delta2 go.  Lives
+// in device memory; the host rewrites it before every round.
+struct WelfordSpec {
+    double* khat[MAX_BATCH];
+    int32_t iter[MAX_BATCH];
+    double* sums;                // [slot][sums_stride]
+    uint32_t sums_stride;
+    int64_t n_train;             // rows below n_train are the train x train block (the first n_train_pairs cells)
+};
+
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -679,7 +690,7 @@ template <typename AccT, typename IdT, int UNROLL, int HINT, bool PIPE = false>
 __global__ void __launch_bounds__(1024)
 accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uint2* __restrict__ task,
                        const uint32_t* __restrict__ woff, uint32_t n, uint32_t row_hi, int slots_per_group,
-                       AccT* __restrict__ K, size_t k_group_stride) {
+                       AccT* __restrict__ K, size_t k_group_stride, const WelfordSpec* __restrict__ wf) {
     constexpr int PER = 16 / sizeof(IdT);
     constexpr int SH = PER == 8 ? 3 : 2;
     extern __shared__ uint32_t row[];
@@ -776,6 +787,33 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
         }
     }
     __syncthreads();
+    if (wf) {
+        // variance mode: the row holds this iteration's partial kernel Ks of the slot's stream; apply the Welford step to the
+        // stream's running mean right here (no Ks in HBM, no separate pass): fastsk_kernel.cpp:121-135
+        __shared__ double ws[32];
+        double* __restrict__ kh = wf->khat[group] + ((size_t)b * (b + 1) >> 1);
+        const double diter = (double)wf->iter[group];
+        const bool train = (int64_t)b < wf->n_train;
+        double acc = 0.0;
+        for (uint32_t i = threadIdx.x; i <= b; i += blockDim.x) {
+            const double ks = (double)row[i];
+            const double k0 = kh[i];
+            const double delta = __dsub_rn(ks, k0);
+            const double nh = __dadd_rn(k0, __ddiv_rn(delta, diter));
+            kh[i] = nh;
+            if (train) acc = __dadd_rn(acc, __dmul_rn(delta, __dsub_rn(ks, nh)));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+        if (lane == 0) ws[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) t = __dadd_rn(t, ws[w]);
+            wf->sums[(size_t)group * wf->sums_stride + b] = t;
+        }
+        return;
+    }
     AccT* __restrict__ Krow = K + (size_t)group * k_group_stride + ((size_t)b * (b + 1) >> 1);
     for (uint32_t i = threadIdx.x; i <= b; i += blockDim.x) {
         const uint32_t v = row[i];
@@ -920,8 +958,11 @@ welford_kernel(AccT* __restrict__ Ks, double* __restrict__ K_hat, int64_t n_pair
     }
 }
 
-__global__ void welford_final_kernel(const double* __restrict__ block_sums, int nblocks, double* __restrict__ out) {
+// grid = slots: block s adds the nblocks partial sums of slot s (block_sums + s * stride) in a fixed order
+__global__ void welford_final_kernel(const double* __restrict__ block_sums_all, size_t stride, int nblocks, double* __restrict__ out_all) {
     __shared__ double ws[32];
+    const double* __restrict__ block_sums = block_sums_all + (size_t)blockIdx.x * stride;
+    double* __restrict__ out = out_all + blockIdx.x;
     double acc = 0.0;
     for (int i = threadIdx.x; i < nblocks; i += blockDim.x) acc = __dadd_rn(acc, block_sums[i]);
 #pragma unroll

@@ -119,6 +119,9 @@ struct fsk_handle {
     double* d_Kf = nullptr;                 // fp64 partial (variance mode): sum of local K_hat
     double *d_diag = nullptr, *d_train = nullptr, *d_test = nullptr;
     double *d_block_sums = nullptr, *d_var = nullptr;
+    WelfordSpec* d_wf = nullptr;            // variance mode: per-slot running means for the fused Welford flush
+    bool wf_active = false;                 // the batch being launched carries d_wf
+    uint32_t sums_stride = WELFORD_BLOCKS;  // partial sums per slot
     unsigned long long* d_counters = nullptr;   // entries, runs, pair updates
     uint32_t* d_flag = nullptr;                 // set by segment_kernel when a sorted batch is not non-decreasing
 
@@ -186,7 +189,7 @@ void release_device(fsk_handle* h) {
     for (auto& p : h->d_Khat) dev_free(p);
     h->d_Khat.clear();
     dev_free(h->d_diag); dev_free(h->d_train); dev_free(h->d_test);
-    dev_free(h->d_block_sums); dev_free(h->d_var); dev_free(h->d_counters); dev_free(h->d_flag);
+    dev_free(h->d_block_sums); dev_free(h->d_var); dev_free(h->d_wf); dev_free(h->d_counters); dev_free(h->d_flag);
     for (auto& s : h->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     h->spans.clear();
     for (auto e : h->event_pool) cudaEventDestroy(e);
@@ -375,7 +378,8 @@ int launch_accumulate(fsk_handle* h, int nb, unsigned long long* K, size_t slot_
                         : h->opt_acc_unroll == 8 ? accumulate_rows_kernel<unsigned long long, IdT, 8, 0>
                                               : accumulate_rows_kernel<unsigned long long, IdT, 4, 0>;
             kern<<<grid, h->rows_threads, h->rows_smem, h->ls>>>(
-                ids, h->ids_stride, h->d_task[h->buf], h->d_woff32, n, (uint32_t)hi, per_group, K, slot_stride);
+                ids, h->ids_stride, h->d_task[h->buf], h->d_woff32, n, (uint32_t)hi, per_group, K, slot_stride,
+                h->wf_active ? h->d_wf : nullptr);
             h->launches++;
         }
     } else {
@@ -409,12 +413,13 @@ int run_batch_dense(fsk_handle* h, int nb, const BatchSpec& spec, unsigned long 
         const unsigned T = (unsigned)((h->N + DG_TILE - 1) / DG_TILE);
         const unsigned tiles = T * (T + 1) / 2;
         if (slot_stride) {   // variance mode: every slot contracts its own k-mer columns into its own Ks
-            syrk_tc_kernel<<<dim3(tiles, (unsigned)nb), DG_THREADS, DG_SMEM, h->ls>>>(h->tmap_C, h->d_tile_order, h->N, 0u, h->nks, h->nks, K, slot_stride);
+            syrk_tc_kernel<<<dim3(tiles, (unsigned)nb), DG_THREADS, DG_SMEM, h->ls>>>(h->tmap_C, h->d_tile_order, h->N, 0u, h->nks, h->nks, K, slot_stride,
+                                                                                          h->wf_active ? h->d_wf : nullptr);
             h->launches++;
         } else {
             for (int c0 = 0; c0 < nb; c0 += h->dense_chunk) {
                 const int cs = std::min(h->dense_chunk, nb - c0);
-                syrk_tc_kernel<<<dim3(tiles, 1), DG_THREADS, DG_SMEM, h->ls>>>(h->tmap_C, h->d_tile_order, h->N, (uint32_t)c0 * h->nks, 0u, (uint32_t)cs * h->nks, K, 0);
+                syrk_tc_kernel<<<dim3(tiles, 1), DG_THREADS, DG_SMEM, h->ls>>>(h->tmap_C, h->d_tile_order, h->N, (uint32_t)c0 * h->nks, 0u, (uint32_t)cs * h->nks, K, 0, nullptr);
                 h->launches++;
             }
         }
@@ -989,14 +994,21 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     CU(cudaMemsetAsync(h->d_flag, 0, sizeof(uint32_t), h->stream));
 
     // accumulators
-    h->ks_slots = h->variance_mode ? B : 1;
+    // variance mode keeps a per-slot Ks only on the global-RED path; the row and dense paths fold the Welford step into the
+    // accumulate and never materialise Ks
+    h->ks_slots = (h->variance_mode && !(h->rows_path || h->dense_path)) ? B : 1;
     ALLOC(h->d_Kint, (size_t)h->ks_slots * h->n_pairs);
     CU(cudaMemsetAsync(h->d_Kint, 0, sizeof(unsigned long long) * (size_t)h->ks_slots * h->n_pairs, h->stream));
     if (h->variance_mode) {
         ALLOC(h->d_Kf, h->n_pairs);
         CU(cudaMemsetAsync(h->d_Kf, 0, sizeof(double) * (size_t)h->n_pairs, h->stream));
-        ALLOC(h->d_block_sums, (size_t)B * WELFORD_BLOCKS);
+        // partial sums of the variance per slot: one per Welford block, per row (fused flush of the row path) or per epilogue
+        // warp of every tile (fused epilogue of the dense path)
+        const int64_t Tt = (N + DG_TILE - 1) / DG_TILE;
+        h->sums_stride = (uint32_t)std::max<int64_t>(WELFORD_BLOCKS, h->dense_path ? 2 * Tt * (Tt + 1) : N);
+        ALLOC(h->d_block_sums, (size_t)B * h->sums_stride);
         ALLOC(h->d_var, B);
+        ALLOC(h->d_wf, 1);
     }
     CU(cudaStreamSynchronize(h->stream));
     cudaFree(d_codes); cudaFree(d_off); cudaFree(d_woff);
@@ -1081,12 +1093,13 @@ int build_partial_once(fsk_handle* h) {
         std::vector<Stream> streams;
         std::vector<int32_t> my_streams;
         shard_work(h, my_streams);
-        for (int tid : my_streams) {
-            double* kh;
-            ALLOC(kh, h->n_pairs);
-            h->d_Khat.push_back(kh);
-            CU(cudaMemsetAsync(kh, 0, sizeof(double) * (size_t)h->n_pairs, h->stream));
-            streams.push_back({tid, tid, 1, true, kh});
+        if (!my_streams.empty()) {   // one allocation for the running means of all local streams (cudaMalloc/cudaFree are slow)
+            double* all;
+            ALLOC(all, (size_t)h->n_pairs * my_streams.size());
+            h->d_Khat.push_back(all);
+            CU(cudaMemsetAsync(all, 0, sizeof(double) * (size_t)h->n_pairs * my_streams.size(), h->stream));
+            for (size_t i = 0; i < my_streams.size(); ++i)
+                streams.push_back({my_streams[i], my_streams[i], 1, true, all + i * (size_t)h->n_pairs});
         }
         std::vector<double> var_host((size_t)h->B);
         while (true) {
@@ -1097,18 +1110,38 @@ int build_partial_once(fsk_handle* h) {
                 const int nb = (int)std::min<size_t>((size_t)h->B, active.size() - a0);
                 int32_t combos[MAX_BATCH];
                 for (int s = 0; s < nb; ++s) combos[s] = h->queue[(size_t)active[a0 + s]->item];
-                rc = run_batch(h, combos, nb, h->d_Kint, (size_t)h->n_pairs);   // Ks of each slot is zero on entry
+                // row path and dense path: the Welford step is the flush / epilogue of the accumulate itself (no Ks in HBM);
+                // global-RED path: Ks of each slot (zero on entry) and a separate Welford pass
+                const bool fused_wf = h->rows_path || h->dense_path;
+                int n_sums = WELFORD_BLOCKS;
+                if (fused_wf) {
+                    WelfordSpec wf;
+                    memset(&wf, 0, sizeof wf);
+                    for (int s = 0; s < nb; ++s) { wf.khat[s] = active[a0 + s]->khat; wf.iter[s] = active[a0 + s]->iter; }
+                    wf.sums = h->d_block_sums;
+                    wf.sums_stride = h->sums_stride;
+                    wf.n_train = h->n_train;
+                    CU(cudaMemcpyAsync(h->d_wf, &wf, sizeof wf, cudaMemcpyHostToDevice, h->stream));
+                    const int64_t Tt = (h->N + DG_TILE - 1) / DG_TILE;
+                    n_sums = h->dense_path ? (int)(2 * Tt * (Tt + 1)) : (int)h->N;
+                }
+                h->wf_active = fused_wf;
+                rc = run_batch(h, combos, nb, h->d_Kint, (size_t)h->n_pairs);
+                h->wf_active = false;
                 if (rc) return rc;
                 {
                     Span sp(h, PC_WELFORD);
                     for (int s = 0; s < nb; ++s) {
                         Stream* st = active[a0 + s];
-                        welford_kernel<unsigned long long><<<WELFORD_BLOCKS, 256, 0, h->stream>>>(
-                            h->d_Kint + (size_t)s * h->n_pairs, st->khat, h->n_pairs, h->n_train_pairs, st->iter,
-                            h->d_block_sums + (size_t)s * WELFORD_BLOCKS);
-                        welford_final_kernel<<<1, 256, 0, h->stream>>>(h->d_block_sums + (size_t)s * WELFORD_BLOCKS, WELFORD_BLOCKS, h->d_var + s);
-                        h->launches += 2;
+                        if (!fused_wf) {
+                            welford_kernel<unsigned long long><<<WELFORD_BLOCKS, 256, 0, h->stream>>>(
+                                h->d_Kint + (size_t)s * h->n_pairs, st->khat, h->n_pairs, h->n_train_pairs, st->iter,
+                                h->d_block_sums + (size_t)s * h->sums_stride);
+                            h->launches++;
+                        }
                     }
+                    welford_final_kernel<<<nb, 256, 0, h->stream>>>(h->d_block_sums, (size_t)h->sums_stride, n_sums, h->d_var);
+                    h->launches++;
                     CU(cudaGetLastError());
                 }
                 CU(cudaMemcpyAsync(var_host.data(), h->d_var, sizeof(double) * (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
