@@ -42,9 +42,9 @@ sys.path.insert(0, ROOT)
 
 G, M, N_SEQ, N_TRAIN, SEQ_LEN = 16, 8, 50000, 40000, 200
 METRIC, UNIT = "gkm_kernel_build_combinations_per_s", "combinations/s"
-# dram__bytes_read.sum + dram__bytes_write.sum of accumulate_rows_kernel for one batch of 48 combinations of this workload
-# (all rows in one launch, option wave=400), from the ncu --set full capture profiles/r01_ncu_accumulate_rows_full_batch.txt
-TRAFFIC_ACC_BATCH48 = 129.063252e9 + 10.002295e9
+# dram__bytes_read.sum + dram__bytes_write.sum of accumulate_rows_kernel for one batch of 96 combinations of this workload
+# (all rows in one launch, option wave=400), from the ncu --set full capture profiles/r01_ncu_accumulate_rows_batch96.txt
+TRAFFIC_ACC_BATCH96 = 169.345743e9 + 10.008757e9
 
 
 def synthetic(n=N_SEQ):
@@ -292,13 +292,14 @@ def run_b200(args):
     sort_bytes = combos_rank * nfeat * ((gw_bytes + 4 + rec) + 2 * rec * st1["sort_passes"] + (rec + id_bytes + 8))
     sort_s = (d["ms_pack"] + d["ms_sort"] + d["ms_segment"]) * 1e-3
     roofline = {"kernel": "accumulate_rows_kernel", "bound": "hbm", "achieved": acc_bytes / acc_s / 1e9 if acc_s else None,
-                "peak": peak, "unit": "GB/s", "frac": (acc_bytes / acc_s / 1e9 / peak) if acc_s else None, "traffic": TRAFFIC_ACC_BATCH48 * st1["batch"] / 48.0, "traffic_unit": "bytes per batch (ncu dram read + write)",
+                "peak": peak, "unit": "GB/s", "frac": (acc_bytes / acc_s / 1e9 / peak) if acc_s else None, "traffic": TRAFFIC_ACC_BATCH96 * st1["batch"] / 96.0, "traffic_unit": "bytes per batch (ncu dram read + write)",
                 "achieved_per_launch_bytes": acc_bytes / batches,
                 "peak_source": peak_src, "share_of_step": d["ms_accumulate"] / d["ms_total"] if d["ms_total"] else None,
                 "algorithmic_bytes": f"{id_bytes} B x unit pair-updates (ids of the run prefixes) + 16 B x packed-triangle cells per batch",
                 "launch": "one batch = all row waves of the kernel (launched in waves for L2 locality)",
-                "note": "bound by the HBM gather of ~140-byte id ranges at 64-byte DRAM granularity (ncu: 139 GB moved per batch for 83 GB "
-                        "algorithmic = 4.5 TB/s, 69 % of the measured copy peak) together with shared-memory atomics (smem wavefronts 54-64 %)",
+                "note": "co-limited: ncu (batch 96) shows 179 GB of DRAM traffic for 147 GB algorithmic = 3.7 TB/s (57 % of the measured copy peak; "
+                        "64-byte granularity of the ~140-byte id prefixes, L2 hit rate 5 %), the L1/LSU pipe at 76 % and shared-memory atomic "
+                        "wavefronts at 60 % (4.2 wavefronts per 32-lane atomic from bank conflicts)",
                 "pair_updates_per_s": updates / acc_s if acc_s else None}
     roofline_sort = {"kernel": "pack_hist + onesweep passes + segment", "bound": "hbm", "achieved": sort_bytes / sort_s / 1e9 if sort_s else None,
                      "peak": peak, "unit": "GB/s", "frac": (sort_bytes / sort_s / 1e9 / peak) if sort_s else None,

@@ -668,18 +668,23 @@ __device__ __forceinline__ void smem_inc(uint32_t* row, uint32_t byte_off) {
     atomicAdd(reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(row) + byte_off), 1u);
 }
 
+// col0: first column of K held by this CTA's shared-memory row (0 unless the row is split over several CTAs because N
+// columns do not fit).  id - col0 wraps for ids below col0 -- to at least 2^16 - col0 >= dump in 16-bit arithmetic because
+// N + 32 <= 2^16 there -- so one unsigned min sends both the ids before the window and those after it to the dump words.
 template <typename IdT>
-__device__ __forceinline__ void apply_unit(uint32_t* row, const uint4 v, const uint32_t dump) {
+__device__ __forceinline__ void apply_unit(uint32_t* row, const uint4 v, const uint32_t dump, const uint32_t col0) {
     if (sizeof(IdT) == 2) {
         const uint32_t d2 = dump | (dump << 16);           // dump <= 0xffff whenever ids are 16-bit
-        const uint32_t a = __vminu2(v.x, d2), b = __vminu2(v.y, d2), c = __vminu2(v.z, d2), d = __vminu2(v.w, d2);
+        const uint32_t c2 = col0 | (col0 << 16);
+        const uint32_t a = __vminu2(__vsub2(v.x, c2), d2), b = __vminu2(__vsub2(v.y, c2), d2), c = __vminu2(__vsub2(v.z, c2), d2),
+                       d = __vminu2(__vsub2(v.w, c2), d2);
         smem_inc(row, (a << 2) & 0x3fffcu); smem_inc(row, (a >> 14) & 0x3fffcu);
         smem_inc(row, (b << 2) & 0x3fffcu); smem_inc(row, (b >> 14) & 0x3fffcu);
         smem_inc(row, (c << 2) & 0x3fffcu); smem_inc(row, (c >> 14) & 0x3fffcu);
         smem_inc(row, (d << 2) & 0x3fffcu); smem_inc(row, (d >> 14) & 0x3fffcu);
     } else {
-        atomicAdd(&row[min(v.x, dump)], 1u); atomicAdd(&row[min(v.y, dump)], 1u);
-        atomicAdd(&row[min(v.z, dump)], 1u); atomicAdd(&row[min(v.w, dump)], 1u);
+        atomicAdd(&row[min(v.x - col0, dump)], 1u); atomicAdd(&row[min(v.y - col0, dump)], 1u);
+        atomicAdd(&row[min(v.z - col0, dump)], 1u); atomicAdd(&row[min(v.w - col0, dump)], 1u);
     }
 }
 
@@ -690,7 +695,8 @@ template <typename AccT, typename IdT, int UNROLL, int HINT, bool PIPE = false>
 __global__ void __launch_bounds__(1024)
 accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uint2* __restrict__ task,
                        const uint32_t* __restrict__ woff, uint32_t n, uint32_t row_hi, int slots_per_group,
-                       AccT* __restrict__ K, size_t k_group_stride, const WelfordSpec* __restrict__ wf) {
+                       AccT* __restrict__ K, size_t k_group_stride, const WelfordSpec* __restrict__ wf, uint32_t col0,
+                       uint32_t col_width, uint32_t sums_off) {
     constexpr int PER = 16 / sizeof(IdT);
     constexpr int SH = PER == 8 ? 3 : 2;
     extern __shared__ uint32_t row[];
@@ -701,11 +707,14 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
     const uint32_t wb = woff[b], nw = woff[b + 1] - wb;
     const uint32_t cps = (nw + 31) >> 5;                     // chunks of 32 tasks per slot
     const uint32_t nchunks = cps * (uint32_t)slots_per_group;
+    // this CTA holds columns [col0, col0 + ncols) of row b (all b + 1 of them unless N columns exceed shared memory: then the
+    // host launches the row once per column window, and every window streams the row's tasks)
+    const uint32_t ncols = min(b + 1 - col0, col_width);
     if (threadIdx.x == 0) next_chunk = 0;
-    for (uint32_t i = threadIdx.x; i <= b + 32; i += blockDim.x) row[i] = 0;
+    for (uint32_t i = threadIdx.x; i < ncols + 32; i += blockDim.x) row[i] = 0;
     __syncthreads();
     const uint32_t lane_le = 0xffffffffu >> (31 - lane);
-    const uint32_t dump = b + 1 + lane;                      // 32 words behind the row
+    const uint32_t dump = ncols + lane;                      // 32 words behind the row
     const uint2* __restrict__ task_g = task + (size_t)group * slots_per_group * n + wb;
     const IdT* __restrict__ ids_g = ids + (size_t)group * slots_per_group * ids_stride;
     // chunk c -> (slot, first task); the task of this lane, or an empty one
@@ -761,7 +770,7 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
         auto apply = [&](uint32_t base, const uint4 (&v)[UNROLL]) {
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u)
-                if (base + 32 * u + lane < W) apply_unit<IdT>(row, v[u], dump);
+                if (base + 32 * u + lane < W) apply_unit<IdT>(row, v[u], dump, col0);
         };
         if (PIPE) {
             uint4 va[UNROLL], vb[UNROLL];
@@ -791,11 +800,11 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
         // variance mode: the row holds this iteration's partial kernel Ks of the slot's stream; apply the Welford step to the
         // stream's running mean right here (no Ks in HBM, no separate pass): fastsk_kernel.cpp:121-135
         __shared__ double ws[32];
-        double* __restrict__ kh = wf->khat[group] + ((size_t)b * (b + 1) >> 1);
+        double* __restrict__ kh = wf->khat[group] + ((size_t)b * (b + 1) >> 1) + col0;
         const double diter = (double)wf->iter[group];
         const bool train = (int64_t)b < wf->n_train;
         double acc = 0.0;
-        for (uint32_t i = threadIdx.x; i <= b; i += blockDim.x) {
+        for (uint32_t i = threadIdx.x; i < ncols; i += blockDim.x) {
             const double ks = (double)row[i];
             const double k0 = kh[i];
             const double delta = __dsub_rn(ks, k0);
@@ -810,12 +819,12 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
         if (threadIdx.x == 0) {
             double t = 0.0;
             for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) t = __dadd_rn(t, ws[w]);
-            wf->sums[(size_t)group * wf->sums_stride + b] = t;
+            wf->sums[(size_t)group * wf->sums_stride + sums_off + b] = t;
         }
         return;
     }
-    AccT* __restrict__ Krow = K + (size_t)group * k_group_stride + ((size_t)b * (b + 1) >> 1);
-    for (uint32_t i = threadIdx.x; i <= b; i += blockDim.x) {
+    AccT* __restrict__ Krow = K + (size_t)group * k_group_stride + ((size_t)b * (b + 1) >> 1) + col0;
+    for (uint32_t i = threadIdx.x; i < ncols; i += blockDim.x) {
         const uint32_t v = row[i];
         if (v) atomicAdd(&Krow[i], (AccT)v);                 // RED: no read round trip on the flush
     }

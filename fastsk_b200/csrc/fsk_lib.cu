@@ -103,6 +103,9 @@ struct fsk_handle {
     bool rows_path = false;
     int rows_threads = 256;
     size_t rows_smem = 0;
+    int64_t col_width = 0;                             // columns of K per shared-memory row window (>= N: one window)
+    int col_windows = 1;
+    int opt_acc_cols = 0;                              // 0 auto, else forced window width (tests)
     int wave_rows = 148;                               // rows per accumulate launch
     int64_t maxwin = 0;
     // dense regime (fsk_dense.cuh): per-sequence k-mer counts of a batch, contracted on the tensor cores
@@ -366,8 +369,10 @@ int launch_accumulate(fsk_handle* h, int nb, unsigned long long* K, size_t slot_
         // slot_stride != 0 (variance mode): every slot adds into its own K; else all slots add into one K
         const int groups = slot_stride ? nb : 1, per_group = slot_stride ? 1 : nb;
         const int wave = std::max(1, h->wave_rows / groups);
-        for (int64_t hi = h->N - 1; hi >= 0; hi -= wave) {
-            dim3 grid((unsigned)std::min<int64_t>(wave, hi + 1), groups);
+        // one pass over the rows per column window of K (a single window unless N columns exceed shared memory)
+        for (int64_t col0 = 0, win = 0; col0 < h->N; col0 += h->col_width, ++win)
+        for (int64_t hi = h->N - 1; hi >= col0; hi -= wave) {
+            dim3 grid((unsigned)std::min<int64_t>(wave, hi - col0 + 1), groups);
             auto kern = h->opt_ld_hint == 1 ? accumulate_rows_kernel<unsigned long long, IdT, 4, 1>
                         : h->opt_ld_hint == 2 ? accumulate_rows_kernel<unsigned long long, IdT, 4, 2>
                         : h->opt_acc_pipe == 1 && h->opt_acc_unroll == 2 ? accumulate_rows_kernel<unsigned long long, IdT, 2, 0, true>
@@ -379,7 +384,7 @@ int launch_accumulate(fsk_handle* h, int nb, unsigned long long* K, size_t slot_
                                               : accumulate_rows_kernel<unsigned long long, IdT, 4, 0>;
             kern<<<grid, h->rows_threads, h->rows_smem, h->ls>>>(
                 ids, h->ids_stride, h->d_task[h->buf], h->d_woff32, n, (uint32_t)hi, per_group, K, slot_stride,
-                h->wf_active ? h->d_wf : nullptr);
+                h->wf_active ? h->d_wf : nullptr, (uint32_t)col0, (uint32_t)h->col_width, (uint32_t)(win * h->N));
             h->launches++;
         }
     } else {
@@ -646,6 +651,9 @@ int fsk_set_option(fsk_handle* h, const char* key, int64_t value) {
         h->opt_pad = (int)value;
     } else if (!strcmp(key, "seg_occ")) {
         h->opt_seg_occ = (int)value;
+    } else if (!strcmp(key, "acc_cols")) {
+        if (value != 0 && (value < 32 || value % 32)) return fail(h, FSK_EINVAL, "acc_cols must be 0 (auto) or a positive multiple of 32");
+        h->opt_acc_cols = (int)value;
     } else if (!strcmp(key, "seg_fused")) {
         if (value < 0 || value > 2) return fail(h, FSK_EINVAL, "seg_fused must be 0 (auto), 1 (off) or 2 (on)");
         h->opt_seg_fused = (int)value;
@@ -768,8 +776,16 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     int max_smem = 0, n_sm = 148;
     CU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device));
-    const bool rows_ok = (size_t)N * 4 + 128 + 1024 <= (size_t)max_smem && (double)maxwin * (double)maxwin < 4294967296.0;
-    if (h->opt_acc_path == 2 && !rows_ok) return fail(h, FSK_EINVAL, "acc_path = 2 needs N * 4 B <= %d B of shared memory", max_smem);
+    // a row of K that does not fit is split into column windows, each a pass of its own over the row's tasks (up to 16)
+    {
+        const int64_t fit = (((int64_t)max_smem - 1024 - 128) / 4) & ~31LL;           // columns one CTA can hold
+        const int64_t windows = h->opt_acc_cols ? (N + h->opt_acc_cols - 1) / h->opt_acc_cols : (N + fit - 1) / fit;
+        h->col_windows = (int)std::max<int64_t>(1, windows);
+        h->col_width = h->opt_acc_cols ? h->opt_acc_cols : std::min<int64_t>(fit, ((N + windows - 1) / windows + 31) & ~31LL);
+        if (h->opt_acc_cols && h->opt_acc_cols > fit) return fail(h, FSK_EINVAL, "acc_cols = %d exceeds the %lld columns a CTA can hold", h->opt_acc_cols, (long long)fit);
+    }
+    const bool rows_ok = h->col_windows <= 16 && (double)maxwin * (double)maxwin < 4294967296.0;
+    if (h->opt_acc_path == 2 && !rows_ok) return fail(h, FSK_EINVAL, "acc_path = 2 needs at most 16 column windows of K (N = %lld) and fewer than 65536 windows per sequence", (long long)N);
     h->rows_path = h->opt_acc_path == 2 || (h->opt_acc_path == 0 && rows_ok);
     {
         // dense regime: few distinct k-mers per combination, so K += C C^T on the tensor cores beats the sort + sparse
@@ -787,7 +803,7 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         h->nks = nks;
         if (h->dense_path) h->rows_path = false;
     }
-    h->rows_smem = (size_t)N * 4 + 128;   // + one dump word per lane for masked-off ids
+    h->rows_smem = (size_t)std::min<int64_t>(N, h->col_width) * 4 + 128;   // + one dump word per lane for masked-off ids
     h->rows_threads = N >= 16384 ? 1024 : (N >= 4096 ? 512 : 256);
     if (h->opt_rows_threads) h->rows_threads = h->opt_rows_threads;
     h->ids16 = N <= 65000;   // u16 ids leave room for the 32 dump words b + 1 + lane (packed 16-bit min in the accumulate)
@@ -1005,7 +1021,7 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         // partial sums of the variance per slot: one per Welford block, per row (fused flush of the row path) or per epilogue
         // warp of every tile (fused epilogue of the dense path)
         const int64_t Tt = (N + DG_TILE - 1) / DG_TILE;
-        h->sums_stride = (uint32_t)std::max<int64_t>(WELFORD_BLOCKS, h->dense_path ? 2 * Tt * (Tt + 1) : N);
+        h->sums_stride = (uint32_t)std::max<int64_t>(WELFORD_BLOCKS, h->dense_path ? 2 * Tt * (Tt + 1) : N * h->col_windows);
         ALLOC(h->d_block_sums, (size_t)B * h->sums_stride);
         ALLOC(h->d_var, B);
         ALLOC(h->d_wf, 1);
@@ -1123,8 +1139,10 @@ int build_partial_once(fsk_handle* h) {
                     wf.n_train = h->n_train;
                     CU(cudaMemcpyAsync(h->d_wf, &wf, sizeof wf, cudaMemcpyHostToDevice, h->stream));
                     const int64_t Tt = (h->N + DG_TILE - 1) / DG_TILE;
-                    n_sums = h->dense_path ? (int)(2 * Tt * (Tt + 1)) : (int)h->N;
+                    n_sums = h->dense_path ? (int)(2 * Tt * (Tt + 1)) : (int)(h->N * h->col_windows);
                 }
+                if (fused_wf && h->rows_path && h->col_windows > 1)   // rows below a column window write no partial sum for it
+                    CU(cudaMemsetAsync(h->d_block_sums, 0, sizeof(double) * (size_t)nb * h->sums_stride, h->stream));
                 h->wf_active = fused_wf;
                 rc = run_batch(h, combos, nb, h->d_Kint, (size_t)h->n_pairs);
                 h->wf_active = false;

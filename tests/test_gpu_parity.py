@@ -214,6 +214,31 @@ def test_dense_tensor_core_path_multi_tile_and_chunked(FastSK, oracle_mod):
         f.compute_train(random_seqs(rng, 5, 4, 20, 30))
 
 
+@pytest.mark.parametrize("cols", [32, 96])
+@pytest.mark.parametrize("case", [CASES[0], CASES[4], CASES[5], CASES[9]], ids=lambda c: c[0])
+def test_column_windows_of_the_row_path(FastSK, oracle_mod, case, cols):
+    """A row of K that does not fit in shared memory is split into column windows (N > ~56 000 in production); option
+    acc_cols forces small windows so that the multi-window path runs at test sizes: exact and variance mode."""
+    name, ntr, nte, alpha, (lo, hi), g, m, batch, lowc = case
+    rng = np.random.default_rng(5)
+    n = min(ntr + nte, 16 * cols)                             # at most 16 windows
+    X = random_seqs(rng, n, alpha, max(lo, g), hi, lowc)
+    queue = rng.permutation(comb(g, m))[:24].astype(np.int32)
+    f = FastSK(g, m, combo_sequence=queue)
+    f.set_option("acc_path", 2)
+    f.set_option("acc_cols", cols)
+    f.compute_train(X)
+    _, Ki, _ = oracle_mod.run("c", X, [], g, m, queue)
+    assert np.array_equal(f.get_unnormalised().astype(np.uint64), Ki)
+    f = FastSK(g, m, 3, True, 0.025, 6, False, combo_sequence=queue)
+    f.set_option("acc_path", 2)
+    f.set_option("acc_cols", cols)
+    f.compute_train(X)
+    K, _, sd = oracle_mod.run("c", X, [], g, m, queue, T=3, approx=True, delta=0.025, max_iters=6)
+    np.testing.assert_allclose(f.get_unnormalised(np.float64), K, rtol=RTOL, atol=0)
+    np.testing.assert_allclose(f.get_stdevs(), sd, rtol=RTOL, atol=0)
+
+
 FUSED_CASES = [
     # name, n, alphabet, len range, g, m, low complexity, batch
     ("dna_14bit", 120, 4, (40, 160), 12, 5, False, 0),          # 7 + 7 bits: 128 buckets x 128 runs
