@@ -160,7 +160,12 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
 __global__ void __launch_bounds__(DG_THREADS)
 syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restrict__ tile_order, int64_t nseq, uint32_t k_begin,
                uint32_t k_group, uint32_t klen, unsigned long long* __restrict__ K, size_t out_group_stride,
-               const WelfordSpec* __restrict__ wf) {
+               const WelfordSpec* __restrict__ wf, const uint32_t* __restrict__ klen_dev) {
+    // heavy-run contraction: the number of columns is only known on the device (heavy_fill_kernel's list)
+    if (klen_dev) {
+        klen = (min(*klen_dev, klen) + DG_BK - 1) / DG_BK * DG_BK;     // klen carries the capacity of the list
+        if (klen == 0) return;
+    }
     extern __shared__ uint8_t dg_smem_raw[];
     const uint32_t raw = smem_u32(dg_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                 // swizzle atoms need 1024-byte alignment
@@ -297,6 +302,61 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restr
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(DG_TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Heavy runs of the sparse regime ("dense contraction when the heavy-run C^T C update is dense").  A run of
+// d records costs d^2 / 2 shared-memory updates on the row path but only one column of a tensor-core contraction:
+// segment_kernel files the tasks of runs longer than heavy_tau empty and lists the runs; here each listed run becomes one
+// fp16 column of H[sequence][column] (count of the sequence's records in the run), and syrk_tc_kernel adds H H^T to K.
+// Break-even on B200: d > ~0.05 N (1.3e12 updates/s against 6e14 MAC/s).
+
+// zero the first roundup64(*count) columns of H
+__global__ void heavy_zero_kernel(__half* __restrict__ H, size_t ld, int64_t nseq, const uint32_t* __restrict__ count) {
+    const uint32_t cols = (min(*count, (uint32_t)ld) + DG_BK - 1) / DG_BK * DG_BK;   // ld = capacity of the list
+    if (cols == 0) return;
+    const uint32_t vec = cols / 8;                                   // 16-byte pieces per row
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nseq * vec; i += (int64_t)gridDim.x * blockDim.x)
+        reinterpret_cast<uint4*>(H + (size_t)(i / vec) * ld)[i % vec] = z;
+}
+
+// one CTA per listed run (grid-stride): find the run's end in the sorted records, then every group of equal sequence ids
+// writes its size into the run's column.  `total` accumulates the number of heavy runs since upload (statistics).
+template <typename RecT>
+__global__ void __launch_bounds__(256)
+heavy_fill_kernel(const RecT* __restrict__ rec, uint32_t n, int idbits, const uint2* __restrict__ list,
+                  const uint32_t* __restrict__ count, __half* __restrict__ H, size_t ld, unsigned long long* __restrict__ total) {
+    __shared__ uint32_t s_end;
+    const uint32_t nh = min(*count, (uint32_t)ld);                    // runs beyond the capacity stayed on the sparse path
+    if (blockIdx.x == 0 && threadIdx.x == 0 && total) atomicAdd(total, (unsigned long long)nh);
+    const RecT idmask = ((RecT)1 << idbits) - 1;
+    for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
+        const uint2 e = list[h];
+        const RecT* __restrict__ R = rec + (size_t)e.x * n;
+        const uint32_t rs = e.y;
+        if (threadIdx.x == 0) {                                      // first record after the run: the records are sorted by key
+            const RecT key = R[rs] >> idbits;
+            uint32_t lo = rs + 1, hi = n;
+            while (lo < hi) {
+                const uint32_t mid = lo + ((hi - lo) >> 1);
+                if ((R[mid] >> idbits) == key) lo = mid + 1;
+                else hi = mid;
+            }
+            s_end = lo;
+        }
+        __syncthreads();
+        const uint32_t d = s_end - rs;
+        for (uint32_t t = threadIdx.x; t < d; t += blockDim.x) {
+            const uint32_t id = (uint32_t)(R[rs + t] & idmask);
+            if (t == 0 || (uint32_t)(R[rs + t - 1] & idmask) != id) {
+                uint32_t c = 1;
+                while (t + c < d && (uint32_t)(R[rs + t + c] & idmask) == id) ++c;
+                H[(size_t)id * ld + h] = __uint2half_rn(c);
+            }
+        }
+        __syncthreads();
     }
 }
 

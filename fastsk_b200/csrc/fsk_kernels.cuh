@@ -404,7 +404,11 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
                size_t ids_stride, int idbits, uint32_t nseq, int unit_shift, uint32_t pad_mask, uint32_t* __restrict__ fill,
                IdT* __restrict__ ids, uint2* __restrict__ task, uint32_t* __restrict__ scan_status /* [slot][tile] */,
                uint32_t* __restrict__ ticket, uint32_t* __restrict__ unsorted_flag,
-               unsigned long long* __restrict__ stat_counters, int exp /* timing experiments only: 1-3 file tasks wrongly */) {
+               unsigned long long* __restrict__ stat_counters, int exp /* timing experiments only: 1-3 file tasks wrongly */,
+               uint32_t heavy_tau /* 0 = off: runs longer than this may leave the sparse path */, uint32_t* __restrict__ heavy_count,
+               uint2* __restrict__ heavy_list /* (slot, first sorted record) of every heavy run of the batch */, uint32_t heavy_cap,
+               uint32_t* __restrict__ heavy_bits /* [slot][units / 32]: bit set = the run starting at that id unit is in the list */,
+               size_t heavy_bits_stride) {
     using Ops = RecOps<RecT, KV>;
     constexpr int SEG_ROWS = ROWS;
     constexpr int SEG_WARP_RECS = SEG_ROWS * 32;
@@ -618,8 +622,27 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
             if (i < n) {
                 const uint32_t X = base + xs[h0 + k];
                 ids[(size_t)slot * ids_stride + X + (i - rs[h0 + k])] = (IdT)sq[h0 + k];
-                task[sbase + (exp == 2 ? i : pos[k])] = make_uint2(X >> unit_shift, len[h0 + k]);
-                updates += len[h0 + k];
+                uint32_t ln = len[h0 + k];
+                if (heavy_tau) {
+                    // a run of more than heavy_tau records is a (nearly) dense column of the count matrix: its d^2/2 updates go to
+                    // the tensor-core contraction (heavy_fill_kernel + syrk_tc_kernel) if the batch's list has room, and then the
+                    // accumulate skips its tasks.  The records are sorted, so the run is that long iff the record heavy_tau places
+                    // after its start has the same key.
+                    const uint32_t far = rs[h0 + k] + heavy_tau;
+                    if (far < n && Ops::same_key(R[far], r[h0 + k], idbits)) {
+                        ln |= 0x80000000u;                       // "ask heavy_bits": only the run's first record knows whether the list had room
+                        if (i == rs[h0 + k]) {
+                            const uint32_t at = atomicAdd(heavy_count, 1u);
+                            if (at < heavy_cap) {
+                                heavy_list[at] = make_uint2(slot, i);
+                                const uint32_t xu = X >> unit_shift;
+                                atomicOr(&heavy_bits[(size_t)slot * heavy_bits_stride + (xu >> 5)], 1u << (xu & 31u));
+                            }
+                        }
+                    }
+                }
+                task[sbase + (exp == 2 ? i : pos[k])] = make_uint2(X >> unit_shift, ln);
+                updates += ln & 0x7fffffffu;
             }
         }
     }
@@ -696,7 +719,7 @@ __global__ void __launch_bounds__(1024)
 accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uint2* __restrict__ task,
                        const uint32_t* __restrict__ woff, uint32_t n, uint32_t row_hi, int slots_per_group,
                        AccT* __restrict__ K, size_t k_group_stride, const WelfordSpec* __restrict__ wf, uint32_t col0,
-                       uint32_t col_width, uint32_t sums_off) {
+                       uint32_t col_width, uint32_t sums_off, const uint32_t* __restrict__ heavy_bits, size_t heavy_bits_stride) {
     constexpr int PER = 16 / sizeof(IdT);
     constexpr int SH = PER == 8 ? 3 : 2;
     extern __shared__ uint32_t row[];
@@ -729,6 +752,13 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
             const uint32_t s = c / cps;
             const uint32_t t = ((c - s * cps) << 5) + lane;
             if (t < nw) q = task_g[(size_t)s * n + t];
+            if (q.y >> 31) {   // long run (segment_kernel): an ordinary task unless the tensor-core contraction took the run
+                const uint32_t w = heavy_bits[((size_t)group * slots_per_group + s) * heavy_bits_stride + (q.x >> 5)];
+                q.y &= 0x7fffffffu;
+                // taken: the task must still own one unit (the expansion below hands positions to consecutive lanes, so no
+                // lane in the middle may be empty): the last unit of the slot's id stream, which is always 0xFF.. fill
+                if ((w >> (q.x & 31u)) & 1u) q = make_uint2((uint32_t)(ids_stride / PER) - 1u, 1u);
+            }
         }
         return q;
     };

@@ -25,6 +25,7 @@ std::string g_create_error;
 
 enum RecMode { MODE_R32 = 0, MODE_R64 = 1, MODE_KV = 2 };
 constexpr int SEG_TICKET = 16;   // d_ticket[0 .. MAX_PASS) belong to the sort passes
+constexpr int HEAVY_COUNT = 32;  // d_ticket[32]: heavy runs listed by segment_kernel in this batch (cleared with the tickets)
 enum ProfClass { PC_PACK = 0, PC_SORT, PC_SEGMENT, PC_ACCUMULATE, PC_WELFORD, PC_NORMALISE, PC_COUNT };
 
 struct ProfSpan {
@@ -114,6 +115,23 @@ struct fsk_handle {
     size_t dense_ld = 0;                               // fp16 elements per row of d_C (= B * nks)
     int dense_chunk = 1;                               // slots per GEMM: keeps every fp32 accumulator below 2^24
     __half* d_C = nullptr;
+    // heavy runs of the sparse regime: runs longer than heavy_tau leave the row path for a tensor-core contraction
+    int opt_heavy_tau = 0;                             // 0 auto, -1 off, > 0 forced threshold
+    int opt_heavy_cap = 0;                             // 0 auto, else columns of d_H (tests: a small list overflows)
+    uint32_t heavy_tau = 0;                            // 0 = feature off
+    uint32_t heavy_now = 0;                            // threshold in force for the batch being launched (0 while the feature sleeps)
+    uint32_t heavy_cap = 0;                            // columns of d_H = upper bound on the heavy runs of a batch
+    __half* d_H = nullptr;
+    uint2* d_heavy_list = nullptr;
+    uint32_t* d_heavy_bits = nullptr;                  // [slot][heavy_bits_stride] in the per-batch zero region
+    size_t heavy_bits_stride = 0;
+    // adaptive: when a batch lists no heavy run the feature sleeps (no marking, no launches) and is probed again every 32nd
+    // batch -- the sequences are the same for every combination, so run-length statistics hardly change between batches
+    bool heavy_live = true, heavy_probe_pending = false;
+    int heavy_idle = 0;
+    uint32_t* h_heavy_count = nullptr;                 // pinned
+    cudaEvent_t ev_heavy = nullptr;
+    CUtensorMap tmap_H;
     uint32_t* d_tile_order = nullptr;                  // lower-triangle tiles (I << 16 | J) in L2-friendly launch order
     CUtensorMap tmap_C;
     unsigned long long* d_Kint = nullptr;   // integer partial (exact / skip_variance), or per-slot Ks in variance mode
@@ -186,7 +204,7 @@ void release_device(fsk_handle* h) {
     dev_free(h->d_recA); dev_free(h->d_recB); dev_free(h->d_valA); dev_free(h->d_valB);
     dev_free(h->d_zero);
     h->d_ghist = h->d_ticket = h->d_status = h->d_seg_status = nullptr;
-    dev_free(h->d_woff32); dev_free(h->d_fill); dev_free(h->d_C); dev_free(h->d_tile_order);
+    dev_free(h->d_woff32); dev_free(h->d_fill); dev_free(h->d_C); dev_free(h->d_tile_order); dev_free(h->d_H); dev_free(h->d_heavy_list);
     for (int i = 0; i < 2; ++i) { dev_free(h->d_ids[i]); dev_free(h->d_task[i]); }
     dev_free(h->d_Kint); dev_free(h->d_Kf);
     for (auto& p : h->d_Khat) dev_free(p);
@@ -343,7 +361,8 @@ int launch_segment(fsk_handle* h, int nb) {
     const unsigned grid = h->seg_tiles * (unsigned)nb;
     const int ush = h->ids16 ? 3 : 2;
 #define SEG_ARGS (const RecT*)h->d_recA, h->d_valA, n, h->seg_tiles, h->ids_stride, h->idbits, (uint32_t)h->N, ush, h->pad_mask, h->d_fill
-#define SEG_ARGS2 h->d_task[h->buf], h->d_seg_status, h->d_ticket + SEG_TICKET, h->d_flag, stat, h->opt_seg_exp
+#define SEG_ARGS2 h->d_task[h->buf], h->d_seg_status, h->d_ticket + SEG_TICKET, h->d_flag, stat, h->opt_seg_exp, h->heavy_now, \
+                  h->d_ticket + HEAVY_COUNT, h->d_heavy_list, h->heavy_cap, h->d_heavy_bits, h->heavy_bits_stride
     if (h->seg_rows == 8 && h->opt_seg_occ == 1)
         segment_kernel<RecT, KV, uint16_t, 8, 4><<<grid, SEG_THREADS, 0, h->ls>>>(SEG_ARGS, (uint16_t*)h->d_ids[h->buf], SEG_ARGS2);
     else if (h->seg_rows == 8 && h->opt_seg_occ == 2)
@@ -384,7 +403,8 @@ int launch_accumulate(fsk_handle* h, int nb, unsigned long long* K, size_t slot_
                                               : accumulate_rows_kernel<unsigned long long, IdT, 4, 0>;
             kern<<<grid, h->rows_threads, h->rows_smem, h->ls>>>(
                 ids, h->ids_stride, h->d_task[h->buf], h->d_woff32, n, (uint32_t)hi, per_group, K, slot_stride,
-                h->wf_active ? h->d_wf : nullptr, (uint32_t)col0, (uint32_t)h->col_width, (uint32_t)(win * h->N));
+                h->wf_active ? h->d_wf : nullptr, (uint32_t)col0, (uint32_t)h->col_width, (uint32_t)(win * h->N), h->d_heavy_bits,
+                h->heavy_bits_stride);
             h->launches++;
         }
     } else {
@@ -419,12 +439,12 @@ int run_batch_dense(fsk_handle* h, int nb, const BatchSpec& spec, unsigned long 
         const unsigned tiles = T * (T + 1) / 2;
         if (slot_stride) {   // variance mode: every slot contracts its own k-mer columns into its own Ks
             syrk_tc_kernel<<<dim3(tiles, (unsigned)nb), DG_THREADS, DG_SMEM, h->ls>>>(h->tmap_C, h->d_tile_order, h->N, 0u, h->nks, h->nks, K, slot_stride,
-                                                                                          h->wf_active ? h->d_wf : nullptr);
+                                                                                          h->wf_active ? h->d_wf : nullptr, nullptr);
             h->launches++;
         } else {
             for (int c0 = 0; c0 < nb; c0 += h->dense_chunk) {
                 const int cs = std::min(h->dense_chunk, nb - c0);
-                syrk_tc_kernel<<<dim3(tiles, 1), DG_THREADS, DG_SMEM, h->ls>>>(h->tmap_C, h->d_tile_order, h->N, (uint32_t)c0 * h->nks, 0u, (uint32_t)cs * h->nks, K, 0, nullptr);
+                syrk_tc_kernel<<<dim3(tiles, 1), DG_THREADS, DG_SMEM, h->ls>>>(h->tmap_C, h->d_tile_order, h->N, (uint32_t)c0 * h->nks, 0u, (uint32_t)cs * h->nks, K, 0, nullptr, nullptr);
                 h->launches++;
             }
         }
@@ -454,6 +474,15 @@ int run_batch(fsk_handle* h, const int32_t* combos, int nb, unsigned long long* 
         spec.nseg[s] = (uint8_t)nseg;
     }
     if (h->dense_path) return run_batch_dense(h, nb, spec, K, slot_stride);
+    h->heavy_now = 0;
+    if (h->heavy_tau) {
+        if (h->heavy_probe_pending && cudaEventQuery(h->ev_heavy) == cudaSuccess) {
+            h->heavy_probe_pending = false;
+            if (*h->h_heavy_count == 0 && h->opt_heavy_tau == 0) { h->heavy_live = false; h->heavy_idle = 0; }
+        }
+        if (!h->heavy_live && ++h->heavy_idle >= 32) h->heavy_live = true;
+        if (h->heavy_live) h->heavy_now = h->heavy_tau;
+    }
     // The pack / sort / segment of this batch go to pre_stream and may overlap the accumulate of the previous batch on
     // the main stream (they are HBM / L2 bound, the accumulate is shared-memory bound); ids/task are double-buffered.
     h->buf = (int)(h->batch_index++ & 1);
@@ -482,6 +511,28 @@ int run_batch(fsk_handle* h, const int32_t* combos, int nb, unsigned long long* 
         else rc = launch_segment<uint64_t, true>(h, nb);
         if (rc) return rc;
     }
+    if (h->heavy_now) {
+        // the runs segment_kernel listed become fp16 columns and one tensor-core contraction adds their H H^T to K; the column
+        // count lives on the device, so the three launches are unconditional (they return at once when the list is empty)
+        Span sp(h, PC_ACCUMULATE);
+        const uint32_t* cnt = h->d_ticket + HEAVY_COUNT;
+        heavy_zero_kernel<<<148 * 8, 256, 0, h->ls>>>(h->d_H, (size_t)h->heavy_cap, h->N, cnt);
+        if (h->mode == MODE_R32)
+            heavy_fill_kernel<uint32_t><<<148 * 4, 256, 0, h->ls>>>((const uint32_t*)h->d_recA, (uint32_t)h->nfeat, h->idbits, h->d_heavy_list, cnt,
+                                                                     h->d_H, (size_t)h->heavy_cap, h->d_counters + 3);
+        else
+            heavy_fill_kernel<uint64_t><<<148 * 4, 256, 0, h->ls>>>((const uint64_t*)h->d_recA, (uint32_t)h->nfeat, h->idbits, h->d_heavy_list, cnt,
+                                                                     h->d_H, (size_t)h->heavy_cap, h->d_counters + 3);
+        const unsigned T = (unsigned)((h->N + DG_TILE - 1) / DG_TILE);
+        syrk_tc_kernel<<<dim3(T * (T + 1) / 2, 1), DG_THREADS, DG_SMEM, h->ls>>>(h->tmap_H, h->d_tile_order, h->N, 0u, 0u, h->heavy_cap, K, 0, nullptr, cnt);
+        h->launches += 3;
+        CU(cudaGetLastError());
+        if (!h->heavy_probe_pending) {   // did this batch have any heavy run?  read back without waiting
+            CU(cudaMemcpyAsync(h->h_heavy_count, cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->ls));
+            CU(cudaEventRecord(h->ev_heavy, h->ls));
+            h->heavy_probe_pending = true;
+        }
+    }
     CU(cudaEventRecord(h->ev_pre[h->buf], h->pre_stream));
     h->ls = h->stream;
     CU(cudaStreamWaitEvent(h->stream, h->ev_pre[h->buf], 0));
@@ -493,6 +544,45 @@ int run_batch(fsk_handle* h, const int32_t* combos, int nb, unsigned long long* 
     CU(cudaEventRecord(h->ev_acc[h->buf], h->stream));
     h->combos_done += nb;
     if (h->spans.size() > 2048) resolve_spans(h);
+    return FSK_OK;
+}
+
+// TMA descriptor of a K-major fp16 operand matrix [N rows][ld columns]: boxes of 128 rows x 64 columns landing with the 128-byte
+// swizzle the UMMA descriptors of syrk_tc_kernel expect; rows past N read as zero.  cuTensorMapEncodeTiled is resolved through
+// the runtime (no link-time dependency on libcuda).
+int encode_operand_map(fsk_handle* h, CUtensorMap* map, __half* ptr, size_t ld) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(h, FSK_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)h->N};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)DG_BK, (cuuint32_t)DG_TILE};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult cr = ((EncodeFn)fn)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)ptr, gdim, gstride, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(h, FSK_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+    CU(cudaFuncSetAttribute(syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DG_SMEM));
+    return FSK_OK;
+}
+
+// launch order of the output tiles of syrk_tc_kernel: bands of 16 tile rows, column by column inside a band
+int make_tile_order(fsk_handle* h) {
+    const int64_t T = (h->N + DG_TILE - 1) / DG_TILE;
+    if (T > 65535) return fail(h, FSK_EINVAL, "too many sequences for the tensor-core contraction");
+    std::vector<uint32_t> order;
+    order.reserve((size_t)(T * (T + 1) / 2));
+    for (int64_t b0 = 0; b0 < T; b0 += 16) {
+        const int64_t b1 = std::min<int64_t>(T, b0 + 16);
+        for (int64_t J = 0; J < b1; ++J)
+            for (int64_t I = std::max(b0, J); I < b1; ++I) order.push_back((uint32_t)(I << 16 | J));
+    }
+    ALLOC(h->d_tile_order, order.size());
+    CU(cudaMemcpy(h->d_tile_order, order.data(), order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     return FSK_OK;
 }
 
@@ -608,6 +698,8 @@ void fsk_destroy(fsk_handle* h) {
         for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_pre[i]); cudaEventDestroy(h->ev_acc[i]); }
         cudaEventDestroy(h->ev_sync);
     }
+    if (h->ev_heavy) cudaEventDestroy(h->ev_heavy);
+    if (h->h_heavy_count) cudaFreeHost(h->h_heavy_count);
     delete h;
 }
 
@@ -651,6 +743,12 @@ int fsk_set_option(fsk_handle* h, const char* key, int64_t value) {
         h->opt_pad = (int)value;
     } else if (!strcmp(key, "seg_occ")) {
         h->opt_seg_occ = (int)value;
+    } else if (!strcmp(key, "heavy_tau")) {
+        if (value < -1) return fail(h, FSK_EINVAL, "heavy_tau must be -1 (off), 0 (auto) or a positive run length");
+        h->opt_heavy_tau = (int)value;
+    } else if (!strcmp(key, "heavy_cap")) {
+        if (value != 0 && (value < 64 || value % 64 || value > 65536)) return fail(h, FSK_EINVAL, "heavy_cap must be 0 (auto) or a multiple of 64 up to 65536");
+        h->opt_heavy_cap = (int)value;
     } else if (!strcmp(key, "acc_cols")) {
         if (value != 0 && (value < 32 || value % 32)) return fail(h, FSK_EINVAL, "acc_cols must be 0 (auto) or a positive multiple of 32");
         h->opt_acc_cols = (int)value;
@@ -903,6 +1001,28 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         h->dense_chunk = (int)std::max<int64_t>(1, std::min<int64_t>(Bsel, 16777215 / std::max<int64_t>(1, maxwin * maxwin)));
     }
     h->B = (int)Bsel;
+    {
+        // heavy runs -> tensor cores: integer modes of the row path, records that carry the sequence id, counts exact in fp16
+        // (<= 2048 windows per sequence) and every fp32 accumulator below 2^24 (slots x maxwin^2).  The threshold is the larger
+        // of the measured break-even (~0.05 N; 0.06 N used) and what keeps the batch's heavy runs within 65536 columns / 8 GB.
+        h->heavy_tau = 0;
+        const bool ok = h->rows_path && !h->variance_mode && h->mode != MODE_KV && maxwin <= 2048 &&
+                        (double)Bsel * (double)maxwin * (double)maxwin < 16777216.0 && !h->fused_seg && h->opt_heavy_tau >= 0;
+        if (h->opt_heavy_tau > 0 && !ok)
+            return fail(h, FSK_EINVAL, "heavy_tau needs the row path in an integer mode, at most 2048 windows per sequence and batch x windows^2 < 2^24");
+        if (ok) {
+            // a run of d records costs d^2 / 2 updates at 1.3e12 /s on the row path, one column = N^2 / 2 MACs at 6e14 /s here
+            const int64_t tau = h->opt_heavy_tau > 0 ? h->opt_heavy_tau : std::max<int64_t>(1024, (N * 5 + 99) / 100);
+            if (tau < nfeat) {                                            // a run that long must be possible at all
+                h->heavy_tau = (uint32_t)tau;
+                h->heavy_cap = h->opt_heavy_cap ? (uint32_t)h->opt_heavy_cap
+                                                : (uint32_t)std::max<int64_t>(64, std::min<int64_t>(32768, ((8LL << 30) / (N * 2)) & ~63LL));
+            }
+        }
+        h->heavy_live = true;
+        h->heavy_probe_pending = false;
+        h->heavy_idle = 0;
+    }
     h->sort_tiles = (uint32_t)((nfeat + SORT_THREADS * h->sort_items - 1) / (SORT_THREADS * h->sort_items));
     h->seg_rows = (h->opt_seg_occ >= 1 && h->opt_seg_occ <= 3 && h->ids16 && h->mode == MODE_R32) ? 8 : SEG_ROWS_DEFAULT;
     h->seg_tiles = (uint32_t)((nfeat + seg_tile_records(h->seg_rows) - 1) / seg_tile_records(h->seg_rows));
@@ -947,12 +1067,15 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     const size_t rowcount_words = 0;
     const size_t status_words = (size_t)h->plan.npass * B * h->sort_tiles * RADIX;
     const size_t seg_status_words = (size_t)B * h->seg_tiles;
-    h->zero_bytes = 4 * (ghist_words + ticket_words + status_words + seg_status_words + rowcount_words);
+    h->heavy_bits_stride = h->heavy_tau ? ((h->ids_stride >> (h->ids16 ? 3 : 2)) + 31) / 32 + 1 : 0;
+    const size_t heavy_words = (size_t)B * h->heavy_bits_stride;
+    h->zero_bytes = 4 * (ghist_words + ticket_words + status_words + seg_status_words + rowcount_words + heavy_words);
     ALLOC(h->d_zero, h->zero_bytes);
     h->d_ghist = (uint32_t*)h->d_zero;
     h->d_ticket = h->d_ghist + ghist_words;
     h->d_status = h->d_ticket + ticket_words;
     h->d_seg_status = h->d_status + status_words;
+    h->d_heavy_bits = h->d_seg_status + seg_status_words;
     for (int i = 0; i < 2; ++i) {
         unsigned char* p;
         ALLOC(p, (size_t)B * h->ids_stride * (h->ids16 ? 2 : 4));
@@ -969,40 +1092,24 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     if (h->dense_path) {
         h->dense_ld = (size_t)B * h->nks;
         ALLOC(h->d_C, (size_t)N * h->dense_ld);
-        // TMA descriptor of C: [N rows][dense_ld fp16], boxes of 128 rows x 64 columns landing with the 128-byte swizzle the
-        // UMMA descriptors of syrk_tc_kernel expect; rows past N read as zero
-        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        if (!fn || qres != cudaDriverEntryPointSuccess) return fail(h, FSK_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
-        const cuuint64_t gdim[2] = {(cuuint64_t)h->dense_ld, (cuuint64_t)N};
-        const cuuint64_t gstride[1] = {(cuuint64_t)h->dense_ld * 2};
-        const cuuint32_t box[2] = {(cuuint32_t)DG_BK, (cuuint32_t)DG_TILE};
-        const cuuint32_t estr[2] = {1, 1};
-        const CUresult cr = ((EncodeFn)fn)(&h->tmap_C, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)h->d_C, gdim, gstride, box, estr,
-                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (cr != CUDA_SUCCESS) return fail(h, FSK_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
-        CU(cudaFuncSetAttribute(syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DG_SMEM));
+        int rc_ = encode_operand_map(h, &h->tmap_C, h->d_C, h->dense_ld);
+        if (rc_) return rc_;
         const int count_smem = DENSE_COUNT_WARPS * (int)h->nks * 2;
         CU(cudaFuncSetAttribute(dense_count_kernel<uint64_t, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, count_smem));
         CU(cudaFuncSetAttribute(dense_count_kernel<uint64_t, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, count_smem));
         CU(cudaFuncSetAttribute(dense_count_kernel<uint32_t, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, count_smem));
-        // launch order of the output tiles: bands of 16 tile rows, column by column inside a band
-        const int64_t T = (N + DG_TILE - 1) / DG_TILE;
-        if (T > 65535) return fail(h, FSK_EINVAL, "too many sequences for the dense path");
-        std::vector<uint32_t> order;
-        order.reserve((size_t)(T * (T + 1) / 2));
-        for (int64_t b0 = 0; b0 < T; b0 += 16) {
-            const int64_t b1 = std::min<int64_t>(T, b0 + 16);
-            for (int64_t J = 0; J < b1; ++J)
-                for (int64_t I = std::max(b0, J); I < b1; ++I) order.push_back((uint32_t)(I << 16 | J));
-        }
-        ALLOC(h->d_tile_order, order.size());
-        CU(cudaMemcpy(h->d_tile_order, order.data(), order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    if (h->heavy_tau) {
+        ALLOC(h->d_H, (size_t)N * h->heavy_cap);
+        ALLOC(h->d_heavy_list, h->heavy_cap);
+        if (!h->h_heavy_count) CU(cudaMallocHost((void**)&h->h_heavy_count, sizeof(uint32_t)));
+        if (!h->ev_heavy) CU(cudaEventCreateWithFlags(&h->ev_heavy, cudaEventDisableTiming));
+        int rc_ = encode_operand_map(h, &h->tmap_H, h->d_H, h->heavy_cap);
+        if (rc_) return rc_;
+    }
+    if (h->dense_path || h->heavy_tau) {
+        int rc_ = make_tile_order(h);
+        if (rc_) return rc_;
     }
     ALLOC(h->d_counters, 4);
     CU(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), h->stream));
@@ -1372,12 +1479,13 @@ int fsk_get_stats(fsk_handle* h, fsk_stats* out) {
     out->key_bits = h->keybits; out->id_bits = h->idbits; out->record_bytes = h->rec_bytes; out->sort_passes = h->plan.npass;
     out->alphabet = h->A; out->bits_per_char = h->b; out->batch = h->B; out->acc_bytes = 8;
     out->acc_path = h->dense_path ? 3 : (h->rows_path ? 2 : 1);
+    out->heavy_tau = (int32_t)h->heavy_tau;
     if (h->uploaded) {
         CU(cudaSetDevice(h->device));
         resolve_spans(h);
         unsigned long long c[4] = {0, 0, 0, 0};
         CU(cudaMemcpy(c, h->d_counters, sizeof c, cudaMemcpyDeviceToHost));
-        out->entries = (int64_t)c[0]; out->runs = (int64_t)c[1]; out->pair_updates = (int64_t)c[2];
+        out->entries = (int64_t)c[0]; out->runs = (int64_t)c[1]; out->pair_updates = (int64_t)c[2]; out->heavy_runs = (int64_t)c[3];
     }
     out->ms_pack = h->ms[PC_PACK]; out->ms_sort = h->ms[PC_SORT]; out->ms_segment = h->ms[PC_SEGMENT];
     out->ms_accumulate = h->ms[PC_ACCUMULATE]; out->ms_welford = h->ms[PC_WELFORD]; out->ms_normalise = h->ms[PC_NORMALISE];

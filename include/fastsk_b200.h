@@ -66,7 +66,8 @@ int fsk_set_shard(fsk_handle* h, int rank, int world);
  * 1 = global RED on the packed triangle, 2 = row-stationary shared-memory accumulate, 3 = dense regime:
  * per-sequence k-mer counts contracted as K += C C^T by tcgen05 tensor-core MMAs, no sort; needs at most
  * 12 key bits and 2048 windows per sequence, chosen automatically when its cost model wins); unknown
- * keys give FSK_EINVAL */
+ * keys give FSK_EINVAL.  "heavy_tau": -1 off, 0 auto, > 0 forced run-length threshold above which a run's update goes to the
+ * tensor cores instead of the row path; "acc_cols": forced column-window width of the row path (tests) */
 int fsk_set_option(fsk_handle* h, const char* key, int64_t value);
 
 /* ---- compute ---------------------------------------------------------------------------- */
@@ -131,7 +132,11 @@ typedef struct fsk_stats {
     /* per kernel class, milliseconds on the handle's stream ("profile" only) */
     double ms_pack, ms_sort, ms_segment, ms_accumulate, ms_welford, ms_normalise, ms_total;
     /* accumulate path in use: 1 global RED, 2 shared-memory rows, 3 dense tensor-core contraction (no sort) */
-    int32_t acc_path, reserved0;
+    int32_t acc_path;
+    /* runs longer than heavy_tau records (0 = feature off) leave the row path: their update is one column of a tensor-core
+     * contraction; heavy_runs counts them since upload (pair_updates then counts the row path's share only) */
+    int32_t heavy_tau;
+    int64_t heavy_runs;
 } fsk_stats;
 int fsk_get_stats(fsk_handle* h, fsk_stats* out);
 

@@ -239,6 +239,75 @@ def test_column_windows_of_the_row_path(FastSK, oracle_mod, case, cols):
     np.testing.assert_allclose(f.get_stdevs(), sd, rtol=RTOL, atol=0)
 
 
+def skewed_dna(rng, n, L, motif_len=12, frac=0.5):
+    """SURVEY 8(d) skewed variant: first-order Markov, GC-rich sequences with one planted motif in `frac` of them, so that
+    a few k-mers own very long runs (the uniform synthetic set has ~141 records in every run)."""
+    P = np.array([[0.10, 0.40, 0.40, 0.10], [0.05, 0.45, 0.45, 0.05], [0.05, 0.45, 0.45, 0.05], [0.10, 0.40, 0.40, 0.10]])
+    cdf = np.cumsum(P, axis=1)
+    X = np.empty((n, L), dtype=np.int32)
+    X[:, 0] = rng.integers(0, 4, size=n)
+    u = rng.random((n, L))
+    for t in range(1, L):
+        X[:, t] = (u[:, t, None] > cdf[X[:, t - 1]]).sum(axis=1)
+    motif = rng.integers(0, 4, size=motif_len)
+    for i in np.flatnonzero(rng.random(n) < frac):
+        p = int(rng.integers(0, L - motif_len + 1))
+        X[i, p:p + motif_len] = motif
+    return np.minimum(X, 3) + 1
+
+
+@pytest.mark.parametrize("seg_fused", [1, 2], ids=["two_pass", "fused_bucket"])
+def test_skewed_markov_dna_with_planted_motif(FastSK, oracle_mod, seg_fused):
+    """Heavy-tailed run lengths at the C4 key shape (g=16, m=8): runs of thousands of records next to empty k-mers
+    exercise the long-run paths of segment_kernel / bucket_segment_kernel and the load balancing of the accumulate."""
+    rng = np.random.default_rng(1)
+    X = skewed_dna(rng, 1500, 120)
+    queue = np.array([0, 17, 4242, 9000, 12869], dtype=np.int32)     # incl. the first and last combination
+    f = FastSK(16, 8, combo_sequence=queue, profile=True)
+    f.set_option("seg_fused", seg_fused)
+    f.compute_kernel(X[:1000], X[1000:])
+    _, Ki, _ = oracle_mod.run("c", X[:1000].tolist(), X[1000:].tolist(), 16, 8, queue)
+    assert np.array_equal(f.get_unnormalised().astype(np.uint64), Ki)
+    st = f.stats()
+    assert st["pair_updates"] > 20 * st["entries"]                # long runs: uniform data of this size has ~2 updates per entry
+
+
+@pytest.mark.parametrize("shape", ["dna16_skewed", "dna8_lowcomplex", "dna5_r64_lowcomplex", "protein_r32_lowcomplex"])
+def test_heavy_runs_on_the_tensor_cores(FastSK, oracle_mod, shape):
+    """heavy_tau: runs longer than the threshold are filed as empty tasks and their update is done as H H^T by the tcgen05
+    contraction (heavy_fill_kernel + syrk_tc_kernel).  A small forced threshold makes many runs heavy at test sizes; the
+    result must equal the all-sparse build and the oracle bit for bit."""
+    rng = np.random.default_rng(23)
+    if shape == "dna16_skewed":
+        g, m, X = 16, 8, skewed_dna(rng, 700, 100).tolist()
+    elif shape == "dna8_lowcomplex":
+        g, m, X = 7, 3, random_seqs(rng, 300, 4, 20, 120, True)
+    elif shape == "dna5_r64_lowcomplex":
+        g, m, X = 16, 4, random_seqs(rng, 150, 5, 40, 80, True)          # 36 key bits: 64-bit records
+    else:
+        g, m, X = 7, 3, random_seqs(rng, 200, 21, 16, 200, True)
+    nc = comb(g, m)
+    queue = rng.permutation(nc)[:min(nc, 12)].astype(np.int32)
+    out = {}
+    for tau, cap in ((-1, 0), (8, 0), (8, 64)):                     # off; on; on with a list that overflows
+        f = FastSK(g, m, combo_sequence=queue, profile=True)
+        f.set_option("acc_path", 2)
+        f.set_option("heavy_tau", tau)
+        f.set_option("heavy_cap", cap)
+        f.set_option("batch", 4)
+        f.compute_train(X)
+        out[tau, cap] = (f.get_unnormalised(), f.stats())
+    off, on, small = out[-1, 0], out[8, 0], out[8, 64]
+    assert off[1]["heavy_tau"] == 0 and off[1]["heavy_runs"] == 0
+    assert on[1]["heavy_tau"] == 8 and on[1]["heavy_runs"] > 0, "the test data must contain runs longer than 8 records"
+    assert 0 < small[1]["heavy_runs"] <= min(on[1]["heavy_runs"], 64 * 3)   # three batches of four combinations, 64 columns each
+    if shape == "dna16_skewed":
+        assert small[1]["heavy_runs"] < on[1]["heavy_runs"], "the 64-column list must overflow on this input"
+    assert np.array_equal(off[0], on[0]) and np.array_equal(off[0], small[0])
+    _, Ki, _ = oracle_mod.run("c", X, [], g, m, queue)
+    assert np.array_equal(on[0].astype(np.uint64), Ki)
+
+
 FUSED_CASES = [
     # name, n, alphabet, len range, g, m, low complexity, batch
     ("dna_14bit", 120, 4, (40, 160), 12, 5, False, 0),          # 7 + 7 bits: 128 buckets x 128 runs

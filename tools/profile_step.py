@@ -33,11 +33,27 @@ ap.add_argument("--l2-fetch", type=int, default=0)
 ap.add_argument("--seg-exp", type=int, default=0)
 ap.add_argument("--seg-occ", type=int, default=0)
 ap.add_argument("--seg-fused", type=int, default=0)
+ap.add_argument("--heavy-tau", type=int, default=0)
+ap.add_argument("--skew", type=int, default=0, help="1 = first-order Markov GC-rich DNA with a planted 12-mer in half of the sequences (SURVEY 8d)")
 ap.add_argument("--acc-unroll", type=int, default=2)
 ap.add_argument("--acc-pipe", type=int, default=0)
 a = ap.parse_args()
 
 X = np.random.default_rng(0).integers(1, a.alphabet + 1, size=(a.n, a.len), dtype=np.int32)
+if a.skew:
+    rng = np.random.default_rng(1)
+    P = np.array([[0.10, 0.40, 0.40, 0.10], [0.05, 0.45, 0.45, 0.05], [0.05, 0.45, 0.45, 0.05], [0.10, 0.40, 0.40, 0.10]])
+    cdf = np.cumsum(P, axis=1)
+    X = np.empty((a.n, a.len), dtype=np.int32)
+    X[:, 0] = rng.integers(0, 4, size=a.n)
+    u = rng.random((a.n, a.len))
+    for t in range(1, a.len):
+        X[:, t] = (u[:, t, None] > cdf[X[:, t - 1]]).sum(axis=1)
+    motif = rng.integers(0, 4, size=12)
+    for i in np.flatnonzero(rng.random(a.n) < 0.5):
+        p = int(rng.integers(0, a.len - 12 + 1))
+        X[i, p:p + 12] = motif
+    X = (np.minimum(X, 3) + 1).astype(np.int32)
 order = np.random.default_rng(0).permutation(comb(a.g, a.m)).astype(np.int32)
 f = FastSK(a.g, a.m, combo_sequence=order, distributed=False, profile=True)
 f.set_option("batch", a.batch)
@@ -51,6 +67,7 @@ f.set_option("l2_fetch", a.l2_fetch)
 f.set_option("seg_exp", a.seg_exp)
 f.set_option("seg_occ", a.seg_occ)
 f.set_option("seg_fused", a.seg_fused)
+f.set_option("heavy_tau", a.heavy_tau)
 f.set_option("acc_unroll", a.acc_unroll)
 f.set_option("acc_pipe", a.acc_pipe)
 codes = np.ascontiguousarray(X.reshape(-1))
@@ -65,7 +82,8 @@ for r in range(1 + a.reps):
         t0 = time.perf_counter()
 wall_ms = (time.perf_counter() - t0) * 1e3
 s1 = f.stats()
-d = {k: s1[k] - s0[k] for k in s1 if k.startswith("ms_") or k in ("pair_updates", "entries", "runs", "combos_done", "kernel_launches")}
+d = {k: s1[k] - s0[k] for k in s1 if k.startswith("ms_") or k in ("pair_updates", "entries", "runs", "combos_done", "kernel_launches", "heavy_runs")}
+d["heavy_tau"] = s1["heavy_tau"]
 d["wall_ms"] = wall_ms
 d["combos_per_s"] = d["combos_done"] / wall_ms * 1e3
 print({k: (round(v, 3) if isinstance(v, float) else v) for k, v in d.items()})
