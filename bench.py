@@ -356,6 +356,8 @@ def run_b200(args):
         return
     cpu = cpu_baseline(args.cpu_budget) if (world == 1 and not args.no_cpu_baseline) else None
     other = other_workloads(local) if world == 1 else None
+    if other is not None and not args.no_skewed:
+        other["skewed"] = skewed_workload(local)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
@@ -412,6 +414,49 @@ def other_workloads(device):
     return out
 
 
+def skewed_dna(n, L, seed=1, motif_len=12, frac=0.5):
+    """SURVEY 8(d) skewed variant of the headline set: first-order Markov, GC-rich, one planted 12-mer in half of the
+    sequences -- heavy-tailed run lengths where the uniform set has ~141 records in every run."""
+    rng = np.random.default_rng(seed)
+    P = np.array([[0.10, 0.40, 0.40, 0.10], [0.05, 0.45, 0.45, 0.05], [0.05, 0.45, 0.45, 0.05], [0.10, 0.40, 0.40, 0.10]])
+    cdf = np.cumsum(P, axis=1)
+    X = np.empty((n, L), dtype=np.int32)
+    X[:, 0] = rng.integers(0, 4, size=n)
+    u = rng.random((n, L))
+    for t in range(1, L):
+        X[:, t] = (u[:, t, None] > cdf[X[:, t - 1]]).sum(axis=1)
+    motif = rng.integers(0, 4, size=motif_len)
+    for i in np.flatnonzero(rng.random(n) < frac):
+        p = int(rng.integers(0, L - motif_len + 1))
+        X[i, p:p + motif_len] = motif
+    return (np.minimum(X, 3) + 1).astype(np.int32)
+
+
+def skewed_workload(device, combos=96):
+    """The headline shape (50000 x 200 bp, g=16 m=8) on the skewed set, one batch of combinations with inputs resident:
+    the row path alone against the row path with its heavy runs (> 0.05 N records) contracted on the tensor cores."""
+    from fastsk_b200 import FastSK, _lib
+    X = skewed_dna(N_SEQ, SEQ_LEN)
+    order = queue_order()[:2 * combos]
+    codes = np.ascontiguousarray(X.reshape(-1))
+    offsets = np.arange(N_SEQ + 1, dtype=np.int64) * SEQ_LEN
+    out = {"workload": f"skewed synthetic DNA {N_SEQ}x{SEQ_LEN} (Markov GC-rich + planted 12-mer), g={G} m={M}, {combos} combinations timed after {combos} warm-up"}
+    for tau, tag in ((-1, "rows_only"), (0, "rows_plus_heavy_runs_on_tensor_cores")):
+        f = FastSK(G, M, combo_sequence=order, device=device, distributed=False, profile=True)
+        f.set_option("heavy_tau", tau)
+        f._call("fsk_upload", codes.ctypes.data_as(_lib.c_i32p), offsets.ctypes.data_as(_lib.c_i64p), N_TRAIN, N_SEQ - N_TRAIN)
+        f._call("fsk_accumulate_combos", order[:combos].ctypes.data_as(_lib.c_i32p), combos, 1)
+        s0 = f.stats()
+        q = np.ascontiguousarray(order[combos:])
+        f._call("fsk_accumulate_combos", q.ctypes.data_as(_lib.c_i32p), combos, 1)
+        s1 = f.stats()
+        ms = s1["ms_total"] - s0["ms_total"]
+        out[tag] = {"device_ms": ms, "combinations_per_s": combos / (ms * 1e-3), "heavy_runs": s1["heavy_runs"] - s0["heavy_runs"],
+                    "heavy_tau": s1["heavy_tau"], "pair_updates": s1["pair_updates"] - s0["pair_updates"]}
+        del f
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -424,6 +469,7 @@ def main():
     ap.add_argument("--wave", type=int, default=4, help="accumulate launch = wave x resident CTAs rows")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of reference CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-skewed", action="store_true", help="skip the skewed-set section of other_workloads (~6 s)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

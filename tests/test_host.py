@@ -50,6 +50,19 @@ def test_constructor_validation_and_queue():
         f.set_option("no_such_option", 1)
 
 
+def test_option_validation_needs_no_device():
+    """fsk_set_option checks its values on the host: the path selectors and the test hooks of the newer stages."""
+    from fastsk_b200 import FastSK
+    f = FastSK(10, 6)
+    for key, good, bad in (("acc_path", 3, 4), ("seg_fused", 2, 3), ("heavy_tau", -1, -2), ("heavy_cap", 128, 100),
+                           ("acc_cols", 64, 48), ("batch", 96, 97)):
+        f.set_option(key, good)
+        with pytest.raises(ValueError):
+            f.set_option(key, bad)
+    st = f.stats()
+    assert {"acc_path", "heavy_tau", "heavy_runs"} <= set(st) and st["heavy_runs"] == 0
+
+
 def test_seeded_queue_equals_libstdcxx_reference_shuffle():
     """fastsk_kernel.cpp:31-38: std::shuffle over 0..C-1 with std::default_random_engine(seed)."""
     import subprocess, tempfile
