@@ -119,6 +119,7 @@ struct fsk_handle {
     int opt_heavy_tau = 0;                             // 0 auto, -1 off, > 0 forced threshold
     int opt_heavy_cap = 0;                             // 0 auto, else columns of d_H (tests: a small list overflows)
     uint32_t heavy_tau = 0;                            // 0 = feature off
+    uint32_t heavy_tau_min = 0;                        // the break-even threshold the adaptive one never goes below
     uint32_t heavy_now = 0;                            // threshold in force for the batch being launched (0 while the feature sleeps)
     uint32_t heavy_cap = 0;                            // columns of d_H = upper bound on the heavy runs of a batch
     __half* d_H = nullptr;
@@ -478,7 +479,15 @@ int run_batch(fsk_handle* h, const int32_t* combos, int nb, unsigned long long* 
     if (h->heavy_tau) {
         if (h->heavy_probe_pending && cudaEventQuery(h->ev_heavy) == cudaSuccess) {
             h->heavy_probe_pending = false;
-            if (*h->h_heavy_count == 0 && h->opt_heavy_tau == 0) { h->heavy_live = false; h->heavy_idle = 0; }
+            const uint32_t cnt = *h->h_heavy_count;           // candidates of an earlier batch, incl. those the list had no room for
+            if (h->opt_heavy_tau == 0) {
+                if (cnt == 0) { h->heavy_live = false; h->heavy_idle = 0; }
+                // The list is first come, first served: when it overflows, short runs crowd out the long ones that matter most.
+                // Run-length statistics barely change between batches (same sequences), so steer the threshold instead.
+                else if (cnt > h->heavy_cap) h->heavy_tau = (uint32_t)std::min<int64_t>(h->nfeat, (int64_t)h->heavy_tau * 3 / 2 + 1);
+                else if (cnt < h->heavy_cap / 8 && h->heavy_tau > h->heavy_tau_min)
+                    h->heavy_tau = std::max(h->heavy_tau_min, h->heavy_tau * 3 / 4);
+            }
         }
         if (!h->heavy_live && ++h->heavy_idle >= 32) h->heavy_live = true;
         if (h->heavy_live) h->heavy_now = h->heavy_tau;
@@ -1014,9 +1023,9 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
             // a run of d records costs d^2 / 2 updates at 1.3e12 /s on the row path, one column = N^2 / 2 MACs at 6e14 /s here
             const int64_t tau = h->opt_heavy_tau > 0 ? h->opt_heavy_tau : std::max<int64_t>(1024, (N * 5 + 99) / 100);
             if (tau < nfeat) {                                            // a run that long must be possible at all
-                h->heavy_tau = (uint32_t)tau;
+                h->heavy_tau = h->heavy_tau_min = (uint32_t)tau;
                 h->heavy_cap = h->opt_heavy_cap ? (uint32_t)h->opt_heavy_cap
-                                                : (uint32_t)std::max<int64_t>(64, std::min<int64_t>(32768, ((8LL << 30) / (N * 2)) & ~63LL));
+                                                : (uint32_t)std::max<int64_t>(64, std::min<int64_t>(65536, ((8LL << 30) / (N * 2)) & ~63LL));
             }
         }
         h->heavy_live = true;
