@@ -292,7 +292,7 @@ def run_b200(args):
     sort_bytes = combos_rank * nfeat * ((gw_bytes + 4 + rec) + 2 * rec * st1["sort_passes"] + (rec + id_bytes + 8))
     sort_s = (d["ms_pack"] + d["ms_sort"] + d["ms_segment"]) * 1e-3
     roofline = {"kernel": "accumulate_rows_kernel", "bound": "hbm", "achieved": acc_bytes / acc_s / 1e9 if acc_s else None,
-                "peak": peak, "unit": "GB/s", "frac": (acc_bytes / acc_s / 1e9 / peak) if acc_s else None, "traffic": TRAFFIC_ACC_BATCH96 * st1["batch"] / 96.0, "traffic_unit": "bytes per batch (ncu dram read + write)",
+                "peak": peak, "unit": "GB/s", "frac": (acc_bytes / acc_s / 1e9 / peak) if acc_s else None, "traffic": (TRAFFIC_ACC_BATCH96 - 16.0 * n_pairs) * st1["batch"] / 96.0 + 16.0 * n_pairs, "traffic_unit": "bytes per batch (ncu dram read + write at batch 96; the id-stream part scaled to this batch, the 16 B x cells flush part not)",
                 "achieved_per_launch_bytes": acc_bytes / batches,
                 "peak_source": peak_src, "share_of_step": d["ms_accumulate"] / d["ms_total"] if d["ms_total"] else None,
                 "algorithmic_bytes": f"{id_bytes} B x unit pair-updates (ids of the run prefixes) + 16 B x packed-triangle cells per batch",
