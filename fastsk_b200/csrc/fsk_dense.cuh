@@ -22,12 +22,17 @@ namespace fsk {
 
 constexpr int DG_TILE = 128;                                     // output tile: 128 x 128 pairs of sequences
 constexpr int DG_BK = 64;                                        // fp16 elements per k-block = one 128-byte swizzle row
-constexpr int DG_STAGES = 3;                                     // 3 x 32 KB: two CTAs per SM, one's epilogue under the other's MMAs
 constexpr int DG_THREADS = 192;                                  // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
 constexpr uint32_t DG_TILE_BYTES = DG_TILE * DG_BK * 2;          // 16 KB
-constexpr uint32_t DG_STAGE_BYTES = 2 * DG_TILE_BYTES;           // A rows + B rows
-constexpr uint32_t DG_TMEM_COLS = 128;                           // 128 lanes x 128 fp32 columns
-constexpr size_t DG_SMEM = (size_t)DG_STAGES * DG_STAGE_BYTES + 1024 /* 1024-byte alignment of the swizzle atom */ + 128;
+// Two shapes of the same kernel.  NA = 1: one 128 x 128 output tile per CTA, 3 stages x 32 KB, two CTAs per SM (one's epilogue
+// runs under the other's MMAs): short contractions (variance mode).  NA = 2: two vertically adjacent tiles per CTA share their
+// B operand (3 loads feed 8 MMAs per k-block: 24 KB of L2 -> shared-memory traffic per M-MAC instead of 32), 4 stages x 48 KB,
+// one CTA per SM, 256 TMEM columns: long contractions, where the operand traffic bounds the 128 x 128 shape.
+__host__ __device__ constexpr int dg_stages(int NA) { return NA == 1 ? 3 : 4; }
+__host__ __device__ constexpr uint32_t dg_stage_bytes(int NA) { return (uint32_t)(NA + 1) * DG_TILE_BYTES; }
+__host__ __device__ constexpr size_t dg_smem(int NA) {
+    return (size_t)dg_stages(NA) * dg_stage_bytes(NA) + 1024 /* 1024-byte alignment of the swizzle atom */ + 128;
+}
 constexpr int DENSE_MAX_KEYS = 4096;
 
 // ------------------------------------------------------------------------------------------
@@ -155,8 +160,9 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// grid = (lower-triangle tiles T (T + 1) / 2 in tile_order, groups).  Group `g` contracts the columns [k_begin + g * k_group,
+// grid = (lower-triangle tiles T (T + 1) / 2 in tile_order -- pairs of tile rows for NA = 2 --, groups).  Group `g` contracts the columns [k_begin + g * k_group,
 // + klen) of C and adds into K + g * out_group_stride (integer modes: one group; variance mode: one per slot).
+template <int NA>
 __global__ void __launch_bounds__(DG_THREADS)
 syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restrict__ tile_order, int64_t nseq, uint32_t k_begin,
                uint32_t k_group, uint32_t klen, unsigned long long* __restrict__ K, size_t out_group_stride,
@@ -166,6 +172,9 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restr
         klen = (min(*klen_dev, klen) + DG_BK - 1) / DG_BK * DG_BK;     // klen carries the capacity of the list
         if (klen == 0) return;
     }
+    constexpr int DG_STAGES = dg_stages(NA);
+    constexpr uint32_t DG_STAGE_BYTES = dg_stage_bytes(NA);
+    constexpr uint32_t DG_TMEM_COLS = NA * 128;                   // 128 lanes x 128 fp32 columns per output tile
     extern __shared__ uint8_t dg_smem_raw[];
     const uint32_t raw = smem_u32(dg_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                 // swizzle atoms need 1024-byte alignment
@@ -176,9 +185,11 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restr
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // tile (I, J), J <= I, in the host's rasterised order: the CTAs resident at once cover a band of 16 tile rows by as
     // many tile columns, so every operand slice TMA fetches is shared by ~16 CTAs through L2
+    // (NA = 2: the entry names the PAIR of tile rows 2 P, 2 P + 1; a tile above the diagonal or past the last row computes
+    // zeros or masked cells and is skipped by the epilogue)
     const uint32_t ij = tile_order[blockIdx.x];
-    const uint32_t I = ij >> 16, J = ij & 0xffffu;
-    const bool diag = I == J;
+    const uint32_t I = NA == 1 ? ij >> 16 : (ij >> 16) * 2u, J = ij & 0xffffu;
+    const bool diag = NA == 1 && I == J;
     const uint32_t kx0 = k_begin + blockIdx.y * k_group;
     const uint32_t nkb = klen / DG_BK;
 
@@ -203,7 +214,7 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restr
     if (warp == 0) {
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-            const uint32_t tx = diag ? DG_TILE_BYTES : DG_STAGE_BYTES;
+            const uint32_t tx = diag ? DG_TILE_BYTES : DG_STAGE_BYTES;   // rows past N are zero-filled and still count
             for (uint32_t kb = 0; kb < nkb; ++kb) {
                 const uint32_t s = kb % DG_STAGES, ph = (kb / DG_STAGES) & 1u;
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);                           // the MMAs that read this stage have completed
@@ -211,7 +222,8 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restr
                 const uint32_t a = base + s * DG_STAGE_BYTES;
                 const int x = (int)(kx0 + kb * DG_BK);
                 tma_load_2d(a, &tmap, full0 + 8 * s, x, (int)(I * DG_TILE));
-                if (!diag) tma_load_2d(a + DG_TILE_BYTES, &tmap, full0 + 8 * s, x, (int)(J * DG_TILE));
+                if (NA == 2) tma_load_2d(a + DG_TILE_BYTES, &tmap, full0 + 8 * s, x, (int)((I + 1) * DG_TILE));
+                if (!diag) tma_load_2d(a + NA * DG_TILE_BYTES, &tmap, full0 + 8 * s, x, (int)(J * DG_TILE));
             }
         }
         __syncwarp();
@@ -223,11 +235,14 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restr
                 mbar_wait(full0 + 8 * s, ph);                                 // TMA has landed this stage
                 tc_fence_after();
                 const uint32_t a = base + s * DG_STAGE_BYTES;
-                const uint64_t adesc = umma_desc_sw128(a);
-                const uint64_t bdesc = umma_desc_sw128(diag ? a : a + DG_TILE_BYTES);
+                const uint64_t bdesc = umma_desc_sw128(diag ? a : a + NA * DG_TILE_BYTES);
 #pragma unroll
-                for (uint32_t k = 0; k < DG_BK / 16; ++k)                     // UMMA_K = 16 fp16 = 32 bytes along the swizzled row
-                    tc_mma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0u);
+                for (int t = 0; t < NA; ++t) {
+                    const uint64_t adesc = umma_desc_sw128(a + t * DG_TILE_BYTES);
+#pragma unroll
+                    for (uint32_t k = 0; k < DG_BK / 16; ++k)                 // UMMA_K = 16 fp16 = 32 bytes along the swizzled row
+                        tc_mma_f16(tmem_base + t * 128u, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0u);
+                }
                 tc_commit(empty0 + 8 * s);                                    // frees the stage once these MMAs are done
             }
             tc_commit(tmem_full);                                             // accumulator complete
@@ -241,7 +256,6 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restr
         // stages are free by now: every MMA has completed) so that the 32 lanes of a warp touch 32 CONSECUTIVE cells of one
         // row of the packed triangle: coalesced 256-byte accesses instead of 32 rows x 8 bytes.
         float* __restrict__ ts = reinterpret_cast<float*>(dg_smem_raw + (base - raw)) + (warp - 2) * (32 * 33);
-        const int64_t ibase = (int64_t)I * DG_TILE + q * 32;
         const int64_t j0 = (int64_t)J * DG_TILE;
         const bool variance = wf != nullptr;
         double* __restrict__ kh = variance ? wf->khat[blockIdx.y] : nullptr;
@@ -250,9 +264,13 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restr
         unsigned long long* __restrict__ Kg = K + (size_t)blockIdx.y * out_group_stride;
         double acc = 0.0;
 #pragma unroll 1
+        for (int t = 0; t < NA; ++t) {
+        if ((int64_t)(I + t) * DG_TILE >= nseq || J > I + t) continue;      // nothing of this tile is at or below the diagonal
+        const int64_t ibase = (int64_t)(I + t) * DG_TILE + q * 32;
+#pragma unroll 1
         for (int c0 = 0; c0 < DG_TILE; c0 += 32) {
             uint32_t v[32];
-            tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + (uint32_t)c0, v);
+            tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + (uint32_t)(t * 128 + c0), v);
 #pragma unroll
             for (int c = 0; c < 32; ++c) ts[lane * 33 + c] = __uint_as_float(v[c]);
             __syncwarp();
@@ -290,6 +308,7 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restr
                 }
             }
             __syncwarp();
+        }
         }
         if (variance) {   // one partial sum of delta * delta2 per epilogue warp, added up in a fixed order by welford_final_kernel
 #pragma unroll

@@ -117,6 +117,7 @@ struct fsk_handle {
     __half* d_C = nullptr;
     // heavy runs of the sparse regime: runs longer than heavy_tau leave the row path for a tensor-core contraction
     int opt_heavy_tau = 0;                             // 0 auto, -1 off, > 0 forced threshold
+    int opt_gemm_shape = 0;                            // 0 auto, 1 one tile per CTA, 2 two tiles per CTA sharing B
     int opt_heavy_cap = 0;                             // 0 auto, else columns of d_H (tests: a small list overflows)
     uint32_t heavy_tau = 0;                            // 0 = feature off
     uint32_t heavy_tau_min = 0;                        // the break-even threshold the adaptive one never goes below
@@ -133,6 +134,8 @@ struct fsk_handle {
     uint32_t* h_heavy_count = nullptr;                 // pinned
     cudaEvent_t ev_heavy = nullptr;
     CUtensorMap tmap_H;
+    uint32_t* d_pair_order = nullptr;                  // the same for pairs of tile rows (two-tile shape of the contraction)
+    uint32_t pair_tiles = 0;
     uint32_t* d_tile_order = nullptr;                  // lower-triangle tiles (I << 16 | J) in L2-friendly launch order
     CUtensorMap tmap_C;
     unsigned long long* d_Kint = nullptr;   // integer partial (exact / skip_variance), or per-slot Ks in variance mode
@@ -205,7 +208,7 @@ void release_device(fsk_handle* h) {
     dev_free(h->d_recA); dev_free(h->d_recB); dev_free(h->d_valA); dev_free(h->d_valB);
     dev_free(h->d_zero);
     h->d_ghist = h->d_ticket = h->d_status = h->d_seg_status = nullptr;
-    dev_free(h->d_woff32); dev_free(h->d_fill); dev_free(h->d_C); dev_free(h->d_tile_order); dev_free(h->d_H); dev_free(h->d_heavy_list);
+    dev_free(h->d_woff32); dev_free(h->d_fill); dev_free(h->d_C); dev_free(h->d_tile_order); dev_free(h->d_pair_order); dev_free(h->d_H); dev_free(h->d_heavy_list);
     for (int i = 0; i < 2; ++i) { dev_free(h->d_ids[i]); dev_free(h->d_task[i]); }
     dev_free(h->d_Kint); dev_free(h->d_Kf);
     for (auto& p : h->d_Khat) dev_free(p);
@@ -439,13 +442,16 @@ int run_batch_dense(fsk_handle* h, int nb, const BatchSpec& spec, unsigned long 
         const unsigned T = (unsigned)((h->N + DG_TILE - 1) / DG_TILE);
         const unsigned tiles = T * (T + 1) / 2;
         if (slot_stride) {   // variance mode: every slot contracts its own k-mer columns into its own Ks
-            syrk_tc_kernel<<<dim3(tiles, (unsigned)nb), DG_THREADS, DG_SMEM, h->ls>>>(h->tmap_C, h->d_tile_order, h->N, 0u, h->nks, h->nks, K, slot_stride,
+            syrk_tc_kernel<1><<<dim3(tiles, (unsigned)nb), DG_THREADS, dg_smem(1), h->ls>>>(h->tmap_C, h->d_tile_order, h->N, 0u, h->nks, h->nks, K, slot_stride,
                                                                                           h->wf_active ? h->d_wf : nullptr, nullptr);
             h->launches++;
         } else {
             for (int c0 = 0; c0 < nb; c0 += h->dense_chunk) {
                 const int cs = std::min(h->dense_chunk, nb - c0);
-                syrk_tc_kernel<<<dim3(tiles, 1), DG_THREADS, DG_SMEM, h->ls>>>(h->tmap_C, h->d_tile_order, h->N, (uint32_t)c0 * h->nks, 0u, (uint32_t)cs * h->nks, K, 0, nullptr, nullptr);
+                if (h->opt_gemm_shape != 1 && (h->opt_gemm_shape == 2 || ((uint32_t)cs * h->nks >= 2048 && T >= 4)))
+                    syrk_tc_kernel<2><<<dim3(h->pair_tiles, 1), DG_THREADS, dg_smem(2), h->ls>>>(h->tmap_C, h->d_pair_order, h->N, (uint32_t)c0 * h->nks, 0u, (uint32_t)cs * h->nks, K, 0, nullptr, nullptr);
+                else
+                    syrk_tc_kernel<1><<<dim3(tiles, 1), DG_THREADS, dg_smem(1), h->ls>>>(h->tmap_C, h->d_tile_order, h->N, (uint32_t)c0 * h->nks, 0u, (uint32_t)cs * h->nks, K, 0, nullptr, nullptr);
                 h->launches++;
             }
         }
@@ -533,7 +539,10 @@ int run_batch(fsk_handle* h, const int32_t* combos, int nb, unsigned long long* 
             heavy_fill_kernel<uint64_t><<<148 * 4, 256, 0, h->ls>>>((const uint64_t*)h->d_recA, (uint32_t)h->nfeat, h->idbits, h->d_heavy_list, cnt,
                                                                      h->d_H, (size_t)h->heavy_cap, h->d_counters + 3);
         const unsigned T = (unsigned)((h->N + DG_TILE - 1) / DG_TILE);
-        syrk_tc_kernel<<<dim3(T * (T + 1) / 2, 1), DG_THREADS, DG_SMEM, h->ls>>>(h->tmap_H, h->d_tile_order, h->N, 0u, 0u, h->heavy_cap, K, 0, nullptr, cnt);
+        if (h->opt_gemm_shape != 1 && (h->opt_gemm_shape == 2 || T >= 4))
+            syrk_tc_kernel<2><<<dim3(h->pair_tiles, 1), DG_THREADS, dg_smem(2), h->ls>>>(h->tmap_H, h->d_pair_order, h->N, 0u, 0u, h->heavy_cap, K, 0, nullptr, cnt);
+        else
+            syrk_tc_kernel<1><<<dim3(T * (T + 1) / 2, 1), DG_THREADS, dg_smem(1), h->ls>>>(h->tmap_H, h->d_tile_order, h->N, 0u, 0u, h->heavy_cap, K, 0, nullptr, cnt);
         h->launches += 3;
         CU(cudaGetLastError());
         if (!h->heavy_probe_pending) {   // did this batch have any heavy run?  read back without waiting
@@ -575,7 +584,8 @@ int encode_operand_map(fsk_handle* h, CUtensorMap* map, __half* ptr, size_t ld) 
                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(h, FSK_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
-    CU(cudaFuncSetAttribute(syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DG_SMEM));
+    CU(cudaFuncSetAttribute(syrk_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dg_smem(1)));
+    CU(cudaFuncSetAttribute(syrk_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dg_smem(2)));
     return FSK_OK;
 }
 
@@ -592,6 +602,17 @@ int make_tile_order(fsk_handle* h) {
     }
     ALLOC(h->d_tile_order, order.size());
     CU(cudaMemcpy(h->d_tile_order, order.data(), order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    // the same for the two-tile shape: entries (P << 16 | J) name the tile rows 2 P and 2 P + 1, J <= 2 P + 1; bands of 8 pairs
+    const int64_t TP = (T + 1) / 2;
+    order.clear();
+    for (int64_t b0 = 0; b0 < TP; b0 += 8) {
+        const int64_t b1 = std::min<int64_t>(TP, b0 + 8);
+        for (int64_t J = 0; J < std::min<int64_t>(T, 2 * b1); ++J)
+            for (int64_t P = std::max(b0, J / 2); P < b1; ++P) order.push_back((uint32_t)(P << 16 | J));
+    }
+    h->pair_tiles = (uint32_t)order.size();
+    ALLOC(h->d_pair_order, order.size());
+    CU(cudaMemcpy(h->d_pair_order, order.data(), order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     return FSK_OK;
 }
 
@@ -755,6 +776,9 @@ int fsk_set_option(fsk_handle* h, const char* key, int64_t value) {
     } else if (!strcmp(key, "heavy_tau")) {
         if (value < -1) return fail(h, FSK_EINVAL, "heavy_tau must be -1 (off), 0 (auto) or a positive run length");
         h->opt_heavy_tau = (int)value;
+    } else if (!strcmp(key, "gemm_shape")) {
+        if (value < 0 || value > 2) return fail(h, FSK_EINVAL, "gemm_shape must be 0 (auto), 1 or 2 tiles per CTA");
+        h->opt_gemm_shape = (int)value;
     } else if (!strcmp(key, "heavy_cap")) {
         if (value != 0 && (value < 64 || value % 64 || value > 65536)) return fail(h, FSK_EINVAL, "heavy_cap must be 0 (auto) or a multiple of 64 up to 65536");
         h->opt_heavy_cap = (int)value;

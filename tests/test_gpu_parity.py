@@ -188,12 +188,14 @@ def test_dense_tensor_core_path_multi_tile_and_chunked(FastSK, oracle_mod):
     g, m = 10, 6                                              # 4 kept characters x 2 bits: 256 k-mers
     X = random_seqs(rng, 333, 4, 60, 100)
     queue = rng.permutation(comb(g, m))[:100].astype(np.int32)   # 100 combinations: a full batch of 96 and a rest
-    f = FastSK(g, m, combo_sequence=queue)
-    f.compute_kernel(X[:250], X[250:])
-    st = f.stats()
-    assert st["acc_path"] == 3, "the cost model should pick the dense path for 256 k-mers x 333 sequences"
     _, Ki, _ = oracle_mod.run("c", X[:250], X[250:], g, m, queue)
-    assert np.array_equal(f.get_unnormalised().astype(np.uint64), Ki)
+    for shape in (0, 1, 2):                                   # auto; one tile per CTA; two tiles per CTA sharing the B operand
+        f = FastSK(g, m, combo_sequence=queue)                # (three tile rows: the second pair's lower tile is past the last row)
+        f.set_option("gemm_shape", shape)
+        f.compute_kernel(X[:250], X[250:])
+        st = f.stats()
+        assert st["acc_path"] == 3, "the cost model should pick the dense path for 256 k-mers x 333 sequences"
+        assert np.array_equal(f.get_unnormalised().astype(np.uint64), Ki), f"gemm_shape {shape}"
 
     g, m = 8, 4
     X = random_seqs(rng, 14, 4, 900, 1100, True)             # homopolymers: counts up to 1093, products above 2^20

@@ -35,6 +35,7 @@ ap.add_argument("--seg-occ", type=int, default=0)
 ap.add_argument("--seg-fused", type=int, default=0)
 ap.add_argument("--heavy-tau", type=int, default=0)
 ap.add_argument("--heavy-cap", type=int, default=0)
+ap.add_argument("--gemm-shape", type=int, default=0)
 ap.add_argument("--skew", type=int, default=0, help="1 = first-order Markov GC-rich DNA with a planted 12-mer in half of the sequences (SURVEY 8d)")
 ap.add_argument("--acc-unroll", type=int, default=2)
 ap.add_argument("--acc-pipe", type=int, default=0)
@@ -70,6 +71,7 @@ f.set_option("seg_occ", a.seg_occ)
 f.set_option("seg_fused", a.seg_fused)
 f.set_option("heavy_tau", a.heavy_tau)
 f.set_option("heavy_cap", a.heavy_cap)
+f.set_option("gemm_shape", a.gemm_shape)
 f.set_option("acc_unroll", a.acc_unroll)
 f.set_option("acc_pipe", a.acc_pipe)
 codes = np.ascontiguousarray(X.reshape(-1))
