@@ -404,7 +404,7 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
                size_t ids_stride, int idbits, uint32_t nseq, int unit_shift, uint32_t pad_mask, uint32_t* __restrict__ fill,
                IdT* __restrict__ ids, uint2* __restrict__ task, uint32_t* __restrict__ scan_status /* [slot][tile] */,
                uint32_t* __restrict__ ticket, uint32_t* __restrict__ unsorted_flag,
-               unsigned long long* __restrict__ stat_counters, int exp /* timing experiments only: 1-3 file tasks wrongly */,
+               unsigned long long* __restrict__ stat_counters,
                uint32_t heavy_tau /* 0 = off: runs longer than this may leave the sparse path */, uint32_t* __restrict__ heavy_count,
                uint2* __restrict__ heavy_list /* (slot, first sorted record) of every heavy run of the batch */, uint32_t heavy_cap,
                uint32_t* __restrict__ heavy_bits /* [slot][units / 32]: bit set = the run starting at that id unit is in the list */,
@@ -585,9 +585,7 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
             const uint32_t i = seg0 + (h0 + k) * 32 + lane;
             pos[k] = 0;
             if (i < n) {
-                if (exp == 1) pos[k] = i;                                              // no atomic, coalesced store
-                else if (exp == 3) pos[k] = (uint32_t)(((uint64_t)i * 2654435761u) % n);   // no atomic, scattered store
-                else pos[k] = atomicAdd(&fill[(size_t)slot * nseq + sq[h0 + k]], 1u);
+                pos[k] = atomicAdd(&fill[(size_t)slot * nseq + sq[h0 + k]], 1u);
             }
         }
         if (h0 == 0) {
@@ -641,7 +639,7 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
                         }
                     }
                 }
-                task[sbase + (exp == 2 ? i : pos[k])] = make_uint2(X >> unit_shift, ln);
+                task[sbase + pos[k]] = make_uint2(X >> unit_shift, ln);
                 updates += ln & 0x7fffffffu;
             }
         }
@@ -677,13 +675,11 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
 // memory atomics.  Runs start on unit boundaries (segment_kernel), so only the LAST unit of a task can hold
 // ids that are not part of it, and those are larger than b (later sequences of the run, or the 0xFF.. fill):
 // min(id, b + 1 + lane) sends them to one of 32 dump words behind the row -- no masks, no branches.
-// HINT: L2 prefetch size attached to the streaming load (0 = 64 B, 1 = none, 2 = 128 B) -- an experiment knob
-template <int HINT>
+// the id stream is read once per task and never again by this CTA: no L1 allocation, 64-byte L2 prefetch
+// (128-byte prefetch and no prefetch measured within 1 %: profiles/r01_v6_l2fetch_ldhint_experiment.txt)
 __device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
     uint4 v;
-    if (HINT == 0) asm("ld.global.nc.L1::no_allocate.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    else if (HINT == 1) asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    else asm("ld.global.nc.L1::no_allocate.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
 
@@ -714,7 +710,7 @@ __device__ __forceinline__ void apply_unit(uint32_t* row, const uint4 v, const u
 // grid = (rows of this wave, groups): CTA x owns row b = row_hi - x; the slots [group * slots_per_group,
 // +slots_per_group) add into the same K.  The host launches the rows in waves of a few CTAs per SM, longest
 // rows first.
-template <typename AccT, typename IdT, int UNROLL, int HINT, bool PIPE = false>
+template <typename AccT, typename IdT, int UNROLL>
 __global__ void __launch_bounds__(1024)
 accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uint2* __restrict__ task,
                        const uint32_t* __restrict__ woff, uint32_t n, uint32_t row_hi, int slots_per_group,
@@ -767,12 +763,6 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
     while (c < nchunks) {
         const uint32_t s = c / cps;
         const uint4* __restrict__ ip = reinterpret_cast<const uint4*>(ids_g + (size_t)s * ids_stride);   // ids_stride is a multiple of 64
-        uint32_t c_next = 0;
-        uint2 q_next = make_uint2(0, 0);
-        if (PIPE) {                                          // the next chunk's tasks travel while this chunk is applied
-            c_next = grab();
-            q_next = load_task(c_next);
-        }
         const uint32_t my_units = (q.y + PER - 1) >> SH;
         uint32_t incl = my_units;
 #pragma unroll
@@ -794,7 +784,7 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
                 const uint32_t j = (started + __popc(m & lane_le) - 1) & 31;
                 started += __popc(m);
                 const uint32_t unit = __shfl_sync(0xffffffffu, u0, j) + wbase + lane;
-                if (wbase + lane < W) v[u] = ldg_stream_u4<HINT>(ip + unit);
+                if (wbase + lane < W) v[u] = ldg_stream_u4(ip + unit);
             }
         };
         auto apply = [&](uint32_t base, const uint4 (&v)[UNROLL]) {
@@ -802,28 +792,15 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
             for (int u = 0; u < UNROLL; ++u)
                 if (base + 32 * u + lane < W) apply_unit<IdT>(row, v[u], dump, col0);
         };
-        if (PIPE) {
-            uint4 va[UNROLL], vb[UNROLL];
-            issue(0, va);
-            for (uint32_t base = 0; base < W; base += 64 * UNROLL) {   // two steps per trip: the buffers swap by name
-                if (base + 32 * UNROLL < W) issue(base + 32 * UNROLL, vb);
-                apply(base, va);
-                if (base + 32 * UNROLL < W) {
-                    if (base + 64 * UNROLL < W) issue(base + 64 * UNROLL, va);
-                    apply(base + 32 * UNROLL, vb);
-                }
-            }
-            c = c_next;
-            q = q_next;
-        } else {
-            for (uint32_t base = 0; base < W; base += 32 * UNROLL) {
-                uint4 v[UNROLL];
-                issue(base, v);
-                apply(base, v);
-            }
-            c = grab();
-            q = load_task(c);
+        // (double-buffering these loads against the applies, and prefetching the next chunk's tasks, measured no gain:
+        // profiles/r01_v6_unroll_pipe_segexp_experiment.txt)
+        for (uint32_t base = 0; base < W; base += 32 * UNROLL) {
+            uint4 v[UNROLL];
+            issue(base, v);
+            apply(base, v);
         }
+        c = grab();
+        q = load_task(c);
     }
     __syncthreads();
     if (wf) {

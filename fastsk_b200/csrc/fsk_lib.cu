@@ -52,16 +52,11 @@ struct fsk_handle {
     int opt_rows_threads = 0;        // threads per row CTA of the accumulate (0 = by N)
     int opt_overlap = 0;             // 1 = pre-pass of the next batch on its own low-priority stream (measured: no gain, the
                                      // row CTAs own the whole SM's shared memory; profiles/r01_overlap_experiment.txt)
-    int opt_ld_hint = 0;             // experiment: L2 prefetch hint of the accumulate's id loads (0 = 64 B, 1 = none, 2 = 128 B)
-    int opt_l2_fetch = 0;            // experiment: cudaLimitMaxL2FetchGranularity (0 = leave alone)
-    int opt_seg_occ = 0;             // experiment: segment_kernel variant (0 = 16 rows per warp, 3 CTAs/SM; 1-3 = 8 rows, 4/5/6 CTAs/SM)
     int seg_rows = SEG_ROWS_DEFAULT;
     int opt_seg_fused = 0;           // 0 auto (= off), 1 off, 2 on: fused last sort pass + segmentation (fsk_bucket.cuh) for two-digit keys
     bool fused_seg = false;
     uint32_t image_cap = 0;          // ids in the shared-memory image of a bucket
-    int opt_seg_exp = 0;             // timing experiments on segment_kernel (results are wrong when != 0; the accumulate is skipped)
-    int opt_acc_pipe = 0;            // 1 = double-buffered id loads + next chunk's tasks prefetched
-    int opt_acc_unroll = 2;          // id units in flight per lane of the accumulate (2, 4, 6 or 8)
+    int opt_acc_unroll = 2;          // id units in flight per lane of the accumulate (2 or 4)
     int opt_wave = 4;                // accumulate launch = opt_wave x (CTAs resident on the chip) rows
     bool profile = false;
     std::string err;
@@ -365,15 +360,9 @@ int launch_segment(fsk_handle* h, int nb) {
     const unsigned grid = h->seg_tiles * (unsigned)nb;
     const int ush = h->ids16 ? 3 : 2;
 #define SEG_ARGS (const RecT*)h->d_recA, h->d_valA, n, h->seg_tiles, h->ids_stride, h->idbits, (uint32_t)h->N, ush, h->pad_mask, h->d_fill
-#define SEG_ARGS2 h->d_task[h->buf], h->d_seg_status, h->d_ticket + SEG_TICKET, h->d_flag, stat, h->opt_seg_exp, h->heavy_now, \
+#define SEG_ARGS2 h->d_task[h->buf], h->d_seg_status, h->d_ticket + SEG_TICKET, h->d_flag, stat, h->heavy_now, \
                   h->d_ticket + HEAVY_COUNT, h->d_heavy_list, h->heavy_cap, h->d_heavy_bits, h->heavy_bits_stride
-    if (h->seg_rows == 8 && h->opt_seg_occ == 1)
-        segment_kernel<RecT, KV, uint16_t, 8, 4><<<grid, SEG_THREADS, 0, h->ls>>>(SEG_ARGS, (uint16_t*)h->d_ids[h->buf], SEG_ARGS2);
-    else if (h->seg_rows == 8 && h->opt_seg_occ == 2)
-        segment_kernel<RecT, KV, uint16_t, 8, 5><<<grid, SEG_THREADS, 0, h->ls>>>(SEG_ARGS, (uint16_t*)h->d_ids[h->buf], SEG_ARGS2);
-    else if (h->seg_rows == 8 && h->opt_seg_occ == 3)
-        segment_kernel<RecT, KV, uint16_t, 8, 6><<<grid, SEG_THREADS, 0, h->ls>>>(SEG_ARGS, (uint16_t*)h->d_ids[h->buf], SEG_ARGS2);
-    else if (h->ids16)
+    if (h->ids16)
         segment_kernel<RecT, KV, uint16_t><<<grid, SEG_THREADS, 0, h->ls>>>(SEG_ARGS, (uint16_t*)h->d_ids[h->buf], SEG_ARGS2);
     else
         segment_kernel<RecT, KV, uint32_t><<<grid, SEG_THREADS, 0, h->ls>>>(SEG_ARGS, (uint32_t*)h->d_ids[h->buf], SEG_ARGS2);
@@ -396,15 +385,8 @@ int launch_accumulate(fsk_handle* h, int nb, unsigned long long* K, size_t slot_
         for (int64_t col0 = 0, win = 0; col0 < h->N; col0 += h->col_width, ++win)
         for (int64_t hi = h->N - 1; hi >= col0; hi -= wave) {
             dim3 grid((unsigned)std::min<int64_t>(wave, hi - col0 + 1), groups);
-            auto kern = h->opt_ld_hint == 1 ? accumulate_rows_kernel<unsigned long long, IdT, 4, 1>
-                        : h->opt_ld_hint == 2 ? accumulate_rows_kernel<unsigned long long, IdT, 4, 2>
-                        : h->opt_acc_pipe == 1 && h->opt_acc_unroll == 2 ? accumulate_rows_kernel<unsigned long long, IdT, 2, 0, true>
-                        : h->opt_acc_pipe == 1 && h->opt_acc_unroll == 4 ? accumulate_rows_kernel<unsigned long long, IdT, 4, 0, true>
-                        : h->opt_acc_pipe == 1 && h->opt_acc_unroll == 3 ? accumulate_rows_kernel<unsigned long long, IdT, 3, 0, true>
-                        : h->opt_acc_unroll == 2 ? accumulate_rows_kernel<unsigned long long, IdT, 2, 0>
-                        : h->opt_acc_unroll == 6 ? accumulate_rows_kernel<unsigned long long, IdT, 6, 0>
-                        : h->opt_acc_unroll == 8 ? accumulate_rows_kernel<unsigned long long, IdT, 8, 0>
-                                              : accumulate_rows_kernel<unsigned long long, IdT, 4, 0>;
+            auto kern = h->opt_acc_unroll == 4 ? accumulate_rows_kernel<unsigned long long, IdT, 4>
+                                               : accumulate_rows_kernel<unsigned long long, IdT, 2>;
             kern<<<grid, h->rows_threads, h->rows_smem, h->ls>>>(
                 ids, h->ids_stride, h->d_task[h->buf], h->d_woff32, n, (uint32_t)hi, per_group, K, slot_stride,
                 h->wf_active ? h->d_wf : nullptr, (uint32_t)col0, (uint32_t)h->col_width, (uint32_t)(win * h->N), h->d_heavy_bits,
@@ -554,7 +536,7 @@ int run_batch(fsk_handle* h, const int32_t* combos, int nb, unsigned long long* 
     CU(cudaEventRecord(h->ev_pre[h->buf], h->pre_stream));
     h->ls = h->stream;
     CU(cudaStreamWaitEvent(h->stream, h->ev_pre[h->buf], 0));
-    if (h->opt_seg_exp == 0) {
+    {
         Span sp(h, PC_ACCUMULATE);
         rc = h->ids16 ? launch_accumulate<uint16_t>(h, nb, K, slot_stride) : launch_accumulate<uint32_t>(h, nb, K, slot_stride);
         if (rc) return rc;
@@ -771,8 +753,6 @@ int fsk_set_option(fsk_handle* h, const char* key, int64_t value) {
     } else if (!strcmp(key, "pad")) {
         if (value < 0 || value > 2) return fail(h, FSK_EINVAL, "pad must be 0 (auto), 1 (16-byte units) or 2 (128-byte lines)");
         h->opt_pad = (int)value;
-    } else if (!strcmp(key, "seg_occ")) {
-        h->opt_seg_occ = (int)value;
     } else if (!strcmp(key, "heavy_tau")) {
         if (value < -1) return fail(h, FSK_EINVAL, "heavy_tau must be -1 (off), 0 (auto) or a positive run length");
         h->opt_heavy_tau = (int)value;
@@ -788,17 +768,9 @@ int fsk_set_option(fsk_handle* h, const char* key, int64_t value) {
     } else if (!strcmp(key, "seg_fused")) {
         if (value < 0 || value > 2) return fail(h, FSK_EINVAL, "seg_fused must be 0 (auto), 1 (off) or 2 (on)");
         h->opt_seg_fused = (int)value;
-    } else if (!strcmp(key, "seg_exp")) {
-        h->opt_seg_exp = (int)value;
     } else if (!strcmp(key, "acc_unroll")) {
-        if (value != 2 && value != 3 && value != 4 && value != 6 && value != 8) return fail(h, FSK_EINVAL, "acc_unroll must be 2, 3, 4, 6 or 8");
+        if (value != 2 && value != 4) return fail(h, FSK_EINVAL, "acc_unroll must be 2 or 4");
         h->opt_acc_unroll = (int)value;
-    } else if (!strcmp(key, "acc_pipe")) {
-        h->opt_acc_pipe = (int)value;
-    } else if (!strcmp(key, "ld_hint")) {
-        h->opt_ld_hint = (int)value;
-    } else if (!strcmp(key, "l2_fetch")) {
-        h->opt_l2_fetch = (int)value;
     } else if (!strcmp(key, "profile")) {
         h->profile = value != 0;
     } else {
@@ -978,28 +950,10 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         h->wave_rows = n_sm * per_sm * std::max(1, h->opt_wave);
     }
     if (h->rows_path) {
-        if (h->ids16) {
-            CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-            CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-            CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-            CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-            CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 6, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-            CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-            CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 2, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-            CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 3, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-            CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 4, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-        } else {
-            CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-            CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-            CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-            CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-            CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 6, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-            CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-            CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 2, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-            CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 3, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-            CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 4, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-        }
-        if (h->opt_l2_fetch) CU(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)h->opt_l2_fetch));
+        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
+        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
+        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
+        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
     }
 
     // batch: combinations per launch group.  The row path flushes every row of K once per batch, so it
@@ -1057,7 +1011,7 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         h->heavy_idle = 0;
     }
     h->sort_tiles = (uint32_t)((nfeat + SORT_THREADS * h->sort_items - 1) / (SORT_THREADS * h->sort_items));
-    h->seg_rows = (h->opt_seg_occ >= 1 && h->opt_seg_occ <= 3 && h->ids16 && h->mode == MODE_R32) ? 8 : SEG_ROWS_DEFAULT;
+    h->seg_rows = SEG_ROWS_DEFAULT;
     h->seg_tiles = (uint32_t)((nfeat + seg_tile_records(h->seg_rows) - 1) / seg_tile_records(h->seg_rows));
 
     // device inputs

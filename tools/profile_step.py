@@ -27,18 +27,13 @@ ap.add_argument("--batches-per-call", type=int, default=1)
 ap.add_argument("--wave", type=int, default=4)
 ap.add_argument("--overlap", type=int, default=0)
 ap.add_argument("--rows-threads", type=int, default=0)
-ap.add_argument("--ld-hint", type=int, default=0)
 ap.add_argument("--pad", type=int, default=0)
-ap.add_argument("--l2-fetch", type=int, default=0)
-ap.add_argument("--seg-exp", type=int, default=0)
-ap.add_argument("--seg-occ", type=int, default=0)
 ap.add_argument("--seg-fused", type=int, default=0)
 ap.add_argument("--heavy-tau", type=int, default=0)
 ap.add_argument("--heavy-cap", type=int, default=0)
 ap.add_argument("--gemm-shape", type=int, default=0)
 ap.add_argument("--skew", type=int, default=0, help="1 = first-order Markov GC-rich DNA with a planted 12-mer in half of the sequences (SURVEY 8d)")
 ap.add_argument("--acc-unroll", type=int, default=2)
-ap.add_argument("--acc-pipe", type=int, default=0)
 a = ap.parse_args()
 
 X = np.random.default_rng(0).integers(1, a.alphabet + 1, size=(a.n, a.len), dtype=np.int32)
@@ -63,17 +58,12 @@ f.set_option("acc_path", a.acc_path)
 f.set_option("wave", a.wave)
 f.set_option("overlap", a.overlap)
 f.set_option("rows_threads", a.rows_threads)
-f.set_option("ld_hint", a.ld_hint)
 f.set_option("pad", a.pad)
-f.set_option("l2_fetch", a.l2_fetch)
-f.set_option("seg_exp", a.seg_exp)
-f.set_option("seg_occ", a.seg_occ)
 f.set_option("seg_fused", a.seg_fused)
 f.set_option("heavy_tau", a.heavy_tau)
 f.set_option("heavy_cap", a.heavy_cap)
 f.set_option("gemm_shape", a.gemm_shape)
 f.set_option("acc_unroll", a.acc_unroll)
-f.set_option("acc_pipe", a.acc_pipe)
 codes = np.ascontiguousarray(X.reshape(-1))
 offsets = np.arange(a.n + 1, dtype=np.int64) * a.len
 f._call("fsk_upload", codes.ctypes.data_as(_lib.c_i32p), offsets.ctypes.data_as(_lib.c_i64p), int(a.n * 0.8), a.n - int(a.n * 0.8))
