@@ -6,6 +6,7 @@ relative in variance mode (the block-wise fp64 reduction order differs from the 
 sequential sum; tolerance from BASELINE.json's north_star).
 """
 import ctypes
+import os
 from math import comb
 
 import numpy as np
@@ -485,3 +486,19 @@ def test_errors_and_api_surface(FastSK, tmp_path):
     assert t.is_cuda and t.shape == (2, 2) and t.cpu().numpy().tolist() == f.get_train_kernel().tolist()
     f.fit(C=1.0, kernel_type="fastsk", Ytrain=[1, 0])
     assert 0.0 <= f.score("accuracy", Ytest=[1, 0]) <= 1.0
+
+
+def test_reference_run_check_auc():
+    """The reference's own end-to-end check (test/run_check.py:45-64): FastSK(g=10, m=6, t=1, approx=True) on EP300,
+    LinearSVC + CalibratedClassifierCV on the kernel rows, AUC >= 0.9; and the exact kernel must do at least as well."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("run_check", os.path.join(root, "examples", "run_check.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    train, test = os.path.join(root, "data", "EP300.train.fasta"), os.path.join(root, "data", "EP300.test.fasta")
+    acc, auc, _, iters = mod.run(train, test)
+    assert iters >= 1 and auc >= 0.9, f"approx: AUC {auc}"
+    acc_x, auc_x, _, iters_x = mod.run(train, test, g=10, m=6)
+    assert iters_x == 0 and auc_x >= 0.9, f"exact: AUC {auc_x}"
+
