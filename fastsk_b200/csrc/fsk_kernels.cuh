@@ -398,7 +398,7 @@ struct RecOps {
     static __device__ __forceinline__ bool key_less(RecT a, RecT b, int idbits) { return KV ? a < b : (a >> idbits) < (b >> idbits); }
 };
 
-template <typename RecT, bool KV, typename IdT, int ROWS = SEG_ROWS_DEFAULT, int MINB = (sizeof(RecT) == 4 ? 3 : 2)>
+template <typename RecT, bool KV, typename IdT, bool HEAVY = false, int ROWS = SEG_ROWS_DEFAULT, int MINB = (sizeof(RecT) == 4 ? 3 : 2)>
 __global__ void __launch_bounds__(SEG_THREADS, MINB)
 segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, uint32_t n, uint32_t tiles_per_slot,
                size_t ids_stride, int idbits, uint32_t nseq, int unit_shift, uint32_t pad_mask, uint32_t* __restrict__ fill,
@@ -621,7 +621,7 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
                 const uint32_t X = base + xs[h0 + k];
                 ids[(size_t)slot * ids_stride + X + (i - rs[h0 + k])] = (IdT)sq[h0 + k];
                 uint32_t ln = len[h0 + k];
-                if (heavy_tau) {
+                if (HEAVY && heavy_tau) {                  // (compiled out of the variant launched while the stage sleeps)
                     // a run of more than heavy_tau records is a (nearly) dense column of the count matrix: its d^2/2 updates go to
                     // the tensor-core contraction (heavy_fill_kernel + syrk_tc_kernel) if the batch's list has room, and then the
                     // accumulate skips its tasks.  The records are sorted, so the run is that long iff the record heavy_tau places

@@ -362,10 +362,14 @@ int launch_segment(fsk_handle* h, int nb) {
 #define SEG_ARGS (const RecT*)h->d_recA, h->d_valA, n, h->seg_tiles, h->ids_stride, h->idbits, (uint32_t)h->N, ush, h->pad_mask, h->d_fill
 #define SEG_ARGS2 h->d_task[h->buf], h->d_seg_status, h->d_ticket + SEG_TICKET, h->d_flag, stat, h->heavy_now, \
                   h->d_ticket + HEAVY_COUNT, h->d_heavy_list, h->heavy_cap, h->d_heavy_bits, h->heavy_bits_stride
-    if (h->ids16)
-        segment_kernel<RecT, KV, uint16_t><<<grid, SEG_THREADS, 0, h->ls>>>(SEG_ARGS, (uint16_t*)h->d_ids[h->buf], SEG_ARGS2);
+    if (h->ids16 && h->heavy_now)
+        segment_kernel<RecT, KV, uint16_t, true><<<grid, SEG_THREADS, 0, h->ls>>>(SEG_ARGS, (uint16_t*)h->d_ids[h->buf], SEG_ARGS2);
+    else if (h->ids16)
+        segment_kernel<RecT, KV, uint16_t, false><<<grid, SEG_THREADS, 0, h->ls>>>(SEG_ARGS, (uint16_t*)h->d_ids[h->buf], SEG_ARGS2);
+    else if (h->heavy_now)
+        segment_kernel<RecT, KV, uint32_t, true><<<grid, SEG_THREADS, 0, h->ls>>>(SEG_ARGS, (uint32_t*)h->d_ids[h->buf], SEG_ARGS2);
     else
-        segment_kernel<RecT, KV, uint32_t><<<grid, SEG_THREADS, 0, h->ls>>>(SEG_ARGS, (uint32_t*)h->d_ids[h->buf], SEG_ARGS2);
+        segment_kernel<RecT, KV, uint32_t, false><<<grid, SEG_THREADS, 0, h->ls>>>(SEG_ARGS, (uint32_t*)h->d_ids[h->buf], SEG_ARGS2);
 #undef SEG_ARGS
 #undef SEG_ARGS2
     h->launches++;
