@@ -710,7 +710,7 @@ __device__ __forceinline__ void apply_unit(uint32_t* row, const uint4 v, const u
 // grid = (rows of this wave, groups): CTA x owns row b = row_hi - x; the slots [group * slots_per_group,
 // +slots_per_group) add into the same K.  The host launches the rows in waves of a few CTAs per SM, longest
 // rows first.
-template <typename AccT, typename IdT, int UNROLL>
+template <typename AccT, typename IdT, int UNROLL, bool PREFETCH = true>
 __global__ void __launch_bounds__(1024)
 accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uint2* __restrict__ task,
                        const uint32_t* __restrict__ woff, uint32_t n, uint32_t row_hi, int slots_per_group,
@@ -763,6 +763,21 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
     while (c < nchunks) {
         const uint32_t s = c / cps;
         const uint4* __restrict__ ip = reinterpret_cast<const uint4*>(ids_g + (size_t)s * ids_stride);   // ids_stride is a multiple of 64
+        // The kernel waits mostly on the id loads (ncu: 45 % of the stall samples at their first use, DRAM at 57 % of its peak,
+        // L2 hit rate 5 %).  So the NEXT chunk's tasks are fetched now and the lines of their id ranges are pulled into L2 while
+        // this chunk is applied: a prefetch holds no register and no scoreboard entry.
+        const uint32_t c_next = PREFETCH ? grab() : 0u;
+        uint2 q_next = make_uint2(0, 0);
+        if (PREFETCH) {
+            q_next = load_task(c_next);
+            if (q_next.y) {
+                const char* p = reinterpret_cast<const char*>(ids_g + (size_t)(c_next / cps) * ids_stride) + (size_t)q_next.x * 16;
+                const uint32_t bytes = q_next.y * (uint32_t)sizeof(IdT);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                if (bytes > 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
+                if (bytes > 256u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 256));
+            }
+        }
         const uint32_t my_units = (q.y + PER - 1) >> SH;
         uint32_t incl = my_units;
 #pragma unroll
@@ -799,8 +814,13 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
             issue(base, v);
             apply(base, v);
         }
-        c = grab();
-        q = load_task(c);
+        if (PREFETCH) {
+            c = c_next;
+            q = q_next;
+        } else {
+            c = grab();
+            q = load_task(c);
+        }
     }
     __syncthreads();
     if (wf) {

@@ -56,6 +56,7 @@ struct fsk_handle {
     int opt_seg_fused = 0;           // 0 auto (= off), 1 off, 2 on: fused last sort pass + segmentation (fsk_bucket.cuh) for two-digit keys
     bool fused_seg = false;
     uint32_t image_cap = 0;          // ids in the shared-memory image of a bucket
+    int opt_acc_prefetch = 1;        // 1 = L2 prefetch of the next chunk's id ranges (0: off, for the A/B measurement)
     int opt_acc_unroll = 2;          // id units in flight per lane of the accumulate (2 or 4)
     int opt_wave = 4;                // accumulate launch = opt_wave x (CTAs resident on the chip) rows
     bool profile = false;
@@ -389,8 +390,9 @@ int launch_accumulate(fsk_handle* h, int nb, unsigned long long* K, size_t slot_
         for (int64_t col0 = 0, win = 0; col0 < h->N; col0 += h->col_width, ++win)
         for (int64_t hi = h->N - 1; hi >= col0; hi -= wave) {
             dim3 grid((unsigned)std::min<int64_t>(wave, hi - col0 + 1), groups);
-            auto kern = h->opt_acc_unroll == 4 ? accumulate_rows_kernel<unsigned long long, IdT, 4>
-                                               : accumulate_rows_kernel<unsigned long long, IdT, 2>;
+            auto kern = h->opt_acc_prefetch == 0 ? accumulate_rows_kernel<unsigned long long, IdT, 2, false>
+                        : h->opt_acc_unroll == 4 ? accumulate_rows_kernel<unsigned long long, IdT, 4>
+                                                 : accumulate_rows_kernel<unsigned long long, IdT, 2>;
             kern<<<grid, h->rows_threads, h->rows_smem, h->ls>>>(
                 ids, h->ids_stride, h->d_task[h->buf], h->d_woff32, n, (uint32_t)hi, per_group, K, slot_stride,
                 h->wf_active ? h->d_wf : nullptr, (uint32_t)col0, (uint32_t)h->col_width, (uint32_t)(win * h->N), h->d_heavy_bits,
@@ -772,6 +774,8 @@ int fsk_set_option(fsk_handle* h, const char* key, int64_t value) {
     } else if (!strcmp(key, "seg_fused")) {
         if (value < 0 || value > 2) return fail(h, FSK_EINVAL, "seg_fused must be 0 (auto), 1 (off) or 2 (on)");
         h->opt_seg_fused = (int)value;
+    } else if (!strcmp(key, "acc_prefetch")) {
+        h->opt_acc_prefetch = value != 0;
     } else if (!strcmp(key, "acc_unroll")) {
         if (value != 2 && value != 4) return fail(h, FSK_EINVAL, "acc_unroll must be 2 or 4");
         h->opt_acc_unroll = (int)value;
@@ -954,6 +958,8 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         h->wave_rows = n_sm * per_sm * std::max(1, h->opt_wave);
     }
     if (h->rows_path) {
+        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
+        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
         CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
         CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
         CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));

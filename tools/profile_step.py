@@ -34,6 +34,7 @@ ap.add_argument("--heavy-cap", type=int, default=0)
 ap.add_argument("--gemm-shape", type=int, default=0)
 ap.add_argument("--skew", type=int, default=0, help="1 = first-order Markov GC-rich DNA with a planted 12-mer in half of the sequences (SURVEY 8d)")
 ap.add_argument("--acc-unroll", type=int, default=2)
+ap.add_argument("--acc-prefetch", type=int, default=1)
 a = ap.parse_args()
 
 X = np.random.default_rng(0).integers(1, a.alphabet + 1, size=(a.n, a.len), dtype=np.int32)
@@ -64,6 +65,7 @@ f.set_option("heavy_tau", a.heavy_tau)
 f.set_option("heavy_cap", a.heavy_cap)
 f.set_option("gemm_shape", a.gemm_shape)
 f.set_option("acc_unroll", a.acc_unroll)
+f.set_option("acc_prefetch", a.acc_prefetch)
 codes = np.ascontiguousarray(X.reshape(-1))
 offsets = np.arange(a.n + 1, dtype=np.int64) * a.len
 f._call("fsk_upload", codes.ctypes.data_as(_lib.c_i32p), offsets.ctypes.data_as(_lib.c_i64p), int(a.n * 0.8), a.n - int(a.n * 0.8))
