@@ -710,6 +710,7 @@ __device__ __forceinline__ void apply_unit(uint32_t* row, const uint4 v, const u
 // grid = (rows of this wave, groups): CTA x owns row b = row_hi - x; the slots [group * slots_per_group,
 // +slots_per_group) add into the same K.  The host launches the rows in waves of a few CTAs per SM, longest
 // rows first.
+constexpr uint32_t PF_STRIDE = 128, PF_LINES = 3;    // one prefetch per 128-byte line, reach per task: 384 bytes of ids
 template <typename AccT, typename IdT, int UNROLL, bool PREFETCH = true>
 __global__ void __launch_bounds__(1024)
 accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uint2* __restrict__ task,
@@ -766,18 +767,20 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
         // The kernel waits mostly on the id loads (ncu: 45 % of the stall samples at their first use, DRAM at 57 % of its peak,
         // L2 hit rate 5 %).  So the NEXT chunk's tasks are fetched now and the lines of their id ranges are pulled into L2 while
         // this chunk is applied: a prefetch holds no register and no scoreboard entry.
+        // (one bulk prefetch of exactly the task's id range, issued after this chunk's first step so that the task loads it
+        // depends on have landed)
         const uint32_t c_next = PREFETCH ? grab() : 0u;
         uint2 q_next = make_uint2(0, 0);
-        if (PREFETCH) {
-            q_next = load_task(c_next);
+        if (PREFETCH) q_next = load_task(c_next);
+        auto prefetch_next = [&]() {                 // per-lane prefetches (the bulk form is warp-uniform: 32 serial issues)
             if (q_next.y) {
                 const char* p = reinterpret_cast<const char*>(ids_g + (size_t)(c_next / cps) * ids_stride) + (size_t)q_next.x * 16;
                 const uint32_t bytes = q_next.y * (uint32_t)sizeof(IdT);
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-                if (bytes > 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
-                if (bytes > 256u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 256));
+#pragma unroll
+                for (uint32_t o = 0; o < PF_LINES * PF_STRIDE; o += PF_STRIDE)
+                    if (bytes > o) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
             }
-        }
+        };
         const uint32_t my_units = (q.y + PER - 1) >> SH;
         uint32_t incl = my_units;
 #pragma unroll
@@ -813,7 +816,9 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
             uint4 v[UNROLL];
             issue(base, v);
             apply(base, v);
+            if (PREFETCH && base == 0) prefetch_next();   // after the first step: the task loads it depends on have landed
         }
+        if (PREFETCH && W == 0) prefetch_next();          // (an empty chunk still owes the next one its prefetch)
         if (PREFETCH) {
             c = c_next;
             q = q_next;
