@@ -43,8 +43,9 @@ sys.path.insert(0, ROOT)
 G, M, N_SEQ, N_TRAIN, SEQ_LEN = 16, 8, 50000, 40000, 200
 METRIC, UNIT = "gkm_kernel_build_combinations_per_s", "combinations/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of accumulate_rows_kernel for one batch of 96 combinations of this workload
-# (all rows in one launch, option wave=400), from the ncu --set full capture profiles/r01_ncu_accumulate_rows_batch96.txt
-TRAFFIC_ACC_BATCH96 = 169.345743e9 + 10.008757e9
+# (all rows in one launch, option wave=400), from the ncu --set full capture profiles/r01_ncu_accumulate_rows_batch96_prefetch.txt
+# (the L2 prefetch of whole 128-byte lines moves 195 GB where the demand loads alone moved 169 GB)
+TRAFFIC_ACC_BATCH96 = 194.906825e9 + 10.006337e9
 
 
 def synthetic(n=N_SEQ):
@@ -297,9 +298,9 @@ def run_b200(args):
                 "peak_source": peak_src, "share_of_step": d["ms_accumulate"] / d["ms_total"] if d["ms_total"] else None,
                 "algorithmic_bytes": f"{id_bytes} B x unit pair-updates (ids of the run prefixes) + 16 B x packed-triangle cells per batch",
                 "launch": "one batch = all row waves of the kernel (launched in waves for L2 locality)",
-                "note": "co-limited: ncu (batch 96) shows 179 GB of DRAM traffic for 147 GB algorithmic = 3.7 TB/s (57 % of the measured copy peak; "
-                        "64-byte granularity of the ~140-byte id prefixes, L2 hit rate 5 %), the L1/LSU pipe at 76 % and shared-memory atomic "
-                        "wavefronts at 60 % (4.2 wavefronts per 32-lane atomic from bank conflicts)",
+                "note": "co-limited: ncu (batch 96) shows 205 GB of DRAM traffic for 147 GB algorithmic = 4.7 TB/s (72 % of the measured copy peak; "
+                        "whole 128-byte lines of the ~140-byte id prefixes are prefetched into L2 one chunk ahead), the L1/LSU pipe at 86 % and "
+                        "shared-memory atomic wavefronts at 67 % (4.2 wavefronts per 32-lane atomic from bank conflicts)",
                 "pair_updates_per_s": updates / acc_s if acc_s else None}
     roofline_sort = {"kernel": "pack_hist + onesweep passes + segment", "bound": "hbm", "achieved": sort_bytes / sort_s / 1e9 if sort_s else None,
                      "peak": peak, "unit": "GB/s", "frac": (sort_bytes / sort_s / 1e9 / peak) if sort_s else None,
