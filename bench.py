@@ -467,7 +467,7 @@ def main():
     ap.add_argument("--combos-per-step", type=int, default=384)
     ap.add_argument("--batch", type=int, default=0, help="combinations per launch group (0 = auto)")
     ap.add_argument("--acc-path", type=int, default=0, help="0 auto, 1 global RED, 2 shared-memory rows, 3 dense tensor-core")
-    ap.add_argument("--wave", type=int, default=4, help="accumulate launch = wave x resident CTAs rows")
+    ap.add_argument("--wave", type=int, default=32, help="accumulate launch = wave x resident CTAs rows")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of reference CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-skewed", action="store_true", help="skip the skewed-set section of other_workloads (~6 s)")

@@ -24,7 +24,7 @@ ap.add_argument("--alphabet", type=int, default=4)
 ap.add_argument("--acc-path", type=int, default=0)
 ap.add_argument("--reps", type=int, default=1)
 ap.add_argument("--batches-per-call", type=int, default=1)
-ap.add_argument("--wave", type=int, default=4)
+ap.add_argument("--wave", type=int, default=32)
 ap.add_argument("--overlap", type=int, default=0)
 ap.add_argument("--rows-threads", type=int, default=0)
 ap.add_argument("--pad", type=int, default=0)
