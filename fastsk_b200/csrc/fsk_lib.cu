@@ -113,6 +113,7 @@ struct fsk_handle {
     __half* d_C = nullptr;
     // heavy runs of the sparse regime: runs longer than heavy_tau leave the row path for a tensor-core contraction
     int opt_heavy_tau = 0;                             // 0 auto, -1 off, > 0 forced threshold
+    int opt_ids32 = 0;                                 // test hook: 32-bit id stream although N <= 65000
     int opt_gemm_shape = 0;                            // 0 auto, 1 one tile per CTA, 2 two tiles per CTA sharing B
     int opt_heavy_cap = 0;                             // 0 auto, else columns of d_H (tests: a small list overflows)
     uint32_t heavy_tau = 0;                            // 0 = feature off
@@ -762,6 +763,8 @@ int fsk_set_option(fsk_handle* h, const char* key, int64_t value) {
     } else if (!strcmp(key, "heavy_tau")) {
         if (value < -1) return fail(h, FSK_EINVAL, "heavy_tau must be -1 (off), 0 (auto) or a positive run length");
         h->opt_heavy_tau = (int)value;
+    } else if (!strcmp(key, "ids32")) {
+        h->opt_ids32 = value != 0;
     } else if (!strcmp(key, "gemm_shape")) {
         if (value < 0 || value > 2) return fail(h, FSK_EINVAL, "gemm_shape must be 0 (auto), 1 or 2 tiles per CTA");
         h->opt_gemm_shape = (int)value;
@@ -917,7 +920,7 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     h->rows_smem = (size_t)std::min<int64_t>(N, h->col_width) * 4 + 128;   // + one dump word per lane for masked-off ids
     h->rows_threads = N >= 16384 ? 1024 : (N >= 4096 ? 512 : 256);
     if (h->opt_rows_threads) h->rows_threads = h->opt_rows_threads;
-    h->ids16 = N <= 65000;   // u16 ids leave room for the 32 dump words b + 1 + lane (packed 16-bit min in the accumulate)
+    h->ids16 = N <= 65000 && !h->opt_ids32;   // u16 ids leave room for the 32 dump words b + 1 + lane (packed 16-bit min in the accumulate)
     {
         // runs of the id stream are aligned (segment_kernel): to one 16-byte unit always, to a 128-byte line when the
         // padding costs at most half of the stream again (few, long runs -- the HBM fetches whole lines either way)

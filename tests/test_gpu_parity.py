@@ -311,6 +311,27 @@ def test_heavy_runs_on_the_tensor_cores(FastSK, oracle_mod, shape):
     assert np.array_equal(on[0].astype(np.uint64), Ki)
 
 
+@pytest.mark.parametrize("heavy_tau,cols", [(-1, 0), (8, 0), (-1, 64), (8, 64)], ids=["plain", "heavy", "windows", "heavy_windows"])
+def test_32bit_id_stream(FastSK, oracle_mod, heavy_tau, cols):
+    """More than 65 000 sequences need 32-bit ids in the id stream (4 ids per 16-byte unit, the min-with-dump-word path
+    of apply_unit); option ids32 forces that layout at test sizes, alone and with heavy runs and column windows."""
+    rng = np.random.default_rng(77)
+    g, m = 9, 4                                                  # 5 x 2 = 10 key bits
+    X = random_seqs(rng, 260, 4, 20, 90, True)
+    queue = rng.permutation(comb(g, m))[:16].astype(np.int32)
+    f = FastSK(g, m, combo_sequence=queue, profile=True)
+    f.set_option("acc_path", 2)
+    f.set_option("ids32", 1)
+    f.set_option("heavy_tau", heavy_tau)
+    if cols:
+        f.set_option("acc_cols", cols)
+    f.compute_train(X)
+    _, Ki, _ = oracle_mod.run("c", X, [], g, m, queue)
+    assert np.array_equal(f.get_unnormalised().astype(np.uint64), Ki)
+    if heavy_tau > 0:
+        assert f.stats()["heavy_runs"] > 0
+
+
 FUSED_CASES = [
     # name, n, alphabet, len range, g, m, low complexity, batch
     ("dna_14bit", 120, 4, (40, 160), 12, 5, False, 0),          # 7 + 7 bits: 128 buckets x 128 runs
