@@ -710,7 +710,7 @@ __device__ __forceinline__ void apply_unit(uint32_t* row, const uint4 v, const u
 // grid = (rows of this wave, groups): CTA x owns row b = row_hi - x; the slots [group * slots_per_group,
 // +slots_per_group) add into the same K.  The host launches the rows in waves of a few CTAs per SM, longest
 // rows first.
-constexpr uint32_t PF_STRIDE = 128, PF_LINES = 3, PF_SKIP = 0;     // one prefetch per 128-byte line, reach 384 bytes of ids (PF_SKIP = 48, not prefetching a line the range barely enters, measured 179.6 against 171.4 ms)
+constexpr uint32_t PF_STRIDE = 128, PF_LINES = 3, PF_SKIP = 0, PF_REACH = 4096;     // one prefetch per 128-byte line, reach 384 bytes of ids (PF_SKIP = 48, not prefetching a line the range barely enters, measured 179.6 against 171.4 ms)
 template <typename AccT, typename IdT, int UNROLL, bool PREFETCH = true>
 __global__ void __launch_bounds__(1024)
 accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uint2* __restrict__ task,
@@ -779,6 +779,9 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
 #pragma unroll
                 for (uint32_t o = 0; o < PF_LINES * PF_STRIDE; o += PF_STRIDE)
                     if (bytes > o + PF_SKIP) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+                // long ranges (skewed inputs): up to PF_REACH bytes; the uniform workload never gets here
+                for (uint32_t o = PF_LINES * PF_STRIDE; o < min(bytes, PF_REACH); o += PF_STRIDE)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
             }
         };
         const uint32_t my_units = (q.y + PER - 1) >> SH;
