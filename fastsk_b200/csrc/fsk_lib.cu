@@ -1007,7 +1007,8 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         // of the measured break-even (~0.05 N; 0.06 N used) and what keeps the batch's heavy runs within 65536 columns / 8 GB.
         h->heavy_tau = 0;
         const bool ok = h->rows_path && !h->variance_mode && h->mode != MODE_KV && maxwin <= 2048 &&
-                        (double)Bsel * (double)maxwin * (double)maxwin < 16777216.0 && !h->fused_seg && h->opt_heavy_tau >= 0;
+                        (double)Bsel * (double)maxwin * (double)maxwin < 16777216.0 && !h->fused_seg && h->opt_heavy_tau >= 0 &&
+                        !h->opt_overlap;   // (the list and its bitmap are single-buffered: not with the two-stream overlap)
         if (h->opt_heavy_tau > 0 && !ok)
             return fail(h, FSK_EINVAL, "heavy_tau needs the row path in an integer mode, at most 2048 windows per sequence and batch x windows^2 < 2^24");
         if (ok) {
