@@ -118,6 +118,44 @@ def test_fasta_utility_matches_reference_encoding():
     assert FastaUtility().shortest_seq(os.path.join(DATA_DIR, "small.train.fasta")) == 5
 
 
+def test_read_encoded_vectorised_and_record_parsers_agree(tmp_path):
+    """FASTA -> flat codes + offsets without lists of Python ints.  Plain ASCII files take one
+    vectorised pass over the bytes; files with blanks, carriage returns or non-ASCII text go record by record.  Both
+    must give read_data's ids (first-seen order, shared vocabulary across train and test) and labels."""
+    from fastsk_b200 import FastaUtility
+    for name in ("EP300", "1.1", "AImed", "small"):
+        a, b = FastaUtility(), FastaUtility()
+        for part in ("train", "test"):                      # one utility for both files, as every caller does
+            path = os.path.join(DATA_DIR, f"{name}.{part}.fasta")
+            X, Y = a.read_data(path)
+            codes, offsets, labels = b.read_encoded(path)
+            assert codes.dtype == np.int32 and offsets.dtype == np.int64
+            assert labels == Y and codes.tolist() == [v for x in X for v in x]
+            assert offsets.tolist() == np.concatenate([[0], np.cumsum([len(x) for x in X])]).tolist()
+        assert str(a._vocab) == str(b._vocab)
+    assert FastaUtility()._read_encoded_bytes(os.path.join(DATA_DIR, "EP300.train.fasta"), False) is not None
+    assert FastaUtility()._read_encoded_bytes(os.path.join(DATA_DIR, "AImed.train.fasta"), False) is None   # text with blanks
+
+    rng = np.random.default_rng(0)
+    letters = np.array(list("ACGT"))
+    lines = []
+    for i in range(600):
+        s = "".join(letters[rng.integers(0, 4, int(rng.integers(20, 400)))])
+        if i == 500:
+            s = s[:7] + "n" + s[8:]                         # a character that first appears far beyond the head
+        if i % 3 == 0:
+            s = s.lower()
+        lines += [">%s" % ("+1" if i % 7 == 0 else ("-1" if i % 2 else "0")), s]
+    for tag, text in (("lf", "\n".join(lines) + "\n"), ("no_final_newline", "\n".join(lines)), ("crlf", "\r\n".join(lines) + "\r\n")):
+        path = tmp_path / f"{tag}.fasta"
+        path.write_bytes(text.encode())
+        a, b = FastaUtility(), FastaUtility()
+        X, Y = a.read_data(str(path))
+        codes, offsets, labels = b.read_encoded(str(path))
+        assert labels == Y and codes.tolist() == [v for x in X for v in x] and str(a._vocab) == str(b._vocab), tag
+        assert (FastaUtility()._read_encoded_bytes(str(path), False) is None) == (tag == "crlf")
+
+
 def test_flatten_accepts_lists_arrays_and_flat_pairs():
     from fastsk_b200.fastsk import _flatten
     c, o = _flatten([[1, 2, 3], [4, 5]])
