@@ -67,7 +67,10 @@ int fsk_set_shard(fsk_handle* h, int rank, int world);
  * per-sequence k-mer counts contracted as K += C C^T by tcgen05 tensor-core MMAs, no sort; needs at most
  * 12 key bits and 2048 windows per sequence, chosen automatically when its cost model wins); unknown
  * keys give FSK_EINVAL.  "heavy_tau": -1 off, 0 auto, > 0 forced run-length threshold above which a run's update goes to the
- * tensor cores instead of the row path; "acc_cols": forced column-window width of the row path (tests) */
+ * tensor cores instead of the row path; "heavy_cap": columns of that contraction's list (0 auto); "gemm_shape": 0 auto, 1 or 2
+ * output tiles per CTA of the contraction; "seg_fused": 2 = fused last sort pass + segmentation for two-digit keys (opt-in);
+ * "acc_prefetch", "acc_unroll", "wave", "rows_threads", "pad", "overlap", "safe_rank": tuning of the row path (defaults are the
+ * measured optimum); test hooks: "acc_cols" (forced column-window width of the row path), "ids32" (32-bit id stream) */
 int fsk_set_option(fsk_handle* h, const char* key, int64_t value);
 
 /* ---- compute ---------------------------------------------------------------------------- */
