@@ -1101,6 +1101,12 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         CU(cudaFuncSetAttribute(dense_count_kernel<uint32_t, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, count_smem));
     }
     if (h->heavy_tau) {
+        // optional stage: it must not be what makes a large upload run out of memory (K and the outputs are still to come)
+        size_t free_now = 0, total_now = 0;
+        CU(cudaMemGetInfo(&free_now, &total_now));
+        if ((double)free_now < (double)N * h->heavy_cap * 2.0 + (double)k_bytes + (double)(2LL << 30)) h->heavy_tau = h->heavy_tau_min = 0;
+    }
+    if (h->heavy_tau) {
         ALLOC(h->d_H, (size_t)N * h->heavy_cap);
         ALLOC(h->d_heavy_list, h->heavy_cap);
         if (!h->h_heavy_count) CU(cudaMallocHost((void**)&h->h_heavy_count, sizeof(uint32_t)));
