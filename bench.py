@@ -7,14 +7,17 @@
 Workload (config.workload): BASELINE.json configs[3], the north-star target --
     X = numpy.random.default_rng(0).integers(1, 5, size=(50000, 200)), train = first 40000, g=16, m=8,
     exact mode, 12 870 combinations in a seed-0 shuffled order.
-One step = `--combos-per-step` combinations per GPU run through the whole per-combination path
-(pack, sort, segment, accumulate into the resident int64 packed triangle).  Per-GPU work per step is
-fixed, so scaling is "weak"; value = combinations processed by all ranks / max-over-ranks device time.
+One step = ONE COMPLETE BUILD of that kernel: all 12 870 combinations, dealt round-robin to the N ranks (pack, sort,
+segment, accumulate into each rank's int64 packed triangle), then the normalisation of each rank's share of the
+output rows, which merges the partial kernels of all ranks over NVLink as it reads them.  Total work per step is
+fixed, so scaling is "strong"; value = 12 870 x steps / max-over-ranks device time, wall_s_per_build beside it.
 
 value      inputs resident in HBM, CUDA events on the library's stream, barrier + sync on both sides
-e2e        the same number of combinations as one job through the public API with HOST buffers:
-           FastSK(...).compute_kernel(Xtrain, Xtest) (H2D of the sequences, sharded build, NCCL all-reduce
-           when N > 1, normalisation) + get_train_kernel/get_test_kernel into pinned host memory (D2H)
+e2e        the same build as one job through the public API with HOST buffers: FastSK(...).compute_kernel(Xtrain,
+           Xtest) (H2D of the sequences on every rank, sharded build, peer merge + normalisation) +
+           get_train_kernel/get_test_kernel into pinned host memory every rank maps (parallel D2H); wall_s
+parity     after the timed region the job's own output is compared, bit for bit, with the C oracle on a sample of
+           sequences (K_ij depends on sequences i and j only): parity_ok
 roofline   dominant kernel class of the step, timed with CUDA events inside the timed region
 cpu_baseline / --impl reference
            the reference's own C++ engine (oracle/_ref, compiled from /root/reference in the authoring
@@ -124,7 +127,7 @@ def ref_sample_size(budget_s):
     return max(2000, min(46000, n // 1000 * 1000))
 
 
-def reference_step(n_ref, threads, combos):
+def reference_step(n_ref, threads, combos, keep=False):
     """One bounded sample on the host: `threads` reference threads, len(combos) combinations."""
     import oracle
     X = synthetic(n_ref)
@@ -136,23 +139,44 @@ def reference_step(n_ref, threads, combos):
     os.dup2(devnull, 1)       # the reference prints from its worker threads
     try:
         t0 = time.perf_counter()
-        oracle.run("ref" if kind == "reference" else "c", X[:ntr], X[ntr:], G, M, combos, T=threads)
+        K, _, _ = oracle.run("ref" if kind == "reference" else "c", X[:ntr], X[ntr:], G, M, combos, T=threads)
         dt = time.perf_counter() - t0
     finally:
         os.dup2(saved, 1)
         os.close(devnull)
         os.close(saved)
-    return dt, kind
+    return (dt, kind, K) if keep else (dt, kind)
 
 
-def cpu_baseline(budget_s):
+def cpu_baseline(budget_s, device):
+    """The reference on the host cores on a bounded sample, and -- same sequences, same combinations -- this library:
+    the full unnormalised matrix must be equal, and the two times are a like-for-like ratio."""
     n_ref = ref_sample_size(budget_s)
     threads, cores = host_threads(n_ref)
     combos = queue_order()[:threads]
-    dt, kind = reference_step(n_ref, threads, combos)
-    return {"value": len(combos) / dt, "unit": UNIT, "cores": threads, "host_cores": cores, "kind": kind, "seconds": dt,
-            "sample": f"{len(combos)} combinations (one per thread, t={threads}) of the same synthetic set cut to N={n_ref} "
-                      f"sequences x {SEQ_LEN} bp, g={G} m={M}, exact mode, incl. g-mer extraction and merge"}
+    dt, kind, K_ref = reference_step(n_ref, threads, combos, keep=True)
+    cpu = {"value": len(combos) / dt, "unit": UNIT, "cores": threads, "host_cores": cores, "kind": kind, "seconds": dt,
+           "sample": f"{len(combos)} combinations (one per thread, t={threads}) of the same synthetic set cut to N={n_ref} "
+                     f"sequences x {SEQ_LEN} bp, g={G} m={M}, exact mode, incl. g-mer extraction and merge"}
+    from fastsk_b200 import FastSK
+    X = synthetic(n_ref)
+    ntr = int(n_ref * 0.8)
+    best = None
+    for _ in range(2):                     # the second run re-uses the device blocks of the first
+        f = FastSK(G, M, combo_sequence=combos, device=device, distributed=False, profile=True)
+        t0 = time.perf_counter()
+        f.compute_kernel(X[:ntr], X[ntr:])
+        t1 = time.perf_counter() - t0
+        best = t1 if best is None else min(best, t1)
+        dev_ms = f.stats()["ms_total"]
+        K_gpu = f.get_unnormalised(np.float64)
+        del f
+    same = {"workload": cpu["sample"], "parity_ok_full_matrix": bool(np.array_equal(K_gpu, K_ref)), "cells": int(K_ref.size),
+            "reference_s": dt, "b200_compute_kernel_s": best, "b200_device_ms": dev_ms, "ratio_e2e": dt / best,
+            "ratio_device": dt / (dev_ms * 1e-3) if dev_ms else None,
+            "what": "same sequences, same combinations, same mode on both sides; b200 time = compute_kernel from host arrays "
+                    "(upload + build + normalisation), so 16 combinations mostly measure its fixed costs"}
+    return cpu, same
 
 
 def run_reference_arm(args):
@@ -187,10 +211,36 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
+def parity_sample(n_seq, n_train, k=48, seed=5):
+    """Sequences whose K sub-block is checked against the oracle after the timed region: row 0, the last train row, the
+    first test row, row N-1 and random others from both blocks."""
+    rng = np.random.default_rng(seed)
+    fixed = [0, n_train - 1, n_train, n_seq - 1]
+    rest = rng.choice(np.setdiff1d(np.arange(n_seq), fixed), size=k - len(fixed), replace=False)
+    return np.sort(np.concatenate([fixed, rest])).astype(np.int64)
+
+
+def parity_check(X, n_train, train, test, queue, sample):
+    """K_ij depends on sequences i and j only, so the oracle run on the sampled sequences alone gives the cells of the
+    full build at those rows and columns: the normalised values must be bit-equal (exact mode: integer sums, then the
+    same IEEE mul / sqrt / div)."""
+    import oracle
+    sub = X[sample]
+    K, _, _ = oracle.run("c", sub.tolist(), [], G, M, queue, T=1, normalise=True)
+    S = oracle.unpack(K, len(sample))
+    cols = sample[sample < n_train]
+    got = np.empty((len(sample), len(cols)))
+    for a, i in enumerate(sample):
+        got[a] = train[i, cols] if i < n_train else test[i - n_train, cols]
+    want = S[:, :len(cols)]
+    return bool(np.array_equal(got, want)), int((got != want).sum())
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
     from fastsk_b200 import FastSK, _lib
+    from fastsk_b200.fastsk import pinned_empty, shared_output
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -208,46 +258,62 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
+    def reduce_ranks(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    max_over_ranks = lambda x: reduce_ranks(x, dist.ReduceOp.MAX)   # noqa: E731
+    sum_over_ranks = lambda x: reduce_ranks(x, dist.ReduceOp.SUM)   # noqa: E731
 
     X = synthetic()
-    Xtr, Xte = X[:N_TRAIN], X[N_TRAIN:]
-    queue = queue_order()
-    cps = args.combos_per_step
-    total_steps = args.warmup + args.steps
-    need = total_steps * cps * world
-    order = np.resize(queue, need) if need > len(queue) else queue[:need]
+    n_test = N_SEQ - N_TRAIN
+    queue = queue_order() if args.combos == 0 else queue_order()[:args.combos]
+    n_combos = len(queue)
 
-    # ---- resident-input arm -------------------------------------------------------------------
-    f = FastSK(G, M, combo_sequence=order, device=local, distributed=False, profile=True)
+    # ---- resident-input arm: one step = one complete exact build -----------------------------------
+    # reset -> this rank's shard of the combinations (pack, sort, segment, accumulate) -> barrier -> normalisation of this
+    # rank's output rows, which sums the partial kernels of all ranks over NVLink as it reads them -> barrier
+    f = FastSK(G, M, combo_sequence=queue, device=local, distributed=False, profile=True)
     f.set_option("batch", args.batch)
     f.set_option("acc_path", args.acc_path)
     f.set_option("wave", args.wave)
+    f.set_shard(rank, world)
     codes = np.ascontiguousarray(X.reshape(-1))
     offsets = np.arange(N_SEQ + 1, dtype=np.int64) * SEQ_LEN
-    f._call("fsk_upload", codes.ctypes.data_as(_lib.c_i32p), offsets.ctypes.data_as(_lib.c_i64p), N_TRAIN, N_SEQ - N_TRAIN)
+    f._call("fsk_upload", codes.ctypes.data_as(_lib.c_i32p), offsets.ctypes.data_as(_lib.c_i64p), N_TRAIN, n_test)
+    merge = "none (one GPU)"
+    if world > 1:
+        if f._exchange_peers(dist, world):
+            merge = "peer loads over NVLink inside the normalisation kernel (CUDA IPC)"
+        else:
+            merge = "NCCL all-reduce (CUDA IPC unavailable)"
     sp = ctypes.c_void_p()
     f._call("fsk_stream", ctypes.byref(sp))
     stream = torch.cuda.ExternalStream(sp.value, device=f"cuda:{local}")
+    t_build = t_final = 0.0
 
-    def step(i):
-        mine = np.ascontiguousarray(order[(i * world + rank) * cps:(i * world + rank + 1) * cps])
-        f._call("fsk_accumulate_combos", mine.ctypes.data_as(_lib.c_i32p), len(mine), 0)
+    def step(timed):
+        nonlocal t_build, t_final
+        t0 = time.perf_counter()
+        f._call("fsk_build_partial")
+        t1 = time.perf_counter()
+        if world > 1:
+            dist.barrier()
+            if merge.startswith("NCCL"):
+                dist.all_reduce(f.partial_tensor(), op=dist.ReduceOp.SUM)
+                torch.cuda.synchronize()
+        f._call("fsk_finalize")
+        if world > 1:
+            dist.barrier()
+        if timed:
+            t_build += t1 - t0
+            t_final += time.perf_counter() - t1
 
-    for i in range(args.warmup):
-        step(i)
+    for _ in range(args.warmup):
+        step(False)
     f._call("fsk_synchronize")
     st0 = f.stats()
     clocks = ClockSampler(local)
@@ -255,8 +321,8 @@ def run_b200(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     ev0.record(stream)
-    for i in range(args.warmup, total_steps):
-        step(i)
+    for _ in range(args.steps):
+        step(True)
     ev1.record(stream)
     f._call("fsk_synchronize")
     barrier()
@@ -264,64 +330,65 @@ def run_b200(args):
     ms = max_over_ranks(ev0.elapsed_time(ev1))
     clock_info = clocks.stop(t_wall0, t_wall1)
     st1 = f.stats()
-    value = args.steps * cps * world / (ms * 1e-3)
+    value = args.steps * n_combos / (ms * 1e-3)
     d = {k: st1[k] - st0[k] for k in st1 if isinstance(st1[k], (int, float))}
     combos_rank = d["combos_done"]
     updates = d["pair_updates"]
     launches = int(sum_over_ranks(d["kernel_launches"]))
-
-    # finalize (reduction over NVLink + normalisation), timed once, reported beside the rate
-    barrier()
-    t0 = time.perf_counter()
-    if world > 1:
-        dist.all_reduce(f.partial_tensor(), op=dist.ReduceOp.SUM)
-        torch.cuda.synchronize()
-    f._call("fsk_finalize")
-    finalize_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    updates_all = sum_over_ranks(float(updates))
+    build_ms = max_over_ranks(1e3 * t_build / args.steps)
+    merge_norm_ms = max_over_ranks(1e3 * t_final / args.steps)
 
     peak, peak_src = measured_peak()
     n_pairs, nfeat, rec = st1["n_pairs"], st1["nfeat"], st1["record_bytes"]
     batches = max(1, -(-combos_rank // max(1, st1["batch"])))
-    id_bytes = 2 if N_SEQ <= 65536 else 4
-    # accumulate (dominant kernel, launched in waves of rows; figures are per batch = one pass over all rows): every unit
-    # update streams one sequence id of a run prefix (2 B as u16) and every batch adds each 8-byte cell of the packed
-    # triangle once (RED = read + write)
+    id_bytes = 2 if N_SEQ <= 65000 else 4
+    # accumulate (dominant kernel; figures per batch = one pass over all rows): every unit update streams one sequence id
+    # of a run prefix (2 B as u16) and every batch adds each 8-byte cell of the packed triangle once (RED = read + write)
     acc_bytes = float(id_bytes) * updates + 16.0 * n_pairs * batches
     acc_s = d["ms_accumulate"] * 1e-3
-    # pack + sort + segment: SURVEY 8(d) formula with the record width actually moved (4 B here, not 8)
+    traffic_batch = (TRAFFIC_ACC_BATCH96 - 16.0 * n_pairs) * st1["batch"] / 96.0 + 16.0 * n_pairs
     gw_bytes = 4 if G * st1["bits_per_char"] <= 32 else 8
-    sort_bytes = combos_rank * nfeat * ((gw_bytes + 4 + rec) + 2 * rec * st1["sort_passes"] + (rec + id_bytes + 8))
+    # pre-pass bytes per window and combination.  pack: the g-mer word and window -> sequence table are shared by all
+    # slots of a batch and come from L2 (ncu: 0.07 GB of DRAM reads per batch), so its HBM traffic is the record it writes;
+    # sort: one read + one write per pass; segment: read the sorted record, write the id (+ the task of the task-list form)
+    seg_bytes = rec + id_bytes + (8 if st1.get("seg_mode", 0) == 0 else 0)
+    stage_bytes = {"pack": rec, "sort": 2 * rec * st1["sort_passes"], "segment": seg_bytes}
+    sort_bytes = combos_rank * nfeat * sum(stage_bytes.values())
     sort_s = (d["ms_pack"] + d["ms_sort"] + d["ms_segment"]) * 1e-3
     roofline = {"kernel": "accumulate_rows_kernel", "bound": "hbm", "achieved": acc_bytes / acc_s / 1e9 if acc_s else None,
-                "peak": peak, "unit": "GB/s", "frac": (acc_bytes / acc_s / 1e9 / peak) if acc_s else None, "traffic": (TRAFFIC_ACC_BATCH96 - 16.0 * n_pairs) * st1["batch"] / 96.0 + 16.0 * n_pairs, "traffic_unit": "bytes per batch (ncu dram read + write at batch 96; the id-stream part scaled to this batch, the 16 B x cells flush part not)",
+                "peak": peak, "unit": "GB/s", "frac": (acc_bytes / acc_s / 1e9 / peak) if acc_s else None,
+                "traffic": traffic_batch,
+                "traffic_unit": "bytes per batch (ncu dram read + write at batch 96; the id-stream part scaled to this batch, the 16 B x cells flush part not)",
+                "frac_measured_traffic": (traffic_batch * batches / acc_s / 1e9 / peak) if acc_s else None,
                 "achieved_per_launch_bytes": acc_bytes / batches,
                 "peak_source": peak_src, "share_of_step": d["ms_accumulate"] / d["ms_total"] if d["ms_total"] else None,
                 "algorithmic_bytes": f"{id_bytes} B x unit pair-updates (ids of the run prefixes) + 16 B x packed-triangle cells per batch",
                 "launch": "one batch = all row waves of the kernel (launched in waves for L2 locality)",
-                "note": "co-limited: ncu (batch 96) shows 205 GB of DRAM traffic for 147 GB algorithmic = 4.7 TB/s (72 % of the measured copy peak; "
-                        "whole 128-byte lines of the ~140-byte id prefixes are prefetched into L2 one chunk ahead), the L1/LSU pipe at 86 % and "
-                        "shared-memory atomic wavefronts at 67 % (4.2 wavefronts per 32-lane atomic from bank conflicts)",
-                "pair_updates_per_s": updates / acc_s if acc_s else None}
+                "note": "co-limited: shared-memory atomic wavefronts (4.2 per 32-lane atomic from bank conflicts), the L1/LSU pipe and DRAM "
+                        "(whole 128-byte lines of the ~140-byte id prefixes); see profiles/ for the ncu captures"}
     roofline_sort = {"kernel": "pack_hist + onesweep passes + segment", "bound": "hbm", "achieved": sort_bytes / sort_s / 1e9 if sort_s else None,
                      "peak": peak, "unit": "GB/s", "frac": (sort_bytes / sort_s / 1e9 / peak) if sort_s else None,
+                     "frac_survey_8d_nominal": (combos_rank * (N_SEQ * SEQ_LEN + nfeat * 8.0 * (3 + 2 * st1["sort_passes"])) / sort_s / 1e9 / peak) if sort_s else None,
                      "share_of_step": (d["ms_pack"] + d["ms_sort"] + d["ms_segment"]) / d["ms_total"] if d["ms_total"] else None,
-                     "algorithmic_bytes": f"per combination and window: ({gw_bytes}+4+{rec}) pack + 2 x {rec} x {st1['sort_passes']} passes + "
-                                          f"({rec}+{id_bytes}+8) segment",
-                     "per_stage_gbs": {
-                         "pack": combos_rank * nfeat * (gw_bytes + 4 + rec) / (d["ms_pack"] * 1e-3) / 1e9 if d["ms_pack"] else None,
-                         "sort": combos_rank * nfeat * 2 * rec * st1["sort_passes"] / (d["ms_sort"] * 1e-3) / 1e9 if d["ms_sort"] else None,
-                         "segment": combos_rank * nfeat * (rec + id_bytes + 8) / (d["ms_segment"] * 1e-3) / 1e9 if d["ms_segment"] else None}}
+                     "algorithmic_bytes": "per combination and window: " + " + ".join(f"{v} {k}" for k, v in stage_bytes.items()) +
+                                          " (HBM bytes: pack's inputs are L2 hits shared by the slots of a batch); frac_survey_8d_nominal uses "
+                                          "SURVEY 8(d)'s B_combo with 8-byte records",
+                     "per_stage_gbs": {k: (combos_rank * nfeat * v / (d["ms_" + k] * 1e-3) / 1e9 if d["ms_" + k] else None)
+                                       for k, v in stage_bytes.items()}}
     phase_ms = {k[3:]: d[k] / args.steps for k in d if k.startswith("ms_")}
+    f._call("fsk_release_peers")
+    barrier()
     del f
     torch.cuda.empty_cache()
 
-    # ---- end-to-end arm: public API, host buffers ------------------------------------------------
-    job = order[args.warmup * cps * world:]
-    pin = lambda n: torch.empty(n, dtype=torch.float64).pin_memory().numpy()  # noqa: E731
-    out_tr = pin(N_TRAIN * N_TRAIN).reshape(N_TRAIN, N_TRAIN) if rank == 0 else None
-    out_te = pin((N_SEQ - N_TRAIN) * N_TRAIN).reshape(N_SEQ - N_TRAIN, N_TRAIN) if rank == 0 else None
-    Xtr_p = torch.from_numpy(Xtr.copy()).pin_memory().numpy()
-    Xte_p = torch.from_numpy(Xte.copy()).pin_memory().numpy()
+    # ---- end-to-end arm: the same build as ONE job through the public API, host buffers in and out -------------------
+    if world > 1:
+        out_tr, out_te = shared_output(N_TRAIN, N_TRAIN, dist), shared_output(n_test, N_TRAIN, dist)
+    else:
+        out_tr, out_te = pinned_empty((N_TRAIN, N_TRAIN)), pinned_empty((n_test, N_TRAIN))
+    Xtr_p, Xte_p = pinned_empty((N_TRAIN, SEQ_LEN), np.int32), pinned_empty((n_test, SEQ_LEN), np.int32)
+    Xtr_p[:], Xte_p[:] = X[:N_TRAIN], X[N_TRAIN:]
 
     def e2e_job(q):
         t = [time.perf_counter()]
@@ -331,46 +398,69 @@ def run_b200(args):
         fe.set_option("wave", args.wave)
         fe.compute_kernel(Xtr_p, Xte_p)
         t.append(time.perf_counter())
-        if rank == 0:
-            fe.get_train_kernel(out=out_tr)
-            fe.get_test_kernel(out=out_te)
+        fe.get_train_kernel(out=out_tr)
+        fe.get_test_kernel(out=out_te)
         t.append(time.perf_counter())
         return {"compute_kernel_s": t[1] - t[0], "get_kernels_d2h_s": t[2] - t[1]}, fe
 
-    _, fe = e2e_job(job[:world * min(cps, 8)])        # warm-up: allocator, NCCL channels
+    _, fe = e2e_job(queue[:world * 8])               # warm-up: device blocks, NCCL channels, IPC
     del fe
+    e2e_runs = []
+    for _ in range(1 if world == 1 else 2):
+        barrier()
+        t0 = time.perf_counter()
+        e2e_parts, fe = e2e_job(queue)               # both kernels are in host memory when this returns
+        torch.cuda.synchronize()
+        e2e_runs.append(max_over_ranks(time.perf_counter() - t0))
+        del fe
+    e2e_s = min(e2e_runs)
     barrier()
-    t0 = time.perf_counter()
-    e2e_parts, fe = e2e_job(job)                      # both kernels are in host memory when this returns
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    del fe                                            # teardown (cudaFree of ~40 GB) is not part of the job's result
-    barrier()
-    e2e = {"value": len(job) / e2e_s, "unit": UNIT, "seconds": e2e_s, "combinations": int(len(job)), "parts_rank0": e2e_parts,
-           "h2d_bytes_per_step": int(X.nbytes // args.steps), "d2h_bytes_per_step": int((out_tr.nbytes + out_te.nbytes) // args.steps) if rank == 0 else 0,
-           "what": "FastSK(g,m,combo_sequence=<the timed region's combinations>).compute_kernel(Xtrain, Xtest) from pinned host int32 + "
-                   "get_train_kernel/get_test_kernel into pinned host fp64 (one job = all steps; bytes are per-step shares)"}
+    d2h = int(sum_over_ranks(float(out_tr.nbytes // world + out_te.nbytes // world)))
+    e2e = {"value": n_combos / e2e_s, "unit": UNIT, "wall_s": e2e_s, "runs_s": e2e_runs, "combinations": int(n_combos),
+           "parts_rank0": e2e_parts, "h2d_bytes_per_step": int(X.nbytes) * world, "d2h_bytes_per_step": d2h,
+           "what": "one job = one step: FastSK(g, m, combo_sequence=<all combinations>).compute_kernel(Xtrain, Xtest) from pinned host "
+                   "int32 (every rank uploads the sequences) + get_train_kernel / get_test_kernel into host fp64 (every rank copies its "
+                   "rows over its own PCIe link into one buffer all ranks map)"}
 
+    # ---- parity inside the run: the job's own output against the oracle ------------------------------------------------
+    parity = None
+    if rank == 0 and not args.no_parity:
+        sample = parity_sample(N_SEQ, N_TRAIN)
+        t0 = time.perf_counter()
+        ok, bad = parity_check(X, N_TRAIN, out_tr, out_te, queue, sample)
+        parity = {"parity_ok": ok, "cells": int(len(sample) * (sample < N_TRAIN).sum()), "cells_differing": bad,
+                  "what": f"normalised kernel of the e2e job at {len(sample)} sampled sequences (rows 0, n_train-1, n_train, N-1 and "
+                          f"random others) against the C oracle run on those sequences, bit-equal",
+                  "oracle_s": time.perf_counter() - t0}
     if rank != 0:
         if world > 1:
+            aimed_workload(local, dist)
             dist.destroy_process_group()
         return
-    cpu = cpu_baseline(args.cpu_budget) if (world == 1 and not args.no_cpu_baseline) else None
-    other = other_workloads(local) if world == 1 else None
-    if other is not None and not args.no_skewed:
-        other["skewed"] = skewed_workload(local)
+    cpu = same = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu, same = cpu_baseline(args.cpu_budget, local)
+    other = other_workloads(local) if world == 1 else {}
+    if other is not None:
+        if world == 1 and not args.no_skewed:
+            other["skewed"] = skewed_workload(local)
+        other["same_config"] = same
+        other["aimed_approx"] = aimed_workload(local, dist if world > 1 else None)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
-        "data": "synthetic",
-        "config": {"workload": f"synthetic DNA {N_SEQ}x{SEQ_LEN} g={G} m={M} exact (BASELINE configs[3]: 12870 combinations)",
-                   "n_train": N_TRAIN, "n_test": N_SEQ - N_TRAIN, "g": G, "m": M, "combos_per_step_per_gpu": cps, "batch": st1["batch"],
-                   "parallelism": f"combinations sharded over {world} GPU(s), one final NCCL all-reduce",
-                   "l2": "inputs larger than L2: each step streams > 10 GB (packed int64 triangle + per-slot records)",
+        "ms_per_step": ms / args.steps, "wall_s_per_build": ms * 1e-3 / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": f"synthetic DNA {N_SEQ}x{SEQ_LEN} g={G} m={M} exact, the full build (BASELINE configs[3]: {n_combos} combinations per step)",
+                   "n_train": N_TRAIN, "n_test": n_test, "g": G, "m": M, "combinations_per_step": n_combos, "batch": st1["batch"],
+                   "parallelism": f"combinations dealt round-robin to {world} GPU(s); merge: {merge}; every rank normalises 1/{world} of the rows",
+                   "l2": "inputs larger than L2: each batch streams > 10 GB (packed int64 triangle + per-slot records)",
                    "record_bytes": rec, "key_bits": st1["key_bits"], "sort_passes": st1["sort_passes"]},
-        "roofline": roofline, "roofline_sort": roofline_sort, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-        "clocks": clock_info, "phase_ms_per_step": phase_ms, "pair_updates_per_s": updates * world / (ms * 1e-3),
-        "finalize_ms": finalize_ms, "projected_full_build_s": comb(G, M) / value + finalize_ms * 1e-3,
+        "roofline": roofline, "roofline_sort": roofline_sort, "cpu_baseline": cpu, "e2e": e2e, "parity": parity,
+        "parity_ok": None if parity is None else parity["parity_ok"], "gpu_launches": launches,
+        "clocks": clock_info, "phase_ms_per_step": phase_ms, "pair_updates_per_s": updates_all / (ms * 1e-3),
+        "step_parts_ms": {"build_shard": build_ms, "merge_and_normalise": merge_norm_ms,
+                          "what": "host-timed parts of one step, max over ranks: the shard's pack/sort/segment/accumulate; then barrier + "
+                                  "normalisation of this rank's rows with the merge of all ranks' partial kernels fused into its loads + barrier"},
         "other_workloads": other,
     }
     print(json.dumps(line))
@@ -412,6 +502,47 @@ def other_workloads(device):
                 best = row
             del f
         out[tag] = best
+    prot = fasta_workload("1.1", 10, 6, device)
+    if prot is not None:
+        prot["workload"] = "protein remote homology 1.1 train+test (BASELINE configs[2]), g=10 m=6 exact, 210 combinations, 5 bits per character"
+    out["protein_1_1"] = prot
+    return out
+
+
+def fasta_workload(name, g, m, device, dist=None, **kw):
+    """One bundled FASTA set through the public API: read, compute_kernel, train kernel to the host."""
+    tr, te = os.path.join(ROOT, "data", f"{name}.train.fasta"), os.path.join(ROOT, "data", f"{name}.test.fasta")
+    if not (os.path.exists(tr) and os.path.exists(te)):
+        return None
+    from fastsk_b200 import FastSK, FastaUtility
+    fu = FastaUtility()
+    Xtr, _ = fu.read_data(tr)
+    Xte, _ = fu.read_data(te)
+    best = None
+    for _ in range(3):
+        f = FastSK(g, m, seed=0, profile=True, **({"device": device, "distributed": False} if dist is None else {}), **kw)
+        t0 = time.perf_counter()
+        f.compute_kernel(Xtr, Xte)
+        Ktr = f.get_train_kernel()
+        wall = time.perf_counter() - t0
+        st = f.stats()
+        row = {"e2e_s": wall, "device_ms": st["ms_total"], "combinations_done_this_rank": st["combos_done"],
+               "combinations_per_s_e2e_this_rank": st["combos_done"] / wall, "acc_path": st["acc_path"], "n_seq": st["n_seq"],
+               "nfeat": st["nfeat"], "key_bits": st["key_bits"], "sort_passes": st["sort_passes"], "kernel_launches": st["kernel_launches"],
+               "stdevs": len(f.get_stdevs()), "last_stdev": (f.get_stdevs() or [None])[-1], "trace": float(np.trace(Ktr))}
+        if best is None or row["e2e_s"] < best["e2e_s"]:
+            best = row
+        del f
+    return best
+
+
+def aimed_workload(device, dist=None):
+    """BASELINE configs[4]: AImed (55-letter alphabet, 6 bits per character, 60-bit keys, key/value sort), g=20 m=10, approx mode
+    with the variance / convergence test, t=20 virtual streams (dealt over the ranks under torchrun), seed 0, at most 50 iterations
+    per stream.  COLLECTIVE when dist is given."""
+    out = fasta_workload("AImed", 20, 10, device, dist, t=20, approx=True, delta=0.025, max_iters=50)
+    if out is not None:
+        out["workload"] = "AImed train+test (BASELINE configs[4]), g=20 m=10, approx (variance on), t=20, delta=0.025, max_iters=50, seed=0"
     return out
 
 
@@ -461,10 +592,11 @@ def skewed_workload(device, combos=96):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--combos-per-step", type=int, default=384)
+    ap.add_argument("--combos", type=int, default=0, help="combinations per build (0 = all C(16,8) = 12870; smaller only for quick tests)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison after the timed region (~10 s)")
     ap.add_argument("--batch", type=int, default=0, help="combinations per launch group (0 = auto)")
     ap.add_argument("--acc-path", type=int, default=0, help="0 auto, 1 global RED, 2 shared-memory rows, 3 dense tensor-core")
     ap.add_argument("--wave", type=int, default=32, help="accumulate launch = wave x resident CTAs rows")

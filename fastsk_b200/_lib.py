@@ -13,6 +13,7 @@ c_voidpp = ctypes.POINTER(ctypes.c_void_p)
 
 FSK_OK, FSK_EINVAL, FSK_ECUDA, FSK_ENOMEM, FSK_ESTATE = 0, 1, 2, 3, 4
 FSK_DT_I64, FSK_DT_F64 = 0, 1
+FSK_IPC_HANDLE_BYTES = 64
 
 
 class FskStats(ctypes.Structure):
@@ -22,7 +23,8 @@ class FskStats(ctypes.Structure):
                                               "bits_per_char", "batch", "acc_bytes")] + \
                [(n, ctypes.c_double) for n in ("ms_pack", "ms_sort", "ms_segment", "ms_accumulate", "ms_welford",
                                                "ms_normalise", "ms_total")] + \
-               [(n, ctypes.c_int32) for n in ("acc_path", "heavy_tau")] + [("heavy_runs", ctypes.c_int64)]
+               [(n, ctypes.c_int32) for n in ("acc_path", "heavy_tau")] + [("heavy_runs", ctypes.c_int64)] + \
+               [(n, ctypes.c_int32) for n in ("n_devices", "reserved0")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -37,6 +39,17 @@ SIGNATURES = {
     "fsk_last_error": (ctypes.c_char_p, [_H]),
     "fsk_version": (ctypes.c_char_p, []),
     "fsk_set_device": (ctypes.c_int, [_H, ctypes.c_int]),
+    "fsk_set_devices": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
+    "fsk_ipc_export_partial": (ctypes.c_int, [_H, ctypes.c_void_p]),
+    "fsk_set_peer_partials": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_int]),
+    "fsk_set_peer_pointers": (ctypes.c_int, [_H, c_voidpp, ctypes.c_int]),
+    "fsk_release_peers": (ctypes.c_int, [_H]),
+    "fsk_output_rows": (ctypes.c_int, [_H, c_i64p, c_i64p, c_i64p, c_i64p]),
+    "fsk_host_alloc": (ctypes.c_int, [c_voidpp, ctypes.c_size_t]),
+    "fsk_host_free": (ctypes.c_int, [ctypes.c_void_p]),
+    "fsk_host_register": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t]),
+    "fsk_host_unregister": (ctypes.c_int, [ctypes.c_void_p]),
+    "fsk_trim_cache": (ctypes.c_int, []),
     "fsk_set_seed": (ctypes.c_int, [_H, ctypes.c_uint64]),
     "fsk_set_combo_sequence": (ctypes.c_int, [_H, c_i32p, ctypes.c_int64]),
     "fsk_set_shard": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_int]),

@@ -890,10 +890,34 @@ accumulate_global_kernel(const IdT* __restrict__ ids, size_t ids_stride, const u
 // normalisation (fastsk_kernel.cpp:96-103): out = K_ij / sqrt(K_ii * K_jj) with IEEE mul, sqrt,
 // div (bit-identical to the reference's x86-64 doubles); the diagonal formula K_ii/sqrt(K_ii*K_ii)
 // is the same expression.
+// The unnormalised kernel as the normalisation sees it: the SUM of the partial kernels of all ranks.  parts.p[r] is rank r's
+// packed triangle -- this GPU's own buffer, or a peer's HBM mapped over NVLink (cudaDeviceEnablePeerAccess inside one
+// process, cudaIpcOpenMemHandle between the processes of a torchrun launch).  The reduction of the partial kernels
+// (fastsk_kernel.cpp:285-315: the mutex-striped merge) is therefore FUSED into the normalisation: every cell crosses NVLink
+// once, as an operand load of the kernel that consumes it, and no reduced copy of K is ever written.  Integer partials add
+// exactly; fp64 partials (variance mode) are added in rank order on every rank.
+constexpr int MAX_PEERS = 16;
 template <typename T>
-__global__ void diag_kernel(const T* __restrict__ K, int64_t n, double* __restrict__ diag) {
+struct PeerParts {
+    const T* p[MAX_PEERS];
+    int n;
+};
+template <typename T>
+__device__ __forceinline__ double peer_sum(const PeerParts<T>& parts, int64_t idx) {
+    if (std::is_same<T, double>::value) {
+        double s = (double)parts.p[0][idx];
+        for (int r = 1; r < parts.n; ++r) s = __dadd_rn(s, (double)parts.p[r][idx]);
+        return s;
+    }
+    unsigned long long s = (unsigned long long)parts.p[0][idx];
+    for (int r = 1; r < parts.n; ++r) s += (unsigned long long)parts.p[r][idx];
+    return (double)s;
+}
+
+template <typename T>
+__global__ void diag_kernel(const __grid_constant__ PeerParts<T> parts, int64_t n, double* __restrict__ diag) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) diag[i] = (double)K[(i * (i + 1) >> 1) + i];
+    if (i < n) diag[i] = peer_sum(parts, (i * (i + 1) >> 1) + i);
 }
 
 __device__ __forceinline__ double norm_entry(double v, double di, double dj) {
@@ -905,7 +929,7 @@ __device__ __forceinline__ double norm_entry(double v, double di, double dj) {
 // packed triangle is always read along its contiguous direction.
 template <typename T>
 __global__ void __launch_bounds__(256)
-normalise_block_kernel(const T* __restrict__ K, const double* __restrict__ diag, int64_t r0, int64_t nr, int64_t nc,
+normalise_block_kernel(const __grid_constant__ PeerParts<T> parts, const double* __restrict__ diag, int64_t r0, int64_t nr, int64_t nc,
                        double* __restrict__ out) {
     __shared__ double tile[32][33];
     const int64_t ti = (int64_t)blockIdx.y * 32, tj = (int64_t)blockIdx.x * 32;   // tile origin (row offset within block, col)
@@ -916,13 +940,13 @@ normalise_block_kernel(const T* __restrict__ K, const double* __restrict__ diag,
             const int64_t i = r0 + ti + y, j = tj + tx;
             if (ti + y < nr && j < nc) {
                 const int64_t a = i >= j ? i : j, b = i >= j ? j : i;
-                out[(ti + y) * nc + j] = norm_entry((double)K[(a * (a + 1) >> 1) + b], diag[i], diag[j]);
+                out[(ti + y) * nc + j] = norm_entry(peer_sum(parts, (a * (a + 1) >> 1) + b), diag[i], diag[j]);
             }
         }
     } else {
         for (int y = ty; y < 32; y += 8) {      // read K[j][i] with threads along i (contiguous)
             const int64_t j = tj + y, i = r0 + ti + tx;
-            if (ti + tx < nr && j < nc) tile[y][tx] = norm_entry((double)K[(j * (j + 1) >> 1) + i], diag[i], diag[j]);
+            if (ti + tx < nr && j < nc) tile[y][tx] = norm_entry(peer_sum(parts, (j * (j + 1) >> 1) + i), diag[i], diag[j]);
         }
         __syncthreads();
         for (int y = ty; y < 32; y += 8) {
@@ -932,13 +956,28 @@ normalise_block_kernel(const T* __restrict__ K, const double* __restrict__ diag,
     }
 }
 
+// rows [i0, i0 + gridDim.y) of the packed triangle, normalised (out is indexed like the triangle, from row i0's first cell)
 template <typename T>
-__global__ void normalise_packed_kernel(const T* __restrict__ K, const double* __restrict__ diag, int64_t n,
+__global__ void normalise_packed_kernel(const __grid_constant__ PeerParts<T> parts, const double* __restrict__ diag, int64_t i0,
                                         double* __restrict__ out) {
-    const int64_t i = blockIdx.y;
+    const int64_t i = i0 + blockIdx.y;
+    const int64_t base0 = i0 * (i0 + 1) >> 1;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j <= i; j += (int64_t)gridDim.x * blockDim.x) {
         const int64_t p = (i * (i + 1) >> 1) + j;
-        out[p] = norm_entry((double)K[p], diag[i], diag[j]);
+        out[p - base0] = norm_entry(peer_sum(parts, p), diag[i], diag[j]);
+    }
+}
+
+// cells [c0, c0 + n) of the summed triangle, as int64 or fp64 (getters of the unnormalised kernel when K is sharded)
+template <typename T, typename O>
+__global__ void sum_parts_kernel(const __grid_constant__ PeerParts<T> parts, int64_t c0, int64_t n, O* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (std::is_same<T, double>::value || std::is_same<O, double>::value) out[i] = (O)peer_sum(parts, c0 + i);
+        else {
+            unsigned long long s = 0;
+            for (int r = 0; r < parts.n; ++r) s += (unsigned long long)parts.p[r][c0 + i];
+            out[i] = (O)s;
+        }
     }
 }
 

@@ -13,8 +13,13 @@
 #include <cstdio>
 #include <cstring>
 #include <ctime>
+#include <functional>
+#include <map>
+#include <mutex>
 #include <random>
 #include <string>
+#include <thread>
+#include <unordered_map>
 #include <vector>
 
 using namespace fsk;
@@ -45,6 +50,18 @@ struct fsk_handle {
     int device = 0, rank = 0, world = 1;
     bool have_seed = false;
     uint64_t seed = 0;
+    bool run_seed_set = false;       // in-process team: the leader draws the wall-clock seed once per upload for every member
+    uint64_t run_seed = 0;
+    // in-process multi-GPU (fsk_set_devices): team[0] is this handle, team[i] drives devices[i] from its own host thread
+    std::vector<int> devices;
+    std::vector<fsk_handle*> team;
+    fsk_handle* leader = nullptr;    // set on team members other than the leader
+    // sharded finalisation: the partial kernels of all ranks in rank order (own buffer included), and the output rows held here
+    std::vector<const void*> peer_parts;
+    std::vector<void*> ipc_opened;   // peer mappings this handle opened with cudaIpcOpenMemHandle
+    bool sharded = false;            // d_train / d_test hold only the rows [tr_r0, +tr_nr) / [te_r0, +te_nr)
+    int64_t tr_r0 = 0, tr_nr = 0, te_r0 = 0, te_nr = 0;
+    size_t train_cap = 0, test_cap = 0;
     std::vector<int32_t> user_queue;
     int opt_batch = 0;
     int opt_acc_path = 0;            // 0 auto, 1 global RED, 2 row-stationary shared memory, 3 dense tensor-core contraction
@@ -179,11 +196,68 @@ int fail(fsk_handle* h, int code, const char* fmt, ...) {
                         cudaGetErrorString(e_), __FILE__, __LINE__);                                     \
     } while (0)
 
+// Device allocations go through a process-wide cache of exact-size blocks: a handle that computes again on inputs of the same
+// shape (or a new handle doing so: every FastSK object of a benchmark loop) re-uses the ~40 GB of buffers of the previous one
+// instead of ~30 cudaFree + cudaMalloc calls, each of which synchronises the device.  Blocks are plain cudaMalloc memory
+// (CUDA IPC needs that for the peer-mapped partial kernels).  A miss that cannot be served drops the whole cache of that
+// device and retries; fsk_trim_cache() returns everything to the driver.
+struct DevCache {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void*> free_blocks;       // (device, bytes) -> block
+    std::unordered_map<void*, std::pair<int, size_t>> live;
+    size_t cached_bytes = 0;
+    void trim(int device) {                                           // device < 0: all devices (caller holds mu)
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (auto it = free_blocks.begin(); it != free_blocks.end();) {
+            if (device < 0 || it->first.first == device) {
+                cudaSetDevice(it->first.first);
+                cudaFree(it->second);
+                cached_bytes -= it->first.second;
+                it = free_blocks.erase(it);
+            } else ++it;
+        }
+        cudaSetDevice(cur);
+    }
+};
+DevCache g_cache;
+
+cudaError_t cached_malloc(void** p, size_t bytes) {
+    bytes = (bytes + 511) & ~(size_t)511;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    auto it = g_cache.free_blocks.find({dev, bytes});
+    if (it != g_cache.free_blocks.end()) {
+        *p = it->second;
+        g_cache.free_blocks.erase(it);
+        g_cache.cached_bytes -= bytes;
+        g_cache.live[*p] = {dev, bytes};
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        g_cache.trim(dev);
+        e = cudaMalloc(p, bytes);
+    }
+    if (e == cudaSuccess) g_cache.live[*p] = {dev, bytes};
+    return e;
+}
+void cached_free(void* p) {
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    auto it = g_cache.live.find(p);
+    if (it == g_cache.live.end()) { cudaFree(p); return; }
+    g_cache.free_blocks.insert({it->second, p});
+    g_cache.cached_bytes += it->second.second;
+    g_cache.live.erase(it);
+}
+
 template <typename T>
 int dev_alloc(fsk_handle* h, T** p, size_t count) {
     *p = nullptr;
     if (count == 0) count = 1;
-    CU(cudaMalloc((void**)p, count * sizeof(T)));
+    CU(cached_malloc((void**)p, count * sizeof(T)));
     return FSK_OK;
 }
 #define ALLOC(ptr, count)                                   \
@@ -194,7 +268,7 @@ int dev_alloc(fsk_handle* h, T** p, size_t count) {
 
 template <typename T>
 void dev_free(T*& p) {
-    if (p) cudaFree((void*)p);
+    if (p) cached_free((void*)p);
     p = nullptr;
 }
 
@@ -210,6 +284,11 @@ void release_device(fsk_handle* h) {
     dev_free(h->d_Kint); dev_free(h->d_Kf);
     for (auto& p : h->d_Khat) dev_free(p);
     h->d_Khat.clear();
+    for (void* q : h->ipc_opened) cudaIpcCloseMemHandle(q);
+    h->ipc_opened.clear();
+    h->peer_parts.clear();
+    h->sharded = false;
+    h->train_cap = h->test_cap = 0;
     dev_free(h->d_diag); dev_free(h->d_train); dev_free(h->d_test);
     dev_free(h->d_block_sums); dev_free(h->d_var); dev_free(h->d_wf); dev_free(h->d_counters); dev_free(h->d_flag);
     for (auto& s : h->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
@@ -616,7 +695,8 @@ int build_queue(fsk_handle* h) {
     h->queue.resize((size_t)h->ncomb);
     for (int64_t i = 0; i < h->ncomb; ++i) h->queue[(size_t)i] = (int32_t)i;
     auto rng = std::default_random_engine{};
-    rng.seed(h->have_seed ? (std::default_random_engine::result_type)h->seed : (std::default_random_engine::result_type)std::time(0));
+    const uint64_t seed = h->have_seed ? h->seed : (h->run_seed_set ? h->run_seed : (uint64_t)std::time(0));
+    rng.seed((std::default_random_engine::result_type)seed);
     std::shuffle(h->queue.begin(), h->queue.end(), rng);
     return FSK_OK;
 }
@@ -653,17 +733,38 @@ void shard_work(const fsk_handle* h, std::vector<int32_t>& out) {
     for (size_t i = (size_t)h->rank; i < work.size(); i += (size_t)h->world) out.push_back(work[i]);
 }
 
+// the partial kernels the normalisation sums: this handle's own buffer, or those of every rank (sharded finalisation)
+template <typename T>
+PeerParts<T> make_parts(const fsk_handle* h, const T* own) {
+    PeerParts<T> parts;
+    memset(&parts, 0, sizeof parts);
+    if (h->peer_parts.empty()) {
+        parts.p[0] = own;
+        parts.n = 1;
+    } else {
+        parts.n = (int)h->peer_parts.size();
+        for (int r = 0; r < parts.n; ++r) parts.p[r] = (const T*)h->peer_parts[(size_t)r];
+    }
+    return parts;
+}
+
+// normalised train rows [tr_r0, +tr_nr) and test rows [te_r0, +te_nr) of the summed partial kernels (fastsk_kernel.cpp:96-103
+// fused with the merge of the partials, :285-315); one rank alone holds all rows
 template <typename T>
 int finalize_typed(fsk_handle* h, const T* K) {
     h->ls = h->stream;
     Span sp(h, PC_NORMALISE);
-    diag_kernel<T><<<(unsigned)((h->N + 255) / 256), 256, 0, h->stream>>>(K, h->N, h->d_diag);
-    dim3 gtrain((unsigned)((h->n_train + 31) / 32), (unsigned)((h->n_train + 31) / 32));
-    normalise_block_kernel<T><<<gtrain, 256, 0, h->stream>>>(K, h->d_diag, 0, h->n_train, h->n_train, h->d_train);
-    h->launches += 2;
-    if (h->n_test > 0) {
-        dim3 gtest((unsigned)((h->n_train + 31) / 32), (unsigned)((h->n_test + 31) / 32));
-        normalise_block_kernel<T><<<gtest, 256, 0, h->stream>>>(K, h->d_diag, h->n_train, h->n_test, h->n_train, h->d_test);
+    const PeerParts<T> parts = make_parts<T>(h, K);
+    diag_kernel<T><<<(unsigned)((h->N + 255) / 256), 256, 0, h->stream>>>(parts, h->N, h->d_diag);
+    h->launches++;
+    if (h->tr_nr > 0) {
+        dim3 gtrain((unsigned)((h->n_train + 31) / 32), (unsigned)((h->tr_nr + 31) / 32));
+        normalise_block_kernel<T><<<gtrain, 256, 0, h->stream>>>(parts, h->d_diag, h->tr_r0, h->tr_nr, h->n_train, h->d_train);
+        h->launches++;
+    }
+    if (h->te_nr > 0) {
+        dim3 gtest((unsigned)((h->n_train + 31) / 32), (unsigned)((h->te_nr + 31) / 32));
+        normalise_block_kernel<T><<<gtest, 256, 0, h->stream>>>(parts, h->d_diag, h->n_train + h->te_r0, h->te_nr, h->n_train, h->d_test);
         h->launches++;
     }
     CU(cudaGetLastError());
@@ -681,6 +782,83 @@ int sort_was_unstable(fsk_handle* h, bool* bad) {
 }
 
 int build_partial_once(fsk_handle* h);
+int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int64_t n_train, int64_t n_test);
+int reset_one(fsk_handle* h);
+int accumulate_one(fsk_handle* h, const int32_t* combos, int64_t n, int sync);
+int build_one(fsk_handle* h);
+int finalize_one(fsk_handle* h);
+int sync_one(fsk_handle* h);
+void* own_part(const fsk_handle* h) { return h->variance_mode ? (void*)h->d_Kf : (void*)h->d_Kint; }
+void release_peers(fsk_handle* h) {
+    for (void* q : h->ipc_opened) cudaIpcCloseMemHandle(q);
+    h->ipc_opened.clear();
+    h->peer_parts.clear();
+}
+
+// run fn(member) for every member of the team, each from its own host thread (one thread per GPU, like the reference's one
+// std::thread per stream, fastsk_kernel.cpp:86-93); the first failure's message is copied to the leader
+int team_run(fsk_handle* h, const std::function<int(fsk_handle*)>& fn) {
+    const size_t n = h->team.size();
+    std::vector<int> rcs(n, FSK_OK);
+    std::vector<std::thread> th;
+    for (size_t i = 1; i < n; ++i) th.emplace_back([&, i] { rcs[i] = fn(h->team[i]); });
+    rcs[0] = fn(h);
+    for (auto& t : th) t.join();
+    cudaSetDevice(h->device);
+    for (size_t i = 0; i < n; ++i)
+        if (rcs[i]) {
+            if (i) h->err = "device " + std::to_string(h->team[i]->device) + ": " + h->team[i]->err;
+            return rcs[i];
+        }
+    return FSK_OK;
+}
+bool is_team(const fsk_handle* h) { return h->team.size() > 1; }
+
+void destroy_one(fsk_handle* h) {
+    cudaSetDevice(h->device);
+    release_device(h);
+    if (h->stream) {
+        if (h->pre_stream != h->stream) cudaStreamDestroy(h->pre_stream);
+        cudaStreamDestroy(h->stream);
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_pre[i]); cudaEventDestroy(h->ev_acc[i]); }
+        cudaEventDestroy(h->ev_sync);
+    }
+    if (h->ev_heavy) cudaEventDestroy(h->ev_heavy);
+    if (h->h_heavy_count) cudaFreeHost(h->h_heavy_count);
+    delete h;
+}
+
+// (re)create the team members 1 .. n-1 as copies of the leader's configuration
+void sync_team(fsk_handle* h) {
+    if (h->devices.size() < 2) {
+        for (size_t i = 1; i < h->team.size(); ++i) destroy_one(h->team[i]);
+        h->team.clear();
+        return;
+    }
+    if (h->team.empty()) h->team.push_back(h);
+    while (h->team.size() > h->devices.size()) { destroy_one(h->team.back()); h->team.pop_back(); }
+    while (h->team.size() < h->devices.size()) { h->team.push_back(new fsk_handle()); h->team.back()->leader = h; }
+    const int n = (int)h->devices.size();
+    for (int i = 0; i < n; ++i) {
+        fsk_handle* w = h->team[(size_t)i];
+        if (i > 0 && w->stream && w->device != h->devices[(size_t)i]) {   // the member moves to another GPU: start it afresh there
+            destroy_one(w);
+            h->team[(size_t)i] = w = new fsk_handle();
+            w->leader = h;
+        }
+        w->device = h->devices[(size_t)i];
+        w->rank = i; w->world = n;
+        if (i == 0) continue;
+        w->g = h->g; w->m = h->m; w->k = h->k; w->t = h->t; w->approx = h->approx; w->skip_variance = h->skip_variance;
+        w->delta = h->delta; w->max_iters = h->max_iters; w->ncomb = h->ncomb;
+        w->have_seed = h->have_seed; w->seed = h->seed; w->user_queue = h->user_queue;
+        w->opt_batch = h->opt_batch; w->opt_acc_path = h->opt_acc_path; w->safe_rank = h->safe_rank;
+        w->opt_rows_threads = h->opt_rows_threads; w->opt_overlap = h->opt_overlap; w->opt_seg_fused = h->opt_seg_fused;
+        w->opt_acc_prefetch = h->opt_acc_prefetch; w->opt_acc_unroll = h->opt_acc_unroll; w->opt_wave = h->opt_wave;
+        w->profile = h->profile; w->opt_pad = h->opt_pad; w->opt_acc_cols = h->opt_acc_cols; w->opt_heavy_tau = h->opt_heavy_tau;
+        w->opt_ids32 = h->opt_ids32; w->opt_gemm_shape = h->opt_gemm_shape; w->opt_heavy_cap = h->opt_heavy_cap;
+    }
+}
 
 }  // namespace
 
@@ -709,22 +887,56 @@ int fsk_create(fsk_handle** out, int g, int m, int t, int approx, double delta, 
 
 void fsk_destroy(fsk_handle* h) {
     if (!h) return;
-    cudaSetDevice(h->device);
-    release_device(h);
+    for (size_t i = 1; i < h->team.size(); ++i) destroy_one(h->team[i]);
+    h->team.clear();
+    destroy_one(h);
+}
+
+int fsk_set_device(fsk_handle* h, int device) {
+    if (device == h->device && h->devices.size() < 2) return FSK_OK;
+    // moving to another GPU drops what the handle holds on the old one (a second compute on the same object is allowed)
+    if (h->stream) { cudaSetDevice(h->device); release_device(h); }
     if (h->stream) {
         if (h->pre_stream != h->stream) cudaStreamDestroy(h->pre_stream);
         cudaStreamDestroy(h->stream);
         for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_pre[i]); cudaEventDestroy(h->ev_acc[i]); }
         cudaEventDestroy(h->ev_sync);
+        h->stream = h->pre_stream = h->ls = nullptr;
     }
-    if (h->ev_heavy) cudaEventDestroy(h->ev_heavy);
-    if (h->h_heavy_count) cudaFreeHost(h->h_heavy_count);
-    delete h;
+    if (h->ev_heavy) { cudaEventDestroy(h->ev_heavy); h->ev_heavy = nullptr; }
+    if (h->h_heavy_count) { cudaFreeHost(h->h_heavy_count); h->h_heavy_count = nullptr; }
+    h->device = device;
+    h->devices.clear();
+    sync_team(h);
+    return FSK_OK;
 }
 
-int fsk_set_device(fsk_handle* h, int device) {
-    if (h->uploaded) return fail(h, FSK_ESTATE, "fsk_set_device after upload");
-    h->device = device;
+// In-process multi-GPU: the reference fans one compute_kernel call out over T threads (fastsk_kernel.cpp:54-94); here one
+// call fans out over the listed GPUs, one host thread each.  devices == NULL && n == -1 means every visible GPU.
+int fsk_set_devices(fsk_handle* h, const int* devices, int n) {
+    int visible = 0;
+    if (cudaGetDeviceCount(&visible) != cudaSuccess) { cudaGetLastError(); visible = 0; }
+    std::vector<int> dev;
+    if (n == -1 && !devices) for (int i = 0; i < visible; ++i) dev.push_back(i);
+    else {
+        if (n < 1 || !devices) return fail(h, FSK_EINVAL, "fsk_set_devices needs at least one device");
+        dev.assign(devices, devices + n);
+    }
+    if ((int)dev.size() > MAX_PEERS) return fail(h, FSK_EINVAL, "at most %d devices", MAX_PEERS);
+    for (size_t i = 0; i < dev.size(); ++i) {
+        if (dev[i] < 0 || (visible && dev[i] >= visible)) return fail(h, FSK_EINVAL, "device %d is not visible (%d devices)", dev[i], visible);
+        for (size_t j = 0; j < i; ++j) if (dev[j] == dev[i]) return fail(h, FSK_EINVAL, "device %d listed twice", dev[i]);
+    }
+    if (dev.empty()) return fail(h, FSK_ECUDA, "no CUDA device is visible");
+    if (h->world > 1) return fail(h, FSK_ESTATE, "fsk_set_devices and fsk_set_shard are alternatives (one process per GPU, or one process for all)");
+    int rc = fsk_set_device(h, dev[0]);
+    if (rc) return rc;
+    if (dev.size() > 1) {
+        h->devices = dev;
+        sync_team(h);
+    } else {
+        h->rank = 0; h->world = 1;
+    }
     return FSK_OK;
 }
 int fsk_set_seed(fsk_handle* h, uint64_t seed) { h->have_seed = true; h->seed = seed; return FSK_OK; }
@@ -735,6 +947,8 @@ int fsk_set_combo_sequence(fsk_handle* h, const int32_t* combos, int64_t n) {
 }
 int fsk_set_shard(fsk_handle* h, int rank, int world) {
     if (world < 1 || rank < 0 || rank >= world) return fail(h, FSK_EINVAL, "bad shard %d of %d", rank, world);
+    if (world > MAX_PEERS) return fail(h, FSK_EINVAL, "at most %d ranks", MAX_PEERS);
+    if (is_team(h) && world > 1) return fail(h, FSK_ESTATE, "fsk_set_devices and fsk_set_shard are alternatives");
     h->rank = rank; h->world = world;
     return FSK_OK;
 }
@@ -790,7 +1004,10 @@ int fsk_set_option(fsk_handle* h, const char* key, int64_t value) {
     return FSK_OK;
 }
 
-int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int64_t n_train, int64_t n_test) {
+}  // extern "C"
+
+namespace {
+int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int64_t n_train, int64_t n_test) {
     if (!codes || !offsets) return fail(h, FSK_EINVAL, "codes/offsets is NULL");
     // the reference dereferences Xtrain[0] / Xtest[0] unconditionally (fastsk.cpp:33,41); compute_train passes no test set
     if (n_train < 1 || n_test < 0) return fail(h, FSK_EINVAL, "need at least one train sequence (n_train = %lld, n_test = %lld)", (long long)n_train, (long long)n_test);
@@ -976,7 +1193,12 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
                                    (int64_t)h->plan.npass * ((nfeat + 3071) / 3072) * RADIX * 4 + N * 4 + 4096;
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    const int64_t k_bytes = h->n_pairs * 8 * (h->variance_mode ? 3 : 1) + (int64_t)n_train * N * 8;
+    int64_t khat_streams = 0;      // variance mode: one fp64 running mean per local virtual stream (allocated by the build)
+    if (h->variance_mode) {
+        const int64_t nq = h->user_queue.empty() ? h->ncomb : (int64_t)h->user_queue.size();
+        khat_streams = (effective_streams(h, nq) + h->world - 1) / h->world;
+    }
+    const int64_t k_bytes = h->n_pairs * 8 * (h->variance_mode ? 2 + khat_streams : 1) + (int64_t)n_train * N * 8;
     int64_t Bsel = h->opt_batch > 0 ? h->opt_batch : MAX_BATCH;
     if (h->opt_batch == 0) {
         if (!h->rows_path) Bsel = std::max<int64_t>(1, (6LL << 20) / std::max<int64_t>(1, nfeat));
@@ -1141,7 +1363,7 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         ALLOC(h->d_wf, 1);
     }
     CU(cudaStreamSynchronize(h->stream));
-    cudaFree(d_codes); cudaFree(d_off); cudaFree(d_woff);
+    cached_free(d_codes); cached_free(d_off); cached_free(d_woff);
 
     h->combos_done = 0;
     for (double& v : h->ms) v = 0;
@@ -1151,9 +1373,49 @@ int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     h->uploaded = true;
     return FSK_OK;
 }
+}  // namespace
+
+extern "C" {
+
+int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int64_t n_train, int64_t n_test) {
+    if (!is_team(h)) return upload_one(h, codes, offsets, n_train, n_test);
+    // every member must work through the same combination order: the leader draws the wall-clock seed of an unseeded
+    // shuffle (fastsk_kernel.cpp:36-38) once for the whole team
+    sync_team(h);
+    const uint64_t seed = (uint64_t)std::time(0);
+    for (fsk_handle* w : h->team) { w->run_seed_set = true; w->run_seed = seed; }
+    return team_run(h, [&](fsk_handle* w) { return upload_one(w, codes, offsets, n_train, n_test); });
+}
 
 int fsk_reset_partial(fsk_handle* h) {
     if (!h->uploaded) return fail(h, FSK_ESTATE, "nothing uploaded");
+    if (is_team(h)) return team_run(h, reset_one);
+    return reset_one(h);
+}
+
+int fsk_accumulate_combos(fsk_handle* h, const int32_t* combos, int64_t n, int sync) {
+    if (!h->uploaded) return fail(h, FSK_ESTATE, "nothing uploaded");
+    if (h->variance_mode) return fail(h, FSK_ESTATE, "fsk_accumulate_combos needs an integer mode (exact or skip_variance)");
+    if (n < 0 || (n > 0 && !combos)) return fail(h, FSK_EINVAL, "bad combination list");
+    if (!is_team(h)) return accumulate_one(h, combos, n, sync);
+    const int64_t G = (int64_t)h->team.size();      // dealt round-robin, like shard_work
+    return team_run(h, [&](fsk_handle* w) {
+        std::vector<int32_t> mine;
+        for (int64_t i = w->rank; i < n; i += G) mine.push_back(combos[i]);
+        return accumulate_one(w, mine.data(), (int64_t)mine.size(), sync);
+    });
+}
+
+int fsk_build_partial(fsk_handle* h) {
+    if (!h->uploaded) return fail(h, FSK_ESTATE, "nothing uploaded");
+    if (is_team(h)) return team_run(h, build_one);
+    return build_one(h);
+}
+
+}  // extern "C"
+
+namespace {
+int reset_one(fsk_handle* h) {
     CU(cudaSetDevice(h->device));
     CU(cudaMemsetAsync(h->d_Kint, 0, sizeof(unsigned long long) * (size_t)h->ks_slots * h->n_pairs, h->stream));
     if (h->d_Kf) CU(cudaMemsetAsync(h->d_Kf, 0, sizeof(double) * (size_t)h->n_pairs, h->stream));
@@ -1161,9 +1423,7 @@ int fsk_reset_partial(fsk_handle* h) {
     return FSK_OK;
 }
 
-int fsk_accumulate_combos(fsk_handle* h, const int32_t* combos, int64_t n, int sync) {
-    if (!h->uploaded) return fail(h, FSK_ESTATE, "nothing uploaded");
-    if (h->variance_mode) return fail(h, FSK_ESTATE, "fsk_accumulate_combos needs an integer mode (exact or skip_variance)");
+int accumulate_one(fsk_handle* h, const int32_t* combos, int64_t n, int sync) {
     CU(cudaSetDevice(h->device));
     CU(cudaEventRecord(h->ev_sync, h->stream));
     CU(cudaStreamWaitEvent(h->pre_stream, h->ev_sync, 0));
@@ -1181,8 +1441,7 @@ int fsk_accumulate_combos(fsk_handle* h, const int32_t* combos, int64_t n, int s
     return FSK_OK;
 }
 
-int fsk_build_partial(fsk_handle* h) {
-    if (!h->uploaded) return fail(h, FSK_ESTATE, "nothing uploaded");
+int build_one(fsk_handle* h) {
     CU(cudaSetDevice(h->device));
     for (int attempt = 0;; ++attempt) {
         int rc = build_partial_once(h);
@@ -1200,11 +1459,8 @@ int fsk_build_partial(fsk_handle* h) {
     return FSK_OK;
 }
 
-}  // extern "C"
-
-namespace {
 int build_partial_once(fsk_handle* h) {
-    int rc = fsk_reset_partial(h);
+    int rc = reset_one(h);
     if (rc) return rc;
     h->stdevs.clear();
     const int64_t nq = (int64_t)h->queue.size();
@@ -1215,7 +1471,7 @@ int build_partial_once(fsk_handle* h) {
     if (!h->variance_mode) {
         std::vector<int32_t> mine;
         shard_work(h, mine);
-        rc = fsk_accumulate_combos(h, mine.data(), (int64_t)mine.size(), 0);
+        rc = accumulate_one(h, mine.data(), (int64_t)mine.size(), 0);
         if (rc) return rc;
     } else {
         // variance mode: T independent virtual streams (fastsk_kernel.cpp:188-281), stream tid owned by rank tid % world
@@ -1307,29 +1563,137 @@ int build_partial_once(fsk_handle* h) {
     CU(cudaStreamSynchronize(h->stream));
     return FSK_OK;
 }
+
+// normalisation of the rows this handle is responsible for: all of them, or -- when the partial kernels of all ranks are
+// reachable (peer_parts) -- rank r's share of the train rows and of the test rows
+int finalize_one(fsk_handle* h) {
+    CU(cudaSetDevice(h->device));
+    const int W = (int)h->peer_parts.size();
+    h->sharded = W > 1;
+    const int64_t r = h->sharded ? h->rank : 0, w = h->sharded ? W : 1;
+    h->tr_r0 = h->n_train * r / w; h->tr_nr = h->n_train * (r + 1) / w - h->tr_r0;
+    h->te_r0 = h->n_test * r / w; h->te_nr = h->n_test * (r + 1) / w - h->te_r0;
+    if (!h->d_diag) ALLOC(h->d_diag, h->N);
+    const size_t need_tr = (size_t)h->tr_nr * h->n_train, need_te = (size_t)h->te_nr * h->n_train;
+    if (!h->d_train || need_tr > h->train_cap) { dev_free(h->d_train); ALLOC(h->d_train, need_tr); h->train_cap = need_tr; }
+    if (need_te && (!h->d_test || need_te > h->test_cap)) { dev_free(h->d_test); ALLOC(h->d_test, need_te); h->test_cap = need_te; }
+    int rc = h->variance_mode ? finalize_typed<double>(h, h->d_Kf) : finalize_typed<unsigned long long>(h, h->d_Kint);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    h->finalized = true;
+    return FSK_OK;
+}
+
+int sync_one(fsk_handle* h) {
+    if (!h->stream) return FSK_OK;
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->uploaded) {
+        bool bad = false;
+        int rc = sort_was_unstable(h, &bad);
+        if (rc) return rc;
+        if (bad) return fail(h, FSK_ECUDA, "sort verification failed: records out of order after the optimistic ranking; set option safe_rank = 1");
+    }
+    return FSK_OK;
+}
 }  // namespace
 
 extern "C" {
 
 int fsk_partial_buffer(fsk_handle* h, void** dev_ptr, int64_t* n_elems, int* dtype) {
     if (!h->uploaded) return fail(h, FSK_ESTATE, "nothing uploaded");
-    if (dev_ptr) *dev_ptr = h->variance_mode ? (void*)h->d_Kf : (void*)h->d_Kint;
+    if (dev_ptr) *dev_ptr = own_part(h);
     if (n_elems) *n_elems = h->n_pairs;
     if (dtype) *dtype = h->variance_mode ? FSK_DT_F64 : FSK_DT_I64;
     return FSK_OK;
 }
 
+/* ---- sharded finalisation between the processes of a torchrun launch: CUDA IPC over NVLink --------------------------- */
+
+int fsk_ipc_export_partial(fsk_handle* h, void* handle_out) {
+    if (!h->uploaded) return fail(h, FSK_ESTATE, "nothing uploaded");
+    if (!handle_out) return fail(h, FSK_EINVAL, "handle_out is NULL");
+    static_assert(sizeof(cudaIpcMemHandle_t) == FSK_IPC_HANDLE_BYTES, "FSK_IPC_HANDLE_BYTES");
+    CU(cudaSetDevice(h->device));
+    cudaIpcMemHandle_t mh;
+    CU(cudaIpcGetMemHandle(&mh, own_part(h)));
+    memcpy(handle_out, &mh, sizeof mh);
+    return FSK_OK;
+}
+
+int fsk_set_peer_partials(fsk_handle* h, const void* handles, int world) {
+    if (!h->uploaded) return fail(h, FSK_ESTATE, "nothing uploaded");
+    if (is_team(h)) return fail(h, FSK_ESTATE, "a team of in-process devices exchanges its partial kernels by itself");
+    if (world != h->world || !handles) return fail(h, FSK_EINVAL, "need the handles of all %d ranks", h->world);
+    CU(cudaSetDevice(h->device));
+    release_peers(h);
+    h->peer_parts.assign((size_t)world, nullptr);
+    for (int r = 0; r < world; ++r) {
+        if (r == h->rank) { h->peer_parts[(size_t)r] = own_part(h); continue; }
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, (const char*)handles + (size_t)r * FSK_IPC_HANDLE_BYTES, sizeof mh);
+        void* q = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&q, mh, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            release_peers(h);
+            return fail(h, FSK_ECUDA, "cudaIpcOpenMemHandle of rank %d's partial kernel failed: %s", r, cudaGetErrorString(e));
+        }
+        h->ipc_opened.push_back(q);
+        h->peer_parts[(size_t)r] = q;
+    }
+    return FSK_OK;
+}
+
+int fsk_set_peer_pointers(fsk_handle* h, void* const* parts, int world) {
+    if (!h->uploaded) return fail(h, FSK_ESTATE, "nothing uploaded");
+    if (is_team(h)) return fail(h, FSK_ESTATE, "a team of in-process devices exchanges its partial kernels by itself");
+    if (world != h->world || !parts) return fail(h, FSK_EINVAL, "need the partial buffers of all %d ranks", h->world);
+    CU(cudaSetDevice(h->device));
+    release_peers(h);
+    for (int r = 0; r < world; ++r) {
+        if (!parts[r]) { h->peer_parts.clear(); return fail(h, FSK_EINVAL, "partial buffer of rank %d is NULL", r); }
+        h->peer_parts.push_back(r == h->rank ? own_part(h) : parts[r]);
+    }
+    return FSK_OK;
+}
+
+int fsk_release_peers(fsk_handle* h) {
+    if (h->stream) CU(cudaSetDevice(h->device));
+    if (!is_team(h)) release_peers(h);
+    return FSK_OK;
+}
+
+int fsk_output_rows(fsk_handle* h, int64_t* train_r0, int64_t* train_nr, int64_t* test_r0, int64_t* test_nr) {
+    if (!h->finalized) return fail(h, FSK_ESTATE, "no kernel computed yet");
+    if (train_r0) *train_r0 = h->tr_r0;
+    if (train_nr) *train_nr = is_team(h) ? h->n_train : h->tr_nr;
+    if (test_r0) *test_r0 = h->te_r0;
+    if (test_nr) *test_nr = is_team(h) ? h->n_test : h->te_nr;
+    return FSK_OK;
+}
+
 int fsk_finalize(fsk_handle* h) {
     if (!h->uploaded) return fail(h, FSK_ESTATE, "nothing uploaded");
-    CU(cudaSetDevice(h->device));
-    if (!h->d_diag) ALLOC(h->d_diag, h->N);
-    if (!h->d_train) ALLOC(h->d_train, (size_t)h->n_train * h->n_train);
-    if (!h->d_test && h->n_test > 0) ALLOC(h->d_test, (size_t)h->n_test * h->n_train);
-    int rc = h->variance_mode ? finalize_typed<double>(h, h->d_Kf) : finalize_typed<unsigned long long>(h, h->d_Kint);
-    if (rc) return rc;
-    CU(cudaStreamSynchronize(h->stream));
-    h->finalized = true;
-    return FSK_OK;
+    if (!is_team(h)) return finalize_one(h);
+    // every member normalises its rows of the outputs, reading the partial kernels of all members over NVLink
+    for (fsk_handle* w : h->team) {
+        cudaSetDevice(w->device);
+        for (fsk_handle* o : h->team) {
+            if (o == w) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, w->device, o->device);
+            if (!can) { cudaSetDevice(h->device); return fail(h, FSK_ECUDA, "device %d cannot access device %d's memory", w->device, o->device); }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaSetDevice(h->device); return fail(h, FSK_ECUDA, "cudaDeviceEnablePeerAccess failed: %s", cudaGetErrorString(e)); }
+            cudaGetLastError();
+        }
+    }
+    for (fsk_handle* w : h->team) {
+        w->peer_parts.clear();
+        for (fsk_handle* o : h->team) w->peer_parts.push_back(own_part(o));
+    }
+    return team_run(h, finalize_one);
 }
 
 int fsk_compute(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int64_t n_train, int64_t n_test) {
@@ -1347,15 +1711,8 @@ int fsk_stream(fsk_handle* h, void** cuda_stream) {
 }
 int fsk_synchronize(fsk_handle* h) {
     if (!h->stream) return FSK_OK;
-    CU(cudaSetDevice(h->device));
-    CU(cudaStreamSynchronize(h->stream));
-    if (h->uploaded) {
-        bool bad = false;
-        int rc = sort_was_unstable(h, &bad);
-        if (rc) return rc;
-        if (bad) return fail(h, FSK_ECUDA, "sort verification failed: records out of order after the optimistic ranking; set option safe_rank = 1");
-    }
-    return FSK_OK;
+    if (is_team(h)) return team_run(h, sync_one);
+    return sync_one(h);
 }
 
 int fsk_shape(fsk_handle* h, int64_t* n_train, int64_t* n_test, int64_t* nfeat, int64_t* n_combos) {
@@ -1372,61 +1729,126 @@ int fsk_shape(fsk_handle* h, int64_t* n_train, int64_t* n_test, int64_t* nfeat, 
         CU(cudaSetDevice(h->device));                                                      \
     } while (0)
 
+// `out` is always the FULL row-major matrix; a handle that holds only some rows (sharded finalisation) fills those rows
 int fsk_get_train_kernel(fsk_handle* h, double* out) {
-    NEED_FINAL();
-    CU(cudaMemcpyAsync(out, h->d_train, sizeof(double) * (size_t)h->n_train * h->n_train, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    return FSK_OK;
+    if (!h->finalized) return fail(h, FSK_ESTATE, "no kernel computed yet");
+    auto one = [out](fsk_handle* w) -> int {
+        fsk_handle* h = w;
+        CU(cudaSetDevice(h->device));
+        if (h->tr_nr == 0) return FSK_OK;
+        CU(cudaMemcpyAsync(out + (size_t)h->tr_r0 * h->n_train, h->d_train, sizeof(double) * (size_t)h->tr_nr * h->n_train, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        return FSK_OK;
+    };
+    return is_team(h) ? team_run(h, one) : one(h);
 }
 int fsk_get_test_kernel(fsk_handle* h, double* out) {
-    NEED_FINAL();
-    if (h->n_test == 0) return FSK_OK;
-    CU(cudaMemcpyAsync(out, h->d_test, sizeof(double) * (size_t)h->n_test * h->n_train, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    return FSK_OK;
+    if (!h->finalized) return fail(h, FSK_ESTATE, "no kernel computed yet");
+    auto one = [out](fsk_handle* w) -> int {
+        fsk_handle* h = w;
+        CU(cudaSetDevice(h->device));
+        if (h->te_nr == 0) return FSK_OK;
+        CU(cudaMemcpyAsync(out + (size_t)h->te_r0 * h->n_train, h->d_test, sizeof(double) * (size_t)h->te_nr * h->n_train, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        return FSK_OK;
+    };
+    return is_team(h) ? team_run(h, one) : one(h);
 }
+// device-resident outputs of THIS handle: all rows, or the rows fsk_output_rows names after a sharded finalisation
 int fsk_train_kernel_device(fsk_handle* h, void** dev_ptr) { NEED_FINAL(); *dev_ptr = h->d_train; return FSK_OK; }
 int fsk_test_kernel_device(fsk_handle* h, void** dev_ptr) { NEED_FINAL(); *dev_ptr = h->d_test; return FSK_OK; }
 
+// The three getters below see the SUM of the partial kernels this handle can reach: its own buffer, or every rank's while
+// the peers are mapped (a team always; the processes of a torchrun launch between fsk_set_peer_partials and
+// fsk_release_peers).  They stage through a bounded device buffer, so nothing of the triangle's size is allocated.
 int fsk_get_kernel_packed(fsk_handle* h, double* out) {
     NEED_FINAL();
-    double* d_packed;
-    ALLOC(d_packed, h->n_pairs);
-    dim3 grid((unsigned)std::min<int64_t>((h->N + 255) / 256, 64), (unsigned)h->N);
-    if (h->variance_mode) normalise_packed_kernel<double><<<grid, 256, 0, h->stream>>>(h->d_Kf, h->d_diag, h->N, d_packed);
-    else normalise_packed_kernel<unsigned long long><<<grid, 256, 0, h->stream>>>(h->d_Kint, h->d_diag, h->N, d_packed);
-    h->launches++;
-    cudaError_t e = cudaMemcpyAsync(out, d_packed, sizeof(double) * (size_t)h->n_pairs, cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(d_packed);
-    if (e != cudaSuccess) return fail(h, FSK_ECUDA, "packed kernel copy failed: %s", cudaGetErrorString(e));
-    return FSK_OK;
+    const int64_t rows_per = std::max<int64_t>(1, std::min<int64_t>(h->N, (64LL << 20) / std::max<int64_t>(1, h->N)));
+    double* d_stage;
+    ALLOC(d_stage, (size_t)rows_per * h->N);
+    int rc = FSK_OK;
+    for (int64_t i0 = 0; i0 < h->N && rc == FSK_OK; i0 += rows_per) {
+        const int64_t nr = std::min(rows_per, h->N - i0);
+        const int64_t c0 = i0 * (i0 + 1) / 2, c1 = (i0 + nr) * (i0 + nr + 1) / 2;
+        dim3 grid((unsigned)std::min<int64_t>((h->N + 255) / 256, 64), (unsigned)nr);
+        if (h->variance_mode) normalise_packed_kernel<double><<<grid, 256, 0, h->stream>>>(make_parts<double>(h, h->d_Kf), h->d_diag, i0, d_stage);
+        else normalise_packed_kernel<unsigned long long><<<grid, 256, 0, h->stream>>>(make_parts<unsigned long long>(h, h->d_Kint), h->d_diag, i0, d_stage);
+        h->launches++;
+        cudaError_t e = cudaMemcpyAsync(out + c0, d_stage, sizeof(double) * (size_t)(c1 - c0), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(h, FSK_ECUDA, "packed kernel copy failed: %s", cudaGetErrorString(e));
+    }
+    cached_free(d_stage);
+    return rc;
 }
+
+}  // extern "C"
+namespace {
+template <typename T, typename O>
+int get_summed(fsk_handle* h, const T* own, O* out) {
+    CU(cudaSetDevice(h->device));
+    if (h->peer_parts.empty() && std::is_same<T, O>::value) {
+        CU(cudaMemcpyAsync(out, own, sizeof(O) * (size_t)h->n_pairs, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        return FSK_OK;
+    }
+    const int64_t chunk = std::min<int64_t>(h->n_pairs, 32LL << 20);
+    O* d_stage;
+    ALLOC(d_stage, (size_t)chunk);
+    int rc = FSK_OK;
+    for (int64_t c0 = 0; c0 < h->n_pairs && rc == FSK_OK; c0 += chunk) {
+        const int64_t n = std::min(chunk, h->n_pairs - c0);
+        sum_parts_kernel<T, O><<<592, 256, 0, h->stream>>>(make_parts<T>(h, own), c0, n, d_stage);
+        h->launches++;
+        cudaError_t e = cudaMemcpyAsync(out + c0, d_stage, sizeof(O) * (size_t)n, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(h, FSK_ECUDA, "unnormalised kernel copy failed: %s", cudaGetErrorString(e));
+    }
+    cached_free(d_stage);
+    return rc;
+}
+}  // namespace
+extern "C" {
 
 int fsk_get_unnormalised_i64(fsk_handle* h, int64_t* out) {
     if (!h->uploaded) return fail(h, FSK_ESTATE, "nothing uploaded");
     if (h->variance_mode) return fail(h, FSK_ESTATE, "the integer kernel exists only in the exact and skip_variance modes");
-    CU(cudaSetDevice(h->device));
-    CU(cudaMemcpyAsync(out, h->d_Kint, sizeof(int64_t) * (size_t)h->n_pairs, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    return FSK_OK;
+    return get_summed<unsigned long long, long long>(h, h->d_Kint, (long long*)out);
 }
 int fsk_get_unnormalised_f64(fsk_handle* h, double* out) {
     if (!h->uploaded) return fail(h, FSK_ESTATE, "nothing uploaded");
-    CU(cudaSetDevice(h->device));
-    if (h->variance_mode) {
-        CU(cudaMemcpyAsync(out, h->d_Kf, sizeof(double) * (size_t)h->n_pairs, cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        return FSK_OK;
-    }
-    double* d_tmp;
-    ALLOC(d_tmp, h->n_pairs);
-    to_f64_kernel<unsigned long long><<<592, 256, 0, h->stream>>>(h->d_Kint, d_tmp, h->n_pairs);
-    h->launches++;
-    cudaError_t e = cudaMemcpyAsync(out, d_tmp, sizeof(double) * (size_t)h->n_pairs, cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(d_tmp);
-    if (e != cudaSuccess) return fail(h, FSK_ECUDA, "unnormalised kernel copy failed: %s", cudaGetErrorString(e));
+    if (h->variance_mode) return get_summed<double, double>(h, h->d_Kf, out);
+    return get_summed<unsigned long long, double>(h, h->d_Kint, out);
+}
+
+/* pinned host memory for inputs and outputs (the getters and fsk_compute then run at PCIe speed, and -- in a team -- every
+ * GPU copies its rows over its own link at the same time); no torch needed */
+int fsk_host_alloc(void** out, size_t bytes) {
+    if (!out) return FSK_EINVAL;
+    *out = nullptr;
+    const cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); g_create_error = std::string("cudaHostAlloc failed: ") + cudaGetErrorString(e); return e == cudaErrorMemoryAllocation ? FSK_ENOMEM : FSK_ECUDA; }
+    return FSK_OK;
+}
+int fsk_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+    return FSK_OK;
+}
+/* make an existing host range (e.g. a shared-memory mapping all ranks write their rows into) DMA-able */
+int fsk_host_register(void* p, size_t bytes) {
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess && e != cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); g_create_error = std::string("cudaHostRegister failed: ") + cudaGetErrorString(e); return FSK_ECUDA; }
+    cudaGetLastError();
+    return FSK_OK;
+}
+int fsk_host_unregister(void* p) {
+    cudaHostUnregister(p);
+    cudaGetLastError();
+    return FSK_OK;
+}
+int fsk_trim_cache(void) {
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    g_cache.trim(-1);
     return FSK_OK;
 }
 
@@ -1461,20 +1883,30 @@ int fsk_get_shard_work(fsk_handle* h, int32_t* out, int64_t cap, int64_t* n) {
 int fsk_save_kernel(fsk_handle* h, const char* path) {
     NEED_FINAL();
     if (!path || !*path) return FSK_OK;   // fastsk.cpp:226: empty file name is a no-op
-    std::vector<double> K((size_t)h->n_pairs);
-    int rc = fsk_get_kernel_packed(h, K.data());
-    if (rc) return rc;
     FILE* f = fopen(path, "w");
     if (!f) return fail(h, FSK_EINVAL, "cannot open %s for writing", path);
-    for (int64_t i = 0; i < h->N; ++i) {
-        for (int64_t j = 0; j < h->N; ++j) {
-            const int64_t a = std::max(i, j), bb = std::min(i, j);
-            fprintf(f, "%d:%e ", (int)(j + 1), K[(size_t)(a * (a + 1) / 2 + bb)]);
+    // blocks of full rows of the square matrix, normalised on the device: nothing of the triangle's size on the host
+    const int64_t rows_per = std::max<int64_t>(1, std::min<int64_t>(h->N, (32LL << 20) / std::max<int64_t>(1, h->N)));
+    std::vector<double> rows((size_t)rows_per * h->N);
+    double* d_stage = nullptr;
+    int rc = dev_alloc(h, &d_stage, (size_t)rows_per * h->N);
+    for (int64_t i0 = 0; i0 < h->N && rc == FSK_OK; i0 += rows_per) {
+        const int64_t nr = std::min(rows_per, h->N - i0);
+        dim3 grid((unsigned)((h->N + 31) / 32), (unsigned)((nr + 31) / 32));
+        if (h->variance_mode) normalise_block_kernel<double><<<grid, 256, 0, h->stream>>>(make_parts<double>(h, h->d_Kf), h->d_diag, i0, nr, h->N, d_stage);
+        else normalise_block_kernel<unsigned long long><<<grid, 256, 0, h->stream>>>(make_parts<unsigned long long>(h, h->d_Kint), h->d_diag, i0, nr, h->N, d_stage);
+        h->launches++;
+        cudaError_t e = cudaMemcpyAsync(rows.data(), d_stage, sizeof(double) * (size_t)nr * h->N, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) { rc = fail(h, FSK_ECUDA, "kernel rows copy failed: %s", cudaGetErrorString(e)); break; }
+        for (int64_t i = 0; i < nr; ++i) {
+            for (int64_t j = 0; j < h->N; ++j) fprintf(f, "%d:%e ", (int)(j + 1), rows[(size_t)(i * h->N + j)]);
+            fprintf(f, "\n");
         }
-        fprintf(f, "\n");
     }
+    if (d_stage) cached_free(d_stage);
     fclose(f);
-    return FSK_OK;
+    return rc;
 }
 
 int fsk_get_stats(fsk_handle* h, fsk_stats* out) {
@@ -1497,6 +1929,20 @@ int fsk_get_stats(fsk_handle* h, fsk_stats* out) {
     out->ms_pack = h->ms[PC_PACK]; out->ms_sort = h->ms[PC_SORT]; out->ms_segment = h->ms[PC_SEGMENT];
     out->ms_accumulate = h->ms[PC_ACCUMULATE]; out->ms_welford = h->ms[PC_WELFORD]; out->ms_normalise = h->ms[PC_NORMALISE];
     for (int i = 0; i < PC_COUNT; ++i) out->ms_total += h->ms[i];
+    out->n_devices = is_team(h) ? (int32_t)h->team.size() : 1;
+    // a team: counts add up over the members, times are the slowest member's
+    for (size_t i = 1; !h->leader && i < h->team.size(); ++i) {
+        fsk_stats o;
+        int rc = fsk_get_stats(h->team[i], &o);
+        if (rc) { h->err = h->team[i]->err; return rc; }
+        out->combos_done += o.combos_done; out->kernel_launches += o.kernel_launches; out->entries += o.entries;
+        out->runs += o.runs; out->pair_updates += o.pair_updates; out->heavy_runs += o.heavy_runs;
+        out->ms_pack = std::max(out->ms_pack, o.ms_pack); out->ms_sort = std::max(out->ms_sort, o.ms_sort);
+        out->ms_segment = std::max(out->ms_segment, o.ms_segment); out->ms_accumulate = std::max(out->ms_accumulate, o.ms_accumulate);
+        out->ms_welford = std::max(out->ms_welford, o.ms_welford); out->ms_normalise = std::max(out->ms_normalise, o.ms_normalise);
+        out->ms_total = std::max(out->ms_total, o.ms_total);
+    }
+    if (h->stream) cudaSetDevice(h->device);
     return FSK_OK;
 }
 

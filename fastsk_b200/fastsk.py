@@ -3,9 +3,15 @@
 Same constructor (positional order g, m, t, approx, delta, max_iters, skip_variance --
 bindings.cpp:14-22), same method names (bindings.cpp:23-44).  The work is done by the CUDA
 library behind include/fastsk_b200.h, called through ctypes; this file only flattens the
-inputs, forwards calls and, when launched under torchrun, sums the per-GPU partial kernels with
-one NCCL all-reduce.  If the CUDA extension is missing or no B200 is visible the calls raise;
-there is no CPU path.
+inputs and forwards calls.  Multi-GPU comes in two forms, both without a CPU path:
+  * a plain script: ``FastSK(...)`` drives every visible GPU from one process (``devices="auto"``; the
+    library runs one host thread per GPU -- fsk_set_devices -- like the reference runs one std::thread per
+    stream, fastsk_kernel.cpp:54-94); torch is not needed;
+  * under torchrun (one process per GPU): every rank builds the partial kernel of its shard, the ranks
+    exchange CUDA IPC handles of their partial buffers through torch.distributed, and every rank
+    normalises its share of the output rows, summing all partials over NVLink as it reads them
+    (``reduce="peer"``); ``reduce="allreduce"`` is the plain NCCL form (every rank ends with everything).
+If the CUDA extension is missing or no B200 is visible the calls raise.
 
 Deliberate deviations from the reference:
   * getters return NumPy arrays (``.tolist()`` gives the reference's list of lists) -- a Python
@@ -55,9 +61,80 @@ class _DeviceArray:
         self._owner = owner
 
 
+def pinned_empty(shape, dtype=np.float64):
+    """Page-locked host array owned by the library (cudaHostAlloc): getters and compute_kernel move it at PCIe speed,
+    and a team of GPUs fills / reads it over all their links at once.  Freed when the array is garbage-collected."""
+    lib = _lib.load()
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape))
+    ptr = ctypes.c_void_p()
+    rc = lib.fsk_host_alloc(ctypes.byref(ptr), max(1, n * dt.itemsize))
+    _lib.check(lib, None, rc)
+    buf = (ctypes.c_char * max(1, n * dt.itemsize)).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dt, count=n).reshape(shape)
+    import weakref
+    weakref.finalize(buf, lib.fsk_host_free, ptr.value)
+    return arr
+
+
+_BIG_OUTPUT = 64 << 20      # outputs at least this large are allocated pinned
+_SHM_KEEP = []              # shared-memory segments stay mapped for the life of the process (arrays may outlive any object)
+
+
+def shard_rows(n, rank, world):
+    """Rows [r0, r0 + nr) of an n-row output that rank `rank` of `world` normalises and holds (fsk_finalize, sharded)."""
+    r0 = n * rank // world
+    return r0, n * (rank + 1) // world - r0
+
+
+def shared_output(rows, cols, dist=None):
+    """COLLECTIVE over the ranks of a torchrun launch: a rows x cols float64 array in POSIX shared memory that every
+    rank maps, with this rank's share of the rows (shard_rows) page-locked.  Pass it as ``out=`` to get_train_kernel /
+    get_test_kernel: every rank then copies its rows over its own PCIe link and all ranks see the whole matrix.
+    Creating it touches every page, so create it once and re-use it across computes."""
+    from multiprocessing import shared_memory
+    if dist is None:
+        import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    nbytes = max(8, int(rows) * int(cols) * 8)
+    box = [None]
+    shm = None
+    if rank == 0:
+        try:
+            shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            box = [shm.name]
+        except OSError as e:
+            box = ["!" + str(e)]
+    dist.broadcast_object_list(box, src=0)
+    if box[0].startswith("!"):
+        raise MemoryError("cannot create %d bytes of shared memory for the kernel matrix: %s" % (nbytes, box[0][1:]))
+    if rank != 0:
+        shm = shared_memory.SharedMemory(name=box[0])
+        try:                                    # the creator owns the segment: this process's tracker must not unlink it
+            from multiprocessing import resource_tracker
+            resource_tracker.unregister(shm._name, "shared_memory")
+        except Exception:
+            pass
+    arr = np.ndarray((rows, cols), dtype=np.float64, buffer=shm.buf)
+    dist.barrier()
+    if rank == 0:
+        shm.unlink()                            # the mappings stay valid; nothing is left behind in /dev/shm
+    r0, nr = shard_rows(rows, rank, world)
+    if nr:
+        lib = _lib.load()
+        base = arr.ctypes.data
+        lo = (base + r0 * cols * 8) & ~4095
+        hi = min((base + (r0 + nr) * cols * 8 + 4095) & ~4095, (base + shm.size + 4095) & ~4095)
+        lib.fsk_host_register(ctypes.c_void_p(lo), hi - lo)      # best effort: an unpinned range still works, only slower
+    _SHM_KEEP.append(shm)
+    dist.barrier()
+    return arr
+
+
 class FastSK:
     def __init__(self, g, m, t=-1, approx=False, delta=0.025, max_iters=-1, skip_variance=False, *,
-                 seed=None, combo_sequence=None, device=None, distributed="auto", profile=False):
+                 seed=None, combo_sequence=None, device=None, devices="auto", distributed="auto", reduce="peer",
+                 profile=False):
         self._lib = _lib.load()
         self._h = ctypes.c_void_p()
         rc = self._lib.fsk_create(ctypes.byref(self._h), int(g), int(m), int(t), int(bool(approx)), float(delta),
@@ -66,8 +143,15 @@ class FastSK:
         self.g, self.m, self.t = int(g), int(m), int(t)
         self.approx, self.delta, self.max_iters, self.skip_variance = bool(approx), float(delta), int(max_iters), bool(skip_variance)
         self._distributed = distributed
+        if reduce not in ("peer", "allreduce"):
+            raise ValueError("reduce must be 'peer' or 'allreduce'")
+        self._reduce = reduce
+        self._devices = devices if device is None else None      # an explicit device pins the handle to that GPU
+        self._sharded = False       # outputs are row slices of this rank (torchrun + peer finalisation)
+        self._shm = []
         self._labels = (None, None)
         self._clf = None
+        self._seed, self._combo_sequence = seed, combo_sequence
         if seed is not None:
             self._call("fsk_set_seed", int(seed))
         if combo_sequence is not None:
@@ -117,29 +201,103 @@ class FastSK:
         codes, offsets = _flatten(Xtrain)
         self._compute_flat(codes, offsets, len(offsets) - 1, 0)
 
+    # combinations x windows above which a plain script fans out over every visible GPU (below it one GPU finishes in
+    # milliseconds and seven more uploads would only add latency)
+    _TEAM_WORK = 1 << 31
+
+    def _pick_devices(self, n_windows):
+        """In-process team of GPUs for a plain (non-torchrun) call."""
+        dev = self._devices
+        if dev is None:
+            return
+        if isinstance(dev, str):
+            if dev not in ("auto", "all"):
+                raise ValueError("devices must be 'auto', 'all' or a list of CUDA ordinals")
+            if dev == "auto":
+                n_comb = len(self.get_queue()) if not self.approx else max(1, self.max_iters) * (20 if self.t == -1 else self.t)
+                if n_comb * max(1, n_windows) < self._TEAM_WORK:
+                    return
+            rc = self._lib.fsk_set_devices(self._h, None, -1)
+            if rc == _lib.FSK_ECUDA:          # no device visible: the compute call reports it
+                return
+            _lib.check(self._lib, self._h, rc)
+        else:
+            arr = (ctypes.c_int * len(dev))(*[int(d) for d in dev])
+            self._call("fsk_set_devices", arr, len(dev))
+
     def _compute_flat(self, codes, offsets, n_train, n_test):
         self._clf = None
+        self._sharded = False
         rank, world, dist = self._dist()
         cp, op = codes.ctypes.data_as(c_i32p), offsets.ctypes.data_as(c_i64p)
         if dist is None:
+            self._pick_devices(len(codes))
             self._call("fsk_compute", cp, op, n_train, n_test)
             return
         # one process per GPU: every rank builds the partial kernel of its shard of the combinations
-        # (virtual streams in variance mode); one NCCL all-reduce over NVLink combines them.
+        # (virtual streams in variance mode)
         import torch
-        if dist.get_backend() == "nccl":
+        nccl = dist.get_backend() == "nccl"
+        if nccl:
             self._call("fsk_set_device", torch.cuda.current_device())
+        self._agree_on_queue(dist, rank)
+        self._call("fsk_release_peers")
         self._call("fsk_set_shard", rank, world)
         self._call("fsk_upload", cp, op, n_train, n_test)
         self._call("fsk_build_partial")
+        if nccl and self._reduce == "peer" and self._exchange_peers(dist, world):
+            dist.barrier()                      # every rank's partial is complete before anybody reads it
+            self._call("fsk_finalize")          # this rank's rows, summing all partials over NVLink
+            dist.barrier()                      # nobody resets its partial while a peer still reads it
+            if not self._keep_peers:
+                self._call("fsk_release_peers")
+            self._sharded = True
+            return
         self.reduce_partial(self.partial_tensor(), dist)
         torch.cuda.current_stream().synchronize()
         self._call("fsk_finalize")
 
+    def _agree_on_queue(self, dist, rank):
+        """The ranks must walk ONE shuffled queue (their shards are slices of it): without seed= or combo_sequence=, rank 0
+        draws the wall-clock seed the reference would use (fastsk_kernel.cpp:36-38) and every rank takes it."""
+        if self._seed is None and self._combo_sequence is None:
+            import time
+            box = [int(time.time()) if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            self._call("fsk_set_seed", box[0])
+
+    _keep_peers = False     # tests: keep the peers mapped so that get_unnormalised() sees the summed kernel
+
+    def _exchange_peers(self, dist, world):
+        """CUDA IPC handles of all ranks' partial buffers -> fsk_set_peer_partials.  False (on every rank) if any rank
+        could not map its peers; the caller then falls back to the NCCL all-reduce."""
+        import torch
+        buf = ctypes.create_string_buffer(_lib.FSK_IPC_HANDLE_BYTES)
+        ok = 1
+        try:
+            self._call("fsk_ipc_export_partial", buf)
+        except RuntimeError:
+            ok = 0
+        mine = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
+        allh = torch.empty(world * _lib.FSK_IPC_HANDLE_BYTES, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(allh, mine)
+        if ok:
+            raw = bytes(allh.cpu().numpy().tobytes())
+            try:
+                self._call("fsk_set_peer_partials", raw, world)
+            except RuntimeError:
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            self._call("fsk_release_peers")
+            return False
+        return True
+
     @staticmethod
     def reduce_partial(part, dist):
-        """The one collective of the path: sum the ranks' partial kernels in place (int64 in the integer
-        modes, float64 running means in variance mode).  NCCL over NVLink on the GPU box, gloo in CPU tests."""
+        """The plain-collective form of the merge (``reduce="allreduce"``, and the gloo CPU tests): sum the ranks' partial
+        kernels in place (int64 in the integer modes, float64 running means in variance mode)."""
         dist.all_reduce(part, op=dist.ReduceOp.SUM)
         return part
 
@@ -167,21 +325,40 @@ class FastSK:
         self._call("fsk_shape", ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d))
         return a.value, b.value, c.value, d.value
 
+    def output_rows(self):
+        """(train_r0, train_nr, test_r0, test_nr): the rows of the two kernels this rank holds on its device (all rows
+        unless the finalisation was sharded over the ranks of a torchrun launch)."""
+        v = [ctypes.c_int64() for _ in range(4)]
+        self._call("fsk_output_rows", *[ctypes.byref(x) for x in v])
+        return tuple(x.value for x in v)
+
+    def _get_kernel(self, fn, rows, out):
+        n_train = self._shape()[0]
+        if not self._sharded:
+            if out is None:
+                nbytes = rows * n_train * 8
+                out = pinned_empty((rows, n_train)) if nbytes >= _BIG_OUTPUT else np.empty((rows, n_train), dtype=np.float64)
+            self._call(fn, out.ctypes.data_as(c_f64p))
+            return out
+        # torchrun, sharded finalisation: every rank copies ITS rows, over its own PCIe link, into one buffer all ranks
+        # share (POSIX shared memory created here, or the caller's `out` if all ranks were given the same memory)
+        rank, world, dist = self._dist()
+        if out is None:
+            out = self._shared_empty((rows, n_train), dist, rank)
+        self._call(fn, out.ctypes.data_as(c_f64p))
+        dist.barrier()
+        return out
+
+    def _shared_empty(self, shape, dist, rank):
+        return shared_output(shape[0], shape[1], dist)
+
     def get_train_kernel(self, out=None):
         """bindings.cpp:32 / fastsk.cpp:190-200: n_train x n_train (float64 ndarray)."""
-        n_train, _, _, _ = self._shape()
-        if out is None:
-            out = np.empty((n_train, n_train), dtype=np.float64)
-        self._call("fsk_get_train_kernel", out.ctypes.data_as(c_f64p))
-        return out
+        return self._get_kernel("fsk_get_train_kernel", self._shape()[0], out)
 
     def get_test_kernel(self, out=None):
         """bindings.cpp:33 / fastsk.cpp:202-217: n_test x n_train (float64 ndarray)."""
-        n_train, n_test, _, _ = self._shape()
-        if out is None:
-            out = np.empty((n_test, n_train), dtype=np.float64)
-        self._call("fsk_get_test_kernel", out.ctypes.data_as(c_f64p))
-        return out
+        return self._get_kernel("fsk_get_test_kernel", self._shape()[1], out)
 
     def get_stdevs(self):
         """bindings.cpp:34 / fastsk.cpp:219-221."""
@@ -278,7 +455,7 @@ class FastSK:
             raise ValueError("score needs the test labels: score(..., Ytest=...) or set_labels(Ytrain, Ytest)")
         K = self.get_test_kernel()
         if metric == "accuracy":
-            return float(self._clf.score(K, self._labels[1]))
+            return 100.0 * float(self._clf.score(K, self._labels[1]))      # a percentage, like fastsk.cpp:505,529
         from sklearn.metrics import roc_auc_score
         pos = list(self._clf.classes_).index(1) if 1 in self._clf.classes_ else -1
         return float(roc_auc_score(self._labels[1], self._clf.predict_proba(K)[:, pos]))

@@ -14,6 +14,11 @@ from __future__ import annotations
 import numpy as np
 
 
+# ASCII bytes str.strip() removes (the reference strips every line, utils.py:50-96): a file holding any of them inside its
+# sequence lines goes to the record parser
+_STRIPPED = (9, 11, 12, 13, 28, 29, 30, 31, 32)
+
+
 class Vocabulary(object):
     """Maps tokens to integer ids (first-seen order, 0 reserved for "unknown")."""
 
@@ -137,14 +142,14 @@ class FastaUtility:
                 table[ord(tok)] = k
         known = table.copy()
         uniq, first = np.unique(lower[seq[:65536]], return_index=True)     # first-seen order: the head settles almost all
-        pending = [int(v) for v in uniq[np.argsort(first)] if v < 128 and v not in (9, 11, 12, 13, 32) and known[v] < 0]
+        pending = [int(v) for v in uniq[np.argsort(first)] if v < 128 and v not in _STRIPPED and known[v] < 0]
         next_id = self._vocab.size()
         for v in pending:
             known[v] = next_id
             next_id += 1
         table = known[lower]
         table[128:] = -2
-        table[[9, 11, 12, 13, 32]] = -2
+        table[list(_STRIPPED)] = -2
         codes = table[seq]
         lo = int(codes.min()) if codes.size else 0
         if lo == -2:

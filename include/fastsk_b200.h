@@ -18,6 +18,7 @@
 #ifndef FASTSK_B200_H
 #define FASTSK_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -50,7 +51,14 @@ const char* fsk_version(void);
 
 /* ---- configuration (before fsk_compute / fsk_upload) ------------------------------------ */
 
-int fsk_set_device(fsk_handle* h, int device);              /* CUDA ordinal; default 0 */
+int fsk_set_device(fsk_handle* h, int device);              /* CUDA ordinal; default 0; may be called again later (moves the handle) */
+/* In-process multi-GPU: one fsk_compute call fans out over `n` GPUs, one host thread per GPU -- the reference fans one
+ * compute_kernel call out over T std::threads (fastsk_kernel.cpp:54-94).  The combinations (integer modes) or virtual
+ * streams (variance mode) are dealt round-robin to the devices; the partial kernels are merged (fastsk_kernel.cpp:285-315)
+ * inside the normalisation kernel, which reads every peer's partial over NVLink; every device normalises its share of the
+ * output rows and the getters copy all shares to the host at the same time, each over its own PCIe link.
+ * devices == NULL with n == -1 selects every visible GPU.  No NCCL, no torch.  Alternative to fsk_set_shard. */
+int fsk_set_devices(fsk_handle* h, const int* devices, int n);
 /* The reference shuffles the C(g,m) combinations with std::default_random_engine seeded by
  * time(0) (fastsk_kernel.cpp:31-47).  Same libstdc++ calls here, with an injectable seed ...  */
 int fsk_set_seed(fsk_handle* h, uint64_t seed);
@@ -61,6 +69,23 @@ int fsk_set_combo_sequence(fsk_handle* h, const int32_t* combos, int64_t n);
  * virtual streams in the variance mode).  Default 0 of 1.  The caller sums the partial
  * buffers of all ranks (one NCCL reduction) between fsk_build_partial and fsk_finalize. */
 int fsk_set_shard(fsk_handle* h, int rank, int world);
+/* One process per GPU (torchrun): after fsk_build_partial every rank exports its partial kernel (a CUDA IPC handle of
+ * FSK_IPC_HANDLE_BYTES bytes), the caller gathers the handles of all ranks (any transport: torch.distributed, MPI, a file),
+ * fsk_set_peer_partials maps the other ranks' buffers over NVLink, and -- after a barrier: every rank's build must be
+ * complete -- fsk_finalize then normalises only this rank's share of the output rows (fsk_output_rows), summing the partial
+ * kernels of all ranks as it reads them: the merge of fastsk_kernel.cpp:285-315 fused into the normalisation, no reduced
+ * copy of K, no collective library.  fsk_release_peers unmaps (also done by the next upload and by fsk_destroy); a rank
+ * must not upload again or be destroyed while another rank still reads its partial (barrier first). */
+#define FSK_IPC_HANDLE_BYTES 64
+int fsk_ipc_export_partial(fsk_handle* h, void* handle_out);
+int fsk_set_peer_partials(fsk_handle* h, const void* handles /* world x FSK_IPC_HANDLE_BYTES, rank order */, int world);
+/* the same for handles that live in ONE process (the caller's own threads, or two shards on one GPU): plain device pointers
+ * from fsk_partial_buffer, peer access already enabled by the caller where the devices differ */
+int fsk_set_peer_pointers(fsk_handle* h, void* const* parts /* world pointers, rank order */, int world);
+int fsk_release_peers(fsk_handle* h);
+/* rows of the train / test kernels this handle holds after fsk_finalize (all of them unless the finalisation was sharded;
+ * a team of in-process devices reports all rows: its getters collect every member's share) */
+int fsk_output_rows(fsk_handle* h, int64_t* train_r0, int64_t* train_nr, int64_t* test_r0, int64_t* test_nr);
 /* tuning / diagnostics: "batch" (combinations per launch group, 0 = auto), "profile" (1 = time
  * every kernel class with CUDA events and count entries / runs / pair updates), "acc_path" (0 = auto,
  * 1 = global RED on the packed triangle, 2 = row-stationary shared-memory accumulate, 3 = dense regime:
@@ -98,7 +123,9 @@ int fsk_synchronize(fsk_handle* h);
 /* ---- results ------------------------------------------------------------------------------ */
 
 int fsk_shape(fsk_handle* h, int64_t* n_train, int64_t* n_test, int64_t* nfeat, int64_t* n_combos);
-/* FastSK::get_train_kernel -- fastsk.cpp:190-200: n_train x n_train row-major fp64 */
+/* FastSK::get_train_kernel -- fastsk.cpp:190-200: n_train x n_train row-major fp64.  `out` is always the full matrix; a
+ * handle whose finalisation was sharded writes only its rows (fsk_output_rows) -- ranks that share one host buffer
+ * (shared memory) fill it together, each over its own PCIe link. */
 int fsk_get_train_kernel(fsk_handle* h, double* out);
 /* FastSK::get_test_kernel -- fastsk.cpp:202-217: n_test x n_train row-major fp64 */
 int fsk_get_test_kernel(fsk_handle* h, double* out);
@@ -122,6 +149,16 @@ int fsk_get_queue(fsk_handle* h, int32_t* out, int64_t cap, int64_t* n);
  * stream ids in the variance mode.  Needs no device. */
 int fsk_get_shard_work(fsk_handle* h, int32_t* out, int64_t cap, int64_t* n);
 
+/* ---- host memory, device memory ----------------------------------------------------------- */
+
+/* pinned host buffers for inputs / outputs (DMA at PCIe speed), registration of an existing range (e.g. shared memory),
+ * and release of the library's process-wide cache of device blocks (buffers are re-used across computes and handles) */
+int fsk_host_alloc(void** out, size_t bytes);
+int fsk_host_free(void* p);
+int fsk_host_register(void* p, size_t bytes);
+int fsk_host_unregister(void* p);
+int fsk_trim_cache(void);
+
 /* ---- statistics --------------------------------------------------------------------------- */
 
 typedef struct fsk_stats {
@@ -140,6 +177,8 @@ typedef struct fsk_stats {
      * contraction; heavy_runs counts them since upload (pair_updates then counts the row path's share only) */
     int32_t heavy_tau;
     int64_t heavy_runs;
+    int32_t n_devices;          /* GPUs driven by this handle (fsk_set_devices); counts above add up over them, times are the slowest's */
+    int32_t reserved0;
 } fsk_stats;
 int fsk_get_stats(fsk_handle* h, fsk_stats* out);
 

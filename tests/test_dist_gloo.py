@@ -98,3 +98,28 @@ def test_shard_work_partitions_the_queue():
     f = FastSK(9, 4, -1, True, combo_sequence=q, distributed=False)
     f.set_shard(1, 8)
     assert f.get_shard_work().tolist() == [1, 9, 17]
+
+
+def _seed_worker(rank, world, port, out_dir):
+    import sys, time
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch.distributed as dist
+    from fastsk_b200 import FastSK
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        time.sleep(1.2 * rank)                    # the ranks reach the call in different wall-clock seconds
+        f = FastSK(8, 4)                          # no seed=, no combo_sequence=
+        f._agree_on_queue(dist, rank)
+        f.set_shard(rank, world)
+        np.save(os.path.join(out_dir, f"work{rank}.npy"), f.get_shard_work())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_unseeded_ranks_agree_on_one_queue(tmp_path):
+    """without seed= the ranks used to shuffle with their own time(0); the shards were not a partition."""
+    import torch.multiprocessing as mp
+    mp.spawn(_seed_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    w0, w1 = np.load(tmp_path / "work0.npy"), np.load(tmp_path / "work1.npy")
+    assert sorted(np.concatenate([w0, w1]).tolist()) == list(range(comb(8, 4)))

@@ -164,3 +164,28 @@ def test_flatten_accepts_lists_arrays_and_flat_pairs():
     assert c.tolist() == list(range(6)) and o.tolist() == [0, 3, 6]
     c2, o2 = _flatten((c, o))
     assert c2 is c or c2.tolist() == c.tolist()
+
+
+def test_read_encoded_falls_back_for_every_byte_strip_removes(tmp_path):
+    """str.strip() also removes \\x1c-\\x1f; the vectorised reader must hand such files to the record parser."""
+    from fastsk_b200 import FastaUtility
+    p = tmp_path / "odd.fasta"
+    p.write_bytes(b">1\nAC\x1cGT\x1c\n>0\nGGTA\n")
+    a, b = FastaUtility(), FastaUtility()
+    X, Y = a.read_data(str(p))
+    codes, offsets, labels = b.read_encoded(str(p))
+    assert [codes[offsets[i]:offsets[i + 1]].tolist() for i in range(len(offsets) - 1)] == X
+    assert list(labels) == list(Y)
+
+
+def test_set_devices_validation_and_team_options():
+    """fsk_set_devices needs no device to validate its list; it excludes fsk_set_shard."""
+    from fastsk_b200 import FastSK, _lib
+    import ctypes
+    f = FastSK(8, 4)
+    lib = f._lib
+    arr = (ctypes.c_int * 2)(0, 0)
+    assert lib.fsk_set_devices(f._h, arr, 2) == _lib.FSK_EINVAL          # listed twice
+    assert lib.fsk_set_devices(f._h, None, 0) == _lib.FSK_EINVAL
+    st = f.stats()
+    assert st["n_devices"] == 1
