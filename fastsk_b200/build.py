@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfastsk_b200.so")
 SOURCES = [os.path.join(HERE, "csrc", "fsk_lib.cu")]
-DEPS = SOURCES + [os.path.join(HERE, "csrc", "fsk_kernels.cuh"), os.path.join(HERE, "csrc", "fsk_dense.cuh"), os.path.join(HERE, "csrc", "fsk_bucket.cuh"),
+DEPS = SOURCES + [os.path.join(HERE, "csrc", "fsk_kernels.cuh"), os.path.join(HERE, "csrc", "fsk_dense.cuh"), os.path.join(HERE, "csrc", "fsk_bucket.cuh"), os.path.join(HERE, "csrc", "fsk_segment.cuh"),
                   os.path.join(os.path.dirname(HERE), "include", "fastsk_b200.h")]
 
 NVCC_FLAGS = [

@@ -133,7 +133,8 @@ template <typename RecT, bool KV, typename GwT, int NW>
 __global__ void __launch_bounds__(256)
 pack_hist_kernel(const GwT* __restrict__ gw0, const uint64_t* __restrict__ gw1, const uint32_t* __restrict__ wseq,
                  uint32_t nfeat, RecT* __restrict__ rec, uint32_t* __restrict__ val, uint32_t* __restrict__ ghist,
-                 const __grid_constant__ BatchSpec spec, const __grid_constant__ SortPlan plan, int idbits) {
+                 const __grid_constant__ BatchSpec spec, const __grid_constant__ SortPlan plan, int idbits,
+                 uint16_t* __restrict__ wkey /* directory form of the segmentation: the key of every window, in window order */) {
     // a 32-bit g-mer word holds a key of at most 32 bits: keep the arithmetic in 32 bits then
     using KeyT = typename std::conditional<sizeof(GwT) == 4, uint32_t, uint64_t>::type;
     constexpr uint32_t KB = sizeof(KeyT) * 8;
@@ -190,6 +191,7 @@ pack_hist_kernel(const GwT* __restrict__ gw0, const uint64_t* __restrict__ gw1, 
                 } else {
                     rec[sbase + w] = ((RecT)key[i] << idbits) | (RecT)seq[i];
                 }
+                if (wkey) wkey[sbase + w] = (uint16_t)key[i];
             }
         }
         for (int p = 0; p < npass; ++p) {
@@ -398,7 +400,16 @@ struct RecOps {
     static __device__ __forceinline__ bool key_less(RecT a, RecT b, int idbits) { return KV ? a < b : (a >> idbits) < (b >> idbits); }
 };
 
-template <typename RecT, bool KV, typename IdT, bool HEAVY = false, int ROWS = SEG_ROWS_DEFAULT, int MINB = (sizeof(RecT) == 4 ? 3 : 2)>
+//
+// DIRECTORY FORM (DIR = true; key spaces of at most 2^16 k-mers, where every k-mer has a slot of its own): nothing is filed
+// per record -- no atomic, no scattered task store.  The rows of K are cut into blocks of 2^bshift sequences, and the LAST
+// record of every (run, block) group writes ONE entry tdir[block][key] = (run start, records of the run up to the end of
+// this block).  The row CTA of sequence b then finds the task of each of its windows by itself: key of the window
+// (pack_hist_kernel's wkey) -> tdir[b >> bshift][key].  The prefix it reads may run past b's own group to the end of b's
+// block; those ids are larger than b and fall into the dump words like every other id beyond the row.  Entries per slot:
+// (run, block) pairs, ~0.22 per record on the headline workload, against one atomic + one 8-byte scatter per record.
+template <typename RecT, bool KV, typename IdT, bool HEAVY = false, int ROWS = SEG_ROWS_DEFAULT, int MINB = (sizeof(RecT) == 4 ? 3 : 2),
+          bool DIR = false, bool DIRSTATS = false>
 __global__ void __launch_bounds__(SEG_THREADS, MINB)
 segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, uint32_t n, uint32_t tiles_per_slot,
                size_t ids_stride, int idbits, uint32_t nseq, int unit_shift, uint32_t pad_mask, uint32_t* __restrict__ fill,
@@ -408,8 +419,10 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
                uint32_t heavy_tau /* 0 = off: runs longer than this may leave the sparse path */, uint32_t* __restrict__ heavy_count,
                uint2* __restrict__ heavy_list /* (slot, first sorted record) of every heavy run of the batch */, uint32_t heavy_cap,
                uint32_t* __restrict__ heavy_bits /* [slot][units / 32]: bit set = the run starting at that id unit is in the list */,
-               size_t heavy_bits_stride) {
+               size_t heavy_bits_stride, uint2* __restrict__ tdir = nullptr /* [slot][block][key] */, int dir_bshift = 0,
+               uint32_t dir_nb = 0, int dir_keybits = 0) {
     using Ops = RecOps<RecT, KV>;
+    constexpr bool NEED_LEN = !DIR || DIRSTATS;
     constexpr int SEG_ROWS = ROWS;
     constexpr int SEG_WARP_RECS = SEG_ROWS * 32;
     constexpr int SEG_TILE = seg_tile_records(ROWS);
@@ -442,10 +455,11 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
     RecT r_before = 0, r_after = 0;
     uint32_t s_before = 0, s_after = 0;
     const uint32_t seg_end = live ? min(seg0 + SEG_WARP_RECS, n) : seg0;   // exclusive
-    if (live && seg0 > 0) { r_before = R[seg0 - 1]; if (KV) s_before = V[seg0 - 1]; }
-    if (live && seg_end < n) { r_after = R[seg_end]; if (KV) s_after = V[seg_end]; }
+    if (live && seg0 > 0) { r_before = R[seg0 - 1]; s_before = KV ? V[seg0 - 1] : (uint32_t)(r_before & idmask); }
+    if (live && seg_end < n) { r_after = R[seg_end]; s_after = KV ? V[seg_end] : (uint32_t)(r_after & idmask); }
 
-    uint32_t hm[SEG_ROWS], tm[SEG_ROWS], rtm[SEG_ROWS];   // run-head / group-tail / run-tail ballots (warp-uniform)
+    uint32_t hm[SEG_ROWS], tm[NEED_LEN ? SEG_ROWS : 1], rtm[SEG_ROWS];   // run-head / group-tail / run-tail ballots (warp-uniform)
+    uint32_t btm[DIR ? SEG_ROWS : 1];                     // DIR: last record of its (run, block of sequences) group
     uint32_t n_groups = 0;
 #pragma unroll
     for (int k = 0; k < SEG_ROWS; ++k) {
@@ -469,9 +483,10 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
         // the sort must have left the records non-decreasing (key, then sequence id): see onesweep_kernel
         if (valid && i > 0 && (KV ? (pr > r[k] || (pr == r[k] && ps > sq[k])) : pr > r[k])) *unsorted_flag = 1u;
         hm[k] = __ballot_sync(0xffffffffu, head);
-        tm[k] = __ballot_sync(0xffffffffu, tail);
+        if (NEED_LEN) tm[k] = __ballot_sync(0xffffffffu, tail);
         rtm[k] = __ballot_sync(0xffffffffu, rtail);
-        n_groups += __popc(__ballot_sync(0xffffffffu, ghead));
+        if (DIR) btm[k] = __ballot_sync(0xffffffffu, rtail || (valid && (ns >> dir_bshift) != (sq[k] >> dir_bshift)));
+        if (NEED_LEN) n_groups += __popc(__ballot_sync(0xffffffffu, ghead));
     }
 
     // run start of the segment's first record when its run began before the segment: walk back in blocks of 32
@@ -502,8 +517,8 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
     }
 
     // first group tail at or after each record, scanning the rows backwards
-    uint32_t ge[SEG_ROWS];
-    {
+    uint32_t ge[NEED_LEN ? SEG_ROWS : 1];
+    if (NEED_LEN) {
         uint32_t next_tail = 0xffffffffu;   // first tail in the rows after row k (warp-uniform)
         const uint32_t lane_ge = 0xffffffffu << lane;
 #pragma unroll
@@ -517,7 +532,7 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
     // run start and prefix length of every record; a group that runs past the warp's segment is followed in
     // global memory (rare)
     unsigned long long updates = 0;
-    uint32_t rs[SEG_ROWS], len[SEG_ROWS];
+    uint32_t rs[SEG_ROWS], len[NEED_LEN ? SEG_ROWS : 1];
     {
         uint32_t last_head = carry_head;
         const uint32_t lane_le = 0xffffffffu >> (31 - lane);
@@ -527,9 +542,9 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
             const uint32_t m = hm[k] & lane_le;
             rs[k] = m ? base + (31 - __clz(m)) : last_head;
             if (hm[k]) last_head = base + (31 - __clz(hm[k]));
-            len[k] = ge[k] - rs[k] + 1;           // garbage where ge is unknown or the record is out of range: fixed below
+            if (NEED_LEN) len[k] = ge[k] - rs[k] + 1;           // garbage where ge is unknown or the record is out of range: fixed below
         }
-        if (__any_sync(0xffffffffu, ge[SEG_ROWS - 1] == 0xffffffffu && seg0 + (SEG_ROWS - 1) * 32 + lane < n)) {
+        if (NEED_LEN && __any_sync(0xffffffffu, ge[SEG_ROWS - 1] == 0xffffffffu && seg0 + (SEG_ROWS - 1) * 32 + lane < n)) {
 #pragma unroll
             for (int k = 0; k < SEG_ROWS; ++k) {
                 const uint32_t i = seg0 + k * 32 + lane;
@@ -579,13 +594,15 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
     uint32_t base = 0;
 #pragma unroll
     for (int h0 = 0; h0 < SEG_ROWS; h0 += HALF) {
-        uint32_t pos[HALF];                      // fill[] starts at woff[seq]: the atomic returns the task's address
+        uint32_t pos[DIR ? 1 : HALF];            // fill[] starts at woff[seq]: the atomic returns the task's address
+        if (!DIR) {
 #pragma unroll
-        for (int k = 0; k < HALF; ++k) {
-            const uint32_t i = seg0 + (h0 + k) * 32 + lane;
-            pos[k] = 0;
-            if (i < n) {
-                pos[k] = atomicAdd(&fill[(size_t)slot * nseq + sq[h0 + k]], 1u);
+            for (int k = 0; k < HALF; ++k) {
+                const uint32_t i = seg0 + (h0 + k) * 32 + lane;
+                pos[k] = 0;
+                if (i < n) {
+                    pos[k] = atomicAdd(&fill[(size_t)slot * nseq + sq[h0 + k]], 1u);
+                }
             }
         }
         if (h0 == 0) {
@@ -620,14 +637,15 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
             if (i < n) {
                 const uint32_t X = base + xs[h0 + k];
                 ids[(size_t)slot * ids_stride + X + (i - rs[h0 + k])] = (IdT)sq[h0 + k];
-                uint32_t ln = len[h0 + k];
+                const bool writes = !DIR || ((btm[DIR ? h0 + k : 0] >> lane) & 1u);      // DIR: one entry per (run, block) group
+                uint32_t ln = DIR ? i - rs[h0 + k] + 1 : len[NEED_LEN ? h0 + k : 0];
                 if (HEAVY && heavy_tau) {                  // (compiled out of the variant launched while the stage sleeps)
                     // a run of more than heavy_tau records is a (nearly) dense column of the count matrix: its d^2/2 updates go to
                     // the tensor-core contraction (heavy_fill_kernel + syrk_tc_kernel) if the batch's list has room, and then the
                     // accumulate skips its tasks.  The records are sorted, so the run is that long iff the record heavy_tau places
                     // after its start has the same key.
                     const uint32_t far = rs[h0 + k] + heavy_tau;
-                    if (far < n && Ops::same_key(R[far], r[h0 + k], idbits)) {
+                    if ((writes || i == rs[h0 + k]) && far < n && Ops::same_key(R[far], r[h0 + k], idbits)) {
                         ln |= 0x80000000u;                       // "ask heavy_bits": only the run's first record knows whether the list had room
                         if (i == rs[h0 + k]) {
                             const uint32_t at = atomicAdd(heavy_count, 1u);
@@ -639,12 +657,20 @@ segment_kernel(const RecT* __restrict__ rec, const uint32_t* __restrict__ val, u
                         }
                     }
                 }
-                task[sbase + pos[k]] = make_uint2(X >> unit_shift, ln);
-                updates += ln & 0x7fffffffu;
+                if (DIR) {
+                    if (writes) {
+                        const uint32_t key = (uint32_t)(r[h0 + k] >> idbits);
+                        tdir[(((size_t)slot * dir_nb + (sq[h0 + k] >> dir_bshift)) << dir_keybits) + key] = make_uint2(X >> unit_shift, ln);
+                    }
+                    if (DIRSTATS) updates += len[NEED_LEN ? h0 + k : 0];
+                } else {
+                    task[sbase + pos[k]] = make_uint2(X >> unit_shift, ln);
+                    updates += ln & 0x7fffffffu;
+                }
             }
         }
     }
-    if (stat_counters) {
+    if (NEED_LEN && stat_counters) {
         uint32_t n_runs = 0;
 #pragma unroll
         for (int k = 0; k < SEG_ROWS; ++k) n_runs += __popc(hm[k]);
@@ -711,12 +737,22 @@ __device__ __forceinline__ void apply_unit(uint32_t* row, const uint4 v, const u
 // +slots_per_group) add into the same K.  The host launches the rows in waves of a few CTAs per SM, longest
 // rows first.
 constexpr uint32_t PF_STRIDE = 128, PF_LINES = 3, PF_SKIP = 0, PF_REACH = 4096;     // one prefetch per 128-byte line, reach 384 bytes of ids (PF_SKIP = 48, not prefetching a line the range barely enters, measured 179.6 against 171.4 ms)
-template <typename AccT, typename IdT, int UNROLL, bool PREFETCH = true>
+// DIR: the tasks come from the run directory of segment_kernel's directory form: task of window t of row b in slot s =
+// tdir[s][b >> bshift][wkey[s][window]] (two dependent loads, the first coalesced, the second a hit in L2: the rows of
+// one launch belong to one or two blocks, so they all read the same 2^keybits x 8-byte column of each slot).
+struct DirSpec {
+    const uint16_t* wkey;        // [slot][window]
+    const uint2* tdir;           // [slot][block][key]
+    int bshift, keybits;
+    uint32_t nb;
+};
+template <typename AccT, typename IdT, int UNROLL, bool PREFETCH = true, bool DIR = false>
 __global__ void __launch_bounds__(1024)
 accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uint2* __restrict__ task,
                        const uint32_t* __restrict__ woff, uint32_t n, uint32_t row_hi, int slots_per_group,
                        AccT* __restrict__ K, size_t k_group_stride, const WelfordSpec* __restrict__ wf, uint32_t col0,
-                       uint32_t col_width, uint32_t sums_off, const uint32_t* __restrict__ heavy_bits, size_t heavy_bits_stride) {
+                       uint32_t col_width, uint32_t sums_off, const uint32_t* __restrict__ heavy_bits, size_t heavy_bits_stride,
+                       const DirSpec dir) {
     constexpr int PER = 16 / sizeof(IdT);
     constexpr int SH = PER == 8 ? 3 : 2;
     extern __shared__ uint32_t row[];
@@ -735,7 +771,10 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
     __syncthreads();
     const uint32_t lane_le = 0xffffffffu >> (31 - lane);
     const uint32_t dump = ncols + lane;                      // 32 words behind the row
-    const uint2* __restrict__ task_g = task + (size_t)group * slots_per_group * n + wb;
+    const uint2* __restrict__ task_g = DIR ? nullptr : task + (size_t)group * slots_per_group * n + wb;
+    const uint16_t* __restrict__ wkey_g = DIR ? dir.wkey + (size_t)group * slots_per_group * n + wb : nullptr;
+    const uint2* __restrict__ tdir_g = DIR ? dir.tdir + ((((size_t)group * slots_per_group) * dir.nb + (b >> dir.bshift)) << dir.keybits) : nullptr;
+    const size_t tdir_slot = DIR ? ((size_t)dir.nb << dir.keybits) : 0;
     const IdT* __restrict__ ids_g = ids + (size_t)group * slots_per_group * ids_stride;
     // chunk c -> (slot, first task); the task of this lane, or an empty one
     auto grab = [&]() -> uint32_t {
@@ -743,47 +782,65 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
         if (lane == 0) c = atomicAdd(&next_chunk, 1u);
         return __shfl_sync(0xffffffffu, c, 0);
     };
-    auto load_task = [&](uint32_t c) -> uint2 {
+    // DIR: the key of this lane's window in chunk c (0xffffffff: no window), fetched one chunk before the task itself
+    auto load_key = [&](uint32_t c) -> uint32_t {
+        uint32_t k = 0xffffffffu;
+        if (DIR && c < nchunks) {
+            const uint32_t s = c / cps;
+            const uint32_t t = ((c - s * cps) << 5) + lane;
+            if (t < nw) k = wkey_g[(size_t)s * n + t];
+        }
+        return k;
+    };
+    // the task as stored (a plain load, nothing depends on it yet) ...
+    auto load_task = [&](uint32_t c, uint32_t key) -> uint2 {
         uint2 q = make_uint2(0, 0);
         if (c < nchunks) {
             const uint32_t s = c / cps;
             const uint32_t t = ((c - s * cps) << 5) + lane;
-            if (t < nw) q = task_g[(size_t)s * n + t];
-            if (q.y >> 31) {   // long run (segment_kernel): an ordinary task unless the tensor-core contraction took the run
-                const uint32_t w = heavy_bits[((size_t)group * slots_per_group + s) * heavy_bits_stride + (q.x >> 5)];
-                q.y &= 0x7fffffffu;
-                // taken: the task must still own one unit (the expansion below hands positions to consecutive lanes, so no
-                // lane in the middle may be empty): the last unit of the slot's id stream, which is always 0xFF.. fill
-                if ((w >> (q.x & 31u)) & 1u) q = make_uint2((uint32_t)(ids_stride / PER) - 1u, 1u);
-            }
+            if (DIR) { if (key != 0xffffffffu) q = tdir_g[(size_t)s * tdir_slot + key]; }
+            else if (t < nw) q = task_g[(size_t)s * n + t];
         }
         return q;
     };
-    uint32_t c = grab();
-    uint2 q = load_task(c);
+    // ... and as applied, one chunk later: a task of a long run (segment_kernel) is an ordinary task unless the tensor-core
+    // contraction took the run
+    auto settle_task = [&](uint32_t c, uint2 q) -> uint2 {
+        if (q.y >> 31) {
+            const uint32_t s = c / cps;
+            const uint32_t w = heavy_bits[((size_t)group * slots_per_group + s) * heavy_bits_stride + (q.x >> 5)];
+            q.y &= 0x7fffffffu;
+            // taken: the task must still own one unit (the expansion below hands positions to consecutive lanes, so no
+            // lane in the middle may be empty): the last unit of the slot's id stream, which is always 0xFF.. fill
+            if ((w >> (q.x & 31u)) & 1u) q = make_uint2((uint32_t)(ids_stride / PER) - 1u, 1u);
+        }
+        return q;
+    };
+    // Software pipeline over the chunks of 32 tasks, three deep: chunk c is applied while the id ranges of c1 are pulled into
+    // L2 (its tasks were fetched a whole chunk ago, so nothing waits for them), the tasks of c2 are in flight and -- DIR --
+    // so are the keys of c3.  The kernel's stalls are memory latency (ncu: ~28 % of the samples on the first use of the id
+    // loads, 7 % on the task loads with a two-deep pipeline), and a prefetch holds no register and no scoreboard entry.
+    uint32_t c = grab(), c1 = grab(), c2 = grab();
+    uint2 q = settle_task(c, load_task(c, load_key(c)));
+    uint2 q1 = load_task(c1, load_key(c1));
+    uint32_t k2 = load_key(c2);
     while (c < nchunks) {
         const uint32_t s = c / cps;
         const uint4* __restrict__ ip = reinterpret_cast<const uint4*>(ids_g + (size_t)s * ids_stride);   // ids_stride is a multiple of 64
-        // The kernel waits mostly on the id loads (ncu: 45 % of the stall samples at their first use, DRAM at 57 % of its peak,
-        // L2 hit rate 5 %).  So the NEXT chunk's tasks are fetched now and the lines of their id ranges are pulled into L2 while
-        // this chunk is applied: a prefetch holds no register and no scoreboard entry.
-        // (one bulk prefetch of exactly the task's id range, issued after this chunk's first step so that the task loads it
-        // depends on have landed)
-        const uint32_t c_next = PREFETCH ? grab() : 0u;
-        uint2 q_next = make_uint2(0, 0);
-        if (PREFETCH) q_next = load_task(c_next);
-        auto prefetch_next = [&]() {                 // per-lane prefetches (the bulk form is warp-uniform: 32 serial issues)
-            if (q_next.y) {
-                const char* p = reinterpret_cast<const char*>(ids_g + (size_t)(c_next / cps) * ids_stride) + (size_t)q_next.x * 16;
-                const uint32_t bytes = q_next.y * (uint32_t)sizeof(IdT);
+        const uint2 q2 = load_task(c2, k2);
+        const uint32_t c3 = grab();
+        const uint32_t k3 = load_key(c3);
+        q1 = settle_task(c1, q1);
+        if (PREFETCH && q1.y) {                      // per-lane prefetches (the bulk form is warp-uniform: 32 serial issues)
+            const char* p = reinterpret_cast<const char*>(ids_g + (size_t)(c1 / cps) * ids_stride) + (size_t)q1.x * 16;
+            const uint32_t bytes = q1.y * (uint32_t)sizeof(IdT);
 #pragma unroll
-                for (uint32_t o = 0; o < PF_LINES * PF_STRIDE; o += PF_STRIDE)
-                    if (bytes > o + PF_SKIP) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
-                // long ranges (skewed inputs): up to PF_REACH bytes; the uniform workload never gets here
-                for (uint32_t o = PF_LINES * PF_STRIDE; o < min(bytes, PF_REACH); o += PF_STRIDE)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
-            }
-        };
+            for (uint32_t o = 0; o < PF_LINES * PF_STRIDE; o += PF_STRIDE)
+                if (bytes > o + PF_SKIP) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+            // long ranges (skewed inputs): up to PF_REACH bytes; the uniform workload never gets here
+            for (uint32_t o = PF_LINES * PF_STRIDE; o < min(bytes, PF_REACH); o += PF_STRIDE)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+        }
         const uint32_t my_units = (q.y + PER - 1) >> SH;
         uint32_t incl = my_units;
 #pragma unroll
@@ -813,22 +870,15 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
             for (int u = 0; u < UNROLL; ++u)
                 if (base + 32 * u + lane < W) apply_unit<IdT>(row, v[u], dump, col0);
         };
-        // (double-buffering these loads against the applies, and prefetching the next chunk's tasks, measured no gain:
-        // profiles/r01_v6_unroll_pipe_segexp_experiment.txt)
+        // (double-buffering these loads against the applies measured no gain: profiles/r01_v6_unroll_pipe_segexp_experiment.txt)
         for (uint32_t base = 0; base < W; base += 32 * UNROLL) {
             uint4 v[UNROLL];
             issue(base, v);
             apply(base, v);
-            if (PREFETCH && base == 0) prefetch_next();   // after the first step: the task loads it depends on have landed
         }
-        if (PREFETCH && W == 0) prefetch_next();          // (an empty chunk still owes the next one its prefetch)
-        if (PREFETCH) {
-            c = c_next;
-            q = q_next;
-        } else {
-            c = grab();
-            q = load_task(c);
-        }
+        c = c1; q = q1;
+        c1 = c2; q1 = q2;
+        c2 = c3; k2 = k3;
     }
     __syncthreads();
     if (wf) {

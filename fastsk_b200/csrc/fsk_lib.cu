@@ -6,8 +6,11 @@
 #include "fsk_kernels.cuh"
 #include "fsk_dense.cuh"
 #include "fsk_bucket.cuh"
+#include "fsk_segment.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -114,6 +117,18 @@ struct fsk_handle {
     int opt_pad = 0;                                   // 0 auto, 1 unit, 2 line
     bool ids16 = false;
     uint2* d_task[2] = {nullptr, nullptr};
+    // directory form of the segmentation (small key spaces): per-window keys + one task per (run, block of sequences)
+    int opt_seg_dir = 0;                               // 0 auto, 1 off, 2 on
+    int opt_dir_blocks = 32;                           // target number of row blocks (power-of-two block size)
+    bool dir_mode = false;
+    int dir_bshift = 0;
+    uint32_t dir_nb = 0;
+    uint16_t* d_wkey = nullptr;
+    uint2* d_tdir[2] = {nullptr, nullptr};
+    int opt_seg_lean = 0;                              // 0 auto (on for records that carry the id), 1 off, 2 on: register-blocked segmentation
+    bool lean_seg = false;
+    uint32_t lean_tiles = 0;
+    int opt_count_updates = 1;                         // profile: also count entries / runs / pair updates (0: spans only)
     bool rows_path = false;
     int rows_threads = 256;
     size_t rows_smem = 0;
@@ -253,6 +268,19 @@ void cached_free(void* p) {
     g_cache.live.erase(it);
 }
 
+// free device memory as the sizing decisions should see it: what the driver reports plus what this library holds in its
+// cache (a miss that does not fit drops the cache)
+cudaError_t mem_info_with_cache(size_t* free_b, size_t* total_b) {
+    cudaError_t e = cudaMemGetInfo(free_b, total_b);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    for (auto& kv : g_cache.free_blocks)
+        if (kv.first.first == dev) *free_b += kv.first.second;
+    return cudaSuccess;
+}
+
 template <typename T>
 int dev_alloc(fsk_handle* h, T** p, size_t count) {
     *p = nullptr;
@@ -280,7 +308,8 @@ void release_device(fsk_handle* h) {
     dev_free(h->d_zero);
     h->d_ghist = h->d_ticket = h->d_status = h->d_seg_status = nullptr;
     dev_free(h->d_woff32); dev_free(h->d_fill); dev_free(h->d_C); dev_free(h->d_tile_order); dev_free(h->d_pair_order); dev_free(h->d_H); dev_free(h->d_heavy_list);
-    for (int i = 0; i < 2; ++i) { dev_free(h->d_ids[i]); dev_free(h->d_task[i]); }
+    for (int i = 0; i < 2; ++i) { dev_free(h->d_ids[i]); dev_free(h->d_task[i]); dev_free(h->d_tdir[i]); }
+    dev_free(h->d_wkey);
     dev_free(h->d_Kint); dev_free(h->d_Kf);
     for (auto& p : h->d_Khat) dev_free(p);
     h->d_Khat.clear();
@@ -297,6 +326,20 @@ void release_device(fsk_handle* h) {
     h->event_pool.clear();
     h->uploaded = h->built = h->finalized = false;
 }
+
+// FSK_TRACE=1 in the environment: wall-clock milliseconds of the host-side phases on stderr
+struct Trace {
+    bool on;
+    const char* what;
+    std::chrono::steady_clock::time_point t0;
+    explicit Trace(const char* w) : on(getenv("FSK_TRACE") != nullptr), what(w), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char* phase) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[fsk] %s: %s %.3f ms\n", what, phase, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 int64_t nchoosek64(int n, int k) {   // C(n,k); the reference's int version is exact for g <= 20 (shared.cpp:335-345)
     if (k < 0 || k > n) return 0;
@@ -376,13 +419,13 @@ int launch_pack(fsk_handle* h, int nb, const BatchSpec& spec) {
     const uint32_t n = (uint32_t)h->nfeat;
     if (h->NW == 2)
         pack_hist_kernel<RecT, KV, uint64_t, 2><<<grid, 256, 0, h->ls>>>((const uint64_t*)h->d_gw0, h->d_gw1, h->d_wseq, n, rec,
-                                                                           h->d_valA, h->d_ghist, spec, h->plan, h->idbits);
+                                                                           h->d_valA, h->d_ghist, spec, h->plan, h->idbits, h->dir_mode ? h->d_wkey : nullptr);
     else if (h->gw32)
         pack_hist_kernel<RecT, KV, uint32_t, 1><<<grid, 256, 0, h->ls>>>((const uint32_t*)h->d_gw0, nullptr, h->d_wseq, n, rec,
-                                                                           h->d_valA, h->d_ghist, spec, h->plan, h->idbits);
+                                                                           h->d_valA, h->d_ghist, spec, h->plan, h->idbits, h->dir_mode ? h->d_wkey : nullptr);
     else
         pack_hist_kernel<RecT, KV, uint64_t, 1><<<grid, 256, 0, h->ls>>>((const uint64_t*)h->d_gw0, nullptr, h->d_wseq, n, rec,
-                                                                           h->d_valA, h->d_ghist, spec, h->plan, h->idbits);
+                                                                           h->d_valA, h->d_ghist, spec, h->plan, h->idbits, h->dir_mode ? h->d_wkey : nullptr);
     h->launches++;
     CU(cudaGetLastError());
     return FSK_OK;
@@ -418,9 +461,11 @@ int launch_sort(fsk_handle* h, int nb) {
 template <typename RecT, bool KV>
 int launch_segment(fsk_handle* h, int nb) {
     const uint32_t n = (uint32_t)h->nfeat;
-    unsigned long long* stat = h->profile ? h->d_counters : nullptr;
-    init_fill_kernel<<<dim3((unsigned)((h->N + 255) / 256), nb), 256, 0, h->ls>>>(h->d_fill, h->d_woff32, (uint32_t)h->N);
-    h->launches++;
+    unsigned long long* stat = (h->profile && h->opt_count_updates) ? h->d_counters : nullptr;
+    if (!h->dir_mode) {
+        init_fill_kernel<<<dim3((unsigned)((h->N + 255) / 256), nb), 256, 0, h->ls>>>(h->d_fill, h->d_woff32, (uint32_t)h->N);
+        h->launches++;
+    }
     if (h->fused_seg && !h->safe_rank) {
         if (!std::is_same<RecT, uint32_t>::value || KV) return fail(h, FSK_ESTATE, "fused segmentation needs 32-bit records");
         const int lo_bits = h->plan.bits[0], hi_bits = h->plan.bits[1];
@@ -436,6 +481,29 @@ int launch_segment(fsk_handle* h, int nb) {
         CU(cudaGetLastError());
         return FSK_OK;
     }
+    if (h->lean_seg) {
+        if (KV) return fail(h, FSK_ESTATE, "the register-blocked segmentation needs records that carry the sequence id");
+        // (writes the fill between the runs itself: no memset of the id stream)
+        const unsigned lgrid = h->lean_tiles * (unsigned)nb;
+        const int lush = h->ids16 ? 3 : 2;
+        const size_t lsmem = (size_t)lean_cap(sizeof(RecT)) * (h->ids16 ? 2 : 4);
+#define LEAN_ARGS(IDT) (const RecT*)h->d_recA, n, h->lean_tiles, h->ids_stride, h->idbits, (uint32_t)h->N, lush, h->pad_mask, h->d_fill, \
+                  (IDT*)h->d_ids[h->buf], h->d_task[h->buf], h->d_seg_status, h->d_ticket + SEG_TICKET, h->d_flag, stat, h->heavy_now, \
+                  h->d_ticket + HEAVY_COUNT, h->d_heavy_list, h->heavy_cap, h->d_heavy_bits, h->heavy_bits_stride, h->d_tdir[h->buf], \
+                  h->dir_bshift, h->dir_nb, h->keybits
+#define LEAN_GO(IDT, DR, HV, ST) segment_lean_kernel<RecT, IDT, DR, HV, ST><<<lgrid, LEAN_THREADS, lsmem, h->ls>>>(LEAN_ARGS(IDT))
+#define LEAN_HS(IDT, DR) do { if (hv) { if (stt) LEAN_GO(IDT, DR, true, true); else LEAN_GO(IDT, DR, true, false); } \
+                              else { if (stt) LEAN_GO(IDT, DR, false, true); else LEAN_GO(IDT, DR, false, false); } } while (0)
+        const bool hv = h->heavy_now != 0, stt = stat != nullptr;
+        if (h->ids16) { if (h->dir_mode) LEAN_HS(uint16_t, true); else LEAN_HS(uint16_t, false); }
+        else { if (h->dir_mode) LEAN_HS(uint32_t, true); else LEAN_HS(uint32_t, false); }
+#undef LEAN_HS
+#undef LEAN_GO
+#undef LEAN_ARGS
+        h->launches++;
+        CU(cudaGetLastError());
+        return FSK_OK;
+    }
     // the gaps between the aligned runs must read as "no sequence": 0xFF.. clamps to the dump word in the accumulate
     CU(cudaMemsetAsync(h->d_ids[h->buf], 0xff, (size_t)nb * h->ids_stride * (h->ids16 ? 2 : 4), h->ls));
     const unsigned grid = h->seg_tiles * (unsigned)nb;
@@ -443,7 +511,17 @@ int launch_segment(fsk_handle* h, int nb) {
 #define SEG_ARGS (const RecT*)h->d_recA, h->d_valA, n, h->seg_tiles, h->ids_stride, h->idbits, (uint32_t)h->N, ush, h->pad_mask, h->d_fill
 #define SEG_ARGS2 h->d_task[h->buf], h->d_seg_status, h->d_ticket + SEG_TICKET, h->d_flag, stat, h->heavy_now, \
                   h->d_ticket + HEAVY_COUNT, h->d_heavy_list, h->heavy_cap, h->d_heavy_bits, h->heavy_bits_stride
-    if (h->ids16 && h->heavy_now)
+    if (h->dir_mode) {
+        constexpr int MB = sizeof(RecT) == 4 ? 3 : 2;
+#define DIR_ARGS , h->d_tdir[h->buf], h->dir_bshift, h->dir_nb, h->keybits
+#define SEG_DIR(IDT, HV, ST) segment_kernel<RecT, false, IDT, HV, SEG_ROWS_DEFAULT, MB, true, ST><<<grid, SEG_THREADS, 0, h->ls>>>(SEG_ARGS, (IDT*)h->d_ids[h->buf], SEG_ARGS2 DIR_ARGS)
+        if (KV) return fail(h, FSK_ESTATE, "the directory form needs records that carry the sequence id");
+        const bool hv = h->heavy_now != 0, st = stat != nullptr;
+        if (h->ids16) { if (hv) { if (st) SEG_DIR(uint16_t, true, true); else SEG_DIR(uint16_t, true, false); } else { if (st) SEG_DIR(uint16_t, false, true); else SEG_DIR(uint16_t, false, false); } }
+        else { if (hv) { if (st) SEG_DIR(uint32_t, true, true); else SEG_DIR(uint32_t, true, false); } else { if (st) SEG_DIR(uint32_t, false, true); else SEG_DIR(uint32_t, false, false); } }
+#undef SEG_DIR
+#undef DIR_ARGS
+    } else if (h->ids16 && h->heavy_now)
         segment_kernel<RecT, KV, uint16_t, true><<<grid, SEG_THREADS, 0, h->ls>>>(SEG_ARGS, (uint16_t*)h->d_ids[h->buf], SEG_ARGS2);
     else if (h->ids16)
         segment_kernel<RecT, KV, uint16_t, false><<<grid, SEG_THREADS, 0, h->ls>>>(SEG_ARGS, (uint16_t*)h->d_ids[h->buf], SEG_ARGS2);
@@ -470,13 +548,18 @@ int launch_accumulate(fsk_handle* h, int nb, unsigned long long* K, size_t slot_
         for (int64_t col0 = 0, win = 0; col0 < h->N; col0 += h->col_width, ++win)
         for (int64_t hi = h->N - 1; hi >= col0; hi -= wave) {
             dim3 grid((unsigned)std::min<int64_t>(wave, hi - col0 + 1), groups);
-            auto kern = h->opt_acc_prefetch == 0 ? accumulate_rows_kernel<unsigned long long, IdT, 2, false>
+            auto kern = h->dir_mode ? (h->opt_acc_prefetch == 0 ? accumulate_rows_kernel<unsigned long long, IdT, 2, false, true>
+                                       : h->opt_acc_unroll == 4 ? accumulate_rows_kernel<unsigned long long, IdT, 4, true, true>
+                                                                : accumulate_rows_kernel<unsigned long long, IdT, 2, true, true>)
+                        : h->opt_acc_prefetch == 0 ? accumulate_rows_kernel<unsigned long long, IdT, 2, false>
                         : h->opt_acc_unroll == 4 ? accumulate_rows_kernel<unsigned long long, IdT, 4>
                                                  : accumulate_rows_kernel<unsigned long long, IdT, 2>;
+            DirSpec dir;
+            dir.wkey = h->d_wkey; dir.tdir = h->d_tdir[h->buf]; dir.bshift = h->dir_bshift; dir.keybits = h->keybits; dir.nb = h->dir_nb;
             kern<<<grid, h->rows_threads, h->rows_smem, h->ls>>>(
                 ids, h->ids_stride, h->d_task[h->buf], h->d_woff32, n, (uint32_t)hi, per_group, K, slot_stride,
                 h->wf_active ? h->d_wf : nullptr, (uint32_t)col0, (uint32_t)h->col_width, (uint32_t)(win * h->N), h->d_heavy_bits,
-                h->heavy_bits_stride);
+                h->heavy_bits_stride, dir);
             h->launches++;
         }
     } else {
@@ -857,6 +940,8 @@ void sync_team(fsk_handle* h) {
         w->opt_acc_prefetch = h->opt_acc_prefetch; w->opt_acc_unroll = h->opt_acc_unroll; w->opt_wave = h->opt_wave;
         w->profile = h->profile; w->opt_pad = h->opt_pad; w->opt_acc_cols = h->opt_acc_cols; w->opt_heavy_tau = h->opt_heavy_tau;
         w->opt_ids32 = h->opt_ids32; w->opt_gemm_shape = h->opt_gemm_shape; w->opt_heavy_cap = h->opt_heavy_cap;
+        w->opt_seg_lean = h->opt_seg_lean;
+        w->opt_seg_dir = h->opt_seg_dir; w->opt_dir_blocks = h->opt_dir_blocks; w->opt_count_updates = h->opt_count_updates;
     }
 }
 
@@ -991,6 +1076,17 @@ int fsk_set_option(fsk_handle* h, const char* key, int64_t value) {
     } else if (!strcmp(key, "seg_fused")) {
         if (value < 0 || value > 2) return fail(h, FSK_EINVAL, "seg_fused must be 0 (auto), 1 (off) or 2 (on)");
         h->opt_seg_fused = (int)value;
+    } else if (!strcmp(key, "seg_dir")) {
+        if (value < 0 || value > 2) return fail(h, FSK_EINVAL, "seg_dir must be 0 (auto), 1 (off) or 2 (on)");
+        h->opt_seg_dir = (int)value;
+    } else if (!strcmp(key, "seg_lean")) {
+        if (value < 0 || value > 2) return fail(h, FSK_EINVAL, "seg_lean must be 0 (auto), 1 (off) or 2 (on)");
+        h->opt_seg_lean = (int)value;
+    } else if (!strcmp(key, "dir_blocks")) {
+        if (value < 1 || value > 4096) return fail(h, FSK_EINVAL, "dir_blocks must be in [1, 4096]");
+        h->opt_dir_blocks = (int)value;
+    } else if (!strcmp(key, "count_updates")) {
+        h->opt_count_updates = value != 0;
     } else if (!strcmp(key, "acc_prefetch")) {
         h->opt_acc_prefetch = value != 0;
     } else if (!strcmp(key, "acc_unroll")) {
@@ -1009,6 +1105,7 @@ int fsk_set_option(fsk_handle* h, const char* key, int64_t value) {
 namespace {
 int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int64_t n_train, int64_t n_test) {
     if (!codes || !offsets) return fail(h, FSK_EINVAL, "codes/offsets is NULL");
+    Trace tr("upload");
     // the reference dereferences Xtrain[0] / Xtest[0] unconditionally (fastsk.cpp:33,41); compute_train passes no test set
     if (n_train < 1 || n_test < 0) return fail(h, FSK_EINVAL, "need at least one train sequence (n_train = %lld, n_test = %lld)", (long long)n_train, (long long)n_test);
     const int64_t N = n_train + n_test;
@@ -1054,15 +1151,17 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         for (int64_t i = 0; i < total; ++i)
             dense[(size_t)i] = (uint8_t)(std::lower_bound(uniq.begin(), uniq.end(), codes[offsets[0] + i]) - uniq.begin());
     }
+    tr.lap("length scan + dense re-coding");
     const int b = ceil_log2(A);
     const int cpw = 64 / b;
     if (h->k * b > 64) return fail(h, FSK_EINVAL, "(g - m) * bits-per-character = %d * %d exceeds the 64-bit key", h->k, b);
     if (h->g > 2 * cpw) return fail(h, FSK_EINVAL, "g * bits-per-character = %d * %d exceeds the 128-bit g-mer word", h->g, b);
 
     CU(cudaSetDevice(h->device));
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, h->device));
-    if (prop.major < 10) return fail(h, FSK_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", h->device, prop.major, prop.minor);
+    int cc_major = 0, cc_minor = 0;      // (cudaGetDeviceProperties takes ~7 ms: more than a whole small build)
+    CU(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, h->device));
+    CU(cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, h->device));
+    if (cc_major < 10) return fail(h, FSK_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", h->device, cc_major, cc_minor);
     if (!h->stream) {
         int prio_lo = 0, prio_hi = 0;
         CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -1076,7 +1175,9 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         CU(cudaEventCreateWithFlags(&h->ev_sync, cudaEventDisableTiming));
         h->ls = h->stream;
     }
+    tr.lap("device properties, streams");
     release_device(h);
+    tr.lap("release of the previous buffers");
 
     h->n_train = n_train; h->n_test = n_test; h->N = N; h->nfeat = nfeat;
     h->n_pairs = N * (N + 1) / 2;
@@ -1173,6 +1274,24 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         }
     }
     {
+        // directory form of the segmentation: key spaces of at most 2^16 k-mers on the row path, when the directory (one
+        // entry per key and block of rows) is not much larger than the per-record task list it replaces
+        int bs = 0;
+        while (((N + ((int64_t)1 << bs) - 1) >> bs) > h->opt_dir_blocks) ++bs;
+        const int64_t nb = (N + ((int64_t)1 << bs) - 1) >> bs;
+        const bool dir_ok = h->rows_path && !h->dense_path && h->mode != MODE_KV && h->keybits <= 16 && !h->fused_seg;
+        if (h->opt_seg_dir == 2 && !dir_ok)
+            return fail(h, FSK_EINVAL, "seg_dir = 2 needs the row path, at most 16 key bits and records that carry the sequence id");
+        // opt-in: measured on configs[3] (profiles/r02_segment_forms.txt) the directory form halves the segmentation (no atomic,
+        // no per-record scatter) but its 9.25 M random 8-byte look-ups per combination cost the accumulate more than that
+        h->dir_mode = dir_ok && h->opt_seg_dir == 2;
+        h->dir_bshift = bs;
+        h->dir_nb = (uint32_t)nb;
+        const bool lean_ok = h->mode != MODE_KV && !h->fused_seg && !h->dense_path;
+        if (h->opt_seg_lean == 2 && !lean_ok) return fail(h, FSK_EINVAL, "seg_lean = 2 needs records that carry the sequence id");
+        h->lean_seg = lean_ok && h->opt_seg_lean != 1;
+    }
+    {
         // rows per accumulate launch: the CTAs resident at once, times opt_wave (default 1)
         const int per_sm = std::max(1, std::min(2048 / h->rows_threads, (int)((size_t)(max_smem + 1024) / (h->rows_smem + 1024))));
         h->wave_rows = n_sm * per_sm * std::max(1, h->opt_wave);
@@ -1184,15 +1303,22 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
         CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
         CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
+        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
+        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
+        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
+        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
+        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
+        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
     }
 
     // batch: combinations per launch group.  The row path flushes every row of K once per batch, so it
     // wants the batch as large as memory allows; the u32 shared-memory accumulators bound it by 2^32 / maxwin^2.
-    const int64_t per_slot_bytes = nfeat * (2 * (h->mode == MODE_R32 ? 4 : 8) + (h->mode == MODE_KV ? 8 : 0) + 2 * 8) +
+    const int64_t task_bytes = h->dir_mode ? 2 * (((int64_t)h->dir_nb << h->keybits) * 8) + nfeat * 2 : nfeat * 2 * 8;
+    const int64_t per_slot_bytes = nfeat * (2 * (h->mode == MODE_R32 ? 4 : 8) + (h->mode == MODE_KV ? 8 : 0)) + task_bytes +
                                    2 * (int64_t)h->ids_stride * (h->ids16 ? 2 : 4) +
                                    (int64_t)h->plan.npass * ((nfeat + 3071) / 3072) * RADIX * 4 + N * 4 + 4096;
     size_t free_b = 0, total_b = 0;
-    CU(cudaMemGetInfo(&free_b, &total_b));
+    CU(mem_info_with_cache(&free_b, &total_b));
     int64_t khat_streams = 0;      // variance mode: one fp64 running mean per local virtual stream (allocated by the build)
     if (h->variance_mode) {
         const int64_t nq = h->user_queue.empty() ? h->ncomb : (int64_t)h->user_queue.size();
@@ -1249,7 +1375,9 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     h->sort_tiles = (uint32_t)((nfeat + SORT_THREADS * h->sort_items - 1) / (SORT_THREADS * h->sort_items));
     h->seg_rows = SEG_ROWS_DEFAULT;
     h->seg_tiles = (uint32_t)((nfeat + seg_tile_records(h->seg_rows) - 1) / seg_tile_records(h->seg_rows));
+    h->lean_tiles = (uint32_t)((nfeat + 3 + lean_tile(h->rec_bytes == 4 ? 4 : 8) - 1) / lean_tile(h->rec_bytes == 4 ? 4 : 8));
 
+    tr.lap("path selection, kernel attributes");
     // device inputs
     uint8_t* d_codes = nullptr;
     int64_t *d_off = nullptr, *d_woff = nullptr;
@@ -1281,15 +1409,16 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
 
     // scratch for B slots (the dense path sorts nothing: one record keeps the pointers valid)
     const size_t bn = h->dense_path ? 1 : (size_t)h->B * (size_t)nfeat;
-    if (h->dense_path) { h->sort_tiles = h->seg_tiles = 1; h->ids_stride = 64; }
-    { unsigned char* p; ALLOC(p, bn * (h->mode == MODE_R32 ? 4 : 8)); h->d_recA = p; }
-    { unsigned char* p; ALLOC(p, bn * (h->mode == MODE_R32 ? 4 : 8)); h->d_recB = p; }
+    if (h->dense_path) { h->sort_tiles = h->seg_tiles = h->lean_tiles = 1; h->ids_stride = 64; }
+    // (+ 64 bytes: the register-blocked segmentation reads whole aligned 16-byte vectors around the slots' ends)
+    { unsigned char* p; ALLOC(p, bn * (h->mode == MODE_R32 ? 4 : 8) + 64); h->d_recA = p; }
+    { unsigned char* p; ALLOC(p, bn * (h->mode == MODE_R32 ? 4 : 8) + 64); h->d_recB = p; }
     if (h->mode == MODE_KV) { ALLOC(h->d_valA, bn); ALLOC(h->d_valB, bn); }
     const int B = h->B;
     const size_t ghist_words = (size_t)B * MAX_PASS * RADIX, ticket_words = 64;
     const size_t rowcount_words = 0;
     const size_t status_words = (size_t)h->plan.npass * B * h->sort_tiles * RADIX;
-    const size_t seg_status_words = (size_t)B * h->seg_tiles;
+    const size_t seg_status_words = (size_t)B * std::max(h->seg_tiles, h->lean_tiles);
     h->heavy_bits_stride = h->heavy_tau ? ((h->ids_stride >> (h->ids16 ? 3 : 2)) + 31) / 32 + 1 : 0;
     const size_t heavy_words = (size_t)B * h->heavy_bits_stride;
     h->zero_bytes = 4 * (ghist_words + ticket_words + status_words + seg_status_words + rowcount_words + heavy_words);
@@ -1303,9 +1432,11 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         unsigned char* p;
         ALLOC(p, (size_t)B * h->ids_stride * (h->ids16 ? 2 : 4));
         h->d_ids[i] = p;
-        ALLOC(h->d_task[i], bn);
+        ALLOC(h->d_task[i], h->dir_mode ? 1 : bn);
+        if (h->dir_mode) ALLOC(h->d_tdir[i], (size_t)B * ((size_t)h->dir_nb << h->keybits));
     }
-    ALLOC(h->d_fill, h->dense_path ? 1 : (size_t)B * (size_t)N);
+    if (h->dir_mode) ALLOC(h->d_wkey, bn);
+    ALLOC(h->d_fill, (h->dense_path || h->dir_mode) ? 1 : (size_t)B * (size_t)N);
     {
         std::vector<uint32_t> w32((size_t)N + 1);
         for (int64_t i = 0; i <= N; ++i) w32[(size_t)i] = (uint32_t)woff[(size_t)i];
@@ -1325,7 +1456,7 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     if (h->heavy_tau) {
         // optional stage: it must not be what makes a large upload run out of memory (K and the outputs are still to come)
         size_t free_now = 0, total_now = 0;
-        CU(cudaMemGetInfo(&free_now, &total_now));
+        CU(mem_info_with_cache(&free_now, &total_now));
         if ((double)free_now < (double)N * h->heavy_cap * 2.0 + (double)k_bytes + (double)(2LL << 30)) h->heavy_tau = h->heavy_tau_min = 0;
     }
     if (h->heavy_tau) {
@@ -1362,7 +1493,9 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         ALLOC(h->d_var, B);
         ALLOC(h->d_wf, 1);
     }
+    tr.lap("allocations, H2D, g-mer words (launched)");
     CU(cudaStreamSynchronize(h->stream));
+    tr.lap("stream synchronise (memsets of K)");
     cached_free(d_codes); cached_free(d_off); cached_free(d_woff);
 
     h->combos_done = 0;
@@ -1930,6 +2063,7 @@ int fsk_get_stats(fsk_handle* h, fsk_stats* out) {
     out->ms_accumulate = h->ms[PC_ACCUMULATE]; out->ms_welford = h->ms[PC_WELFORD]; out->ms_normalise = h->ms[PC_NORMALISE];
     for (int i = 0; i < PC_COUNT; ++i) out->ms_total += h->ms[i];
     out->n_devices = is_team(h) ? (int32_t)h->team.size() : 1;
+    out->seg_mode = (h->dir_mode ? 1 : (h->fused_seg ? 2 : 0)) + (h->lean_seg ? 4 : 0);
     // a team: counts add up over the members, times are the slowest member's
     for (size_t i = 1; !h->leader && i < h->team.size(); ++i) {
         fsk_stats o;

@@ -94,6 +94,10 @@ int fsk_output_rows(fsk_handle* h, int64_t* train_r0, int64_t* train_nr, int64_t
  * keys give FSK_EINVAL.  "heavy_tau": -1 off, 0 auto, > 0 forced run-length threshold above which a run's update goes to the
  * tensor cores instead of the row path; "heavy_cap": columns of that contraction's list (0 auto); "gemm_shape": 0 auto, 1 or 2
  * output tiles per CTA of the contraction; "seg_fused": 2 = fused last sort pass + segmentation for two-digit keys (opt-in);
+ * "seg_dir": 0 auto, 1 off, 2 on: directory form of the segmentation (one entry per k-mer and block of rows
+ * instead of one filed task per record; at most 16 key bits), "dir_blocks": target number of row blocks (32); "seg_lean": 0 auto, 1 off, 2 on: register-blocked segmentation kernel
+ * (records that carry the sequence id); "count_updates": 0 = "profile"
+ * times the kernels but does not count entries / runs / pair updates;
  * "acc_prefetch", "acc_unroll", "wave", "rows_threads", "pad", "overlap", "safe_rank": tuning of the row path (defaults are the
  * measured optimum); test hooks: "acc_cols" (forced column-window width of the row path), "ids32" (32-bit id stream) */
 int fsk_set_option(fsk_handle* h, const char* key, int64_t value);
@@ -178,7 +182,8 @@ typedef struct fsk_stats {
     int32_t heavy_tau;
     int64_t heavy_runs;
     int32_t n_devices;          /* GPUs driven by this handle (fsk_set_devices); counts above add up over them, times are the slowest's */
-    int32_t reserved0;
+    int32_t seg_mode;           /* segmentation: 0 one task filed per record, 1 run directory (key spaces <= 2^16), 2 fused bucket form; + 4 when
+                                   the register-blocked kernel (fsk_segment.cuh) does it */
 } fsk_stats;
 int fsk_get_stats(fsk_handle* h, fsk_stats* out);
 

@@ -507,7 +507,7 @@ def test_errors_and_api_surface(FastSK, tmp_path):
     t = f.get_train_kernel_tensor()
     assert t.is_cuda and t.shape == (2, 2) and t.cpu().numpy().tolist() == f.get_train_kernel().tolist()
     f.fit(C=1.0, kernel_type="fastsk", Ytrain=[1, 0])
-    assert 0.0 <= f.score("accuracy", Ytest=[1, 0]) <= 1.0
+    assert 0.0 <= f.score("accuracy", Ytest=[1, 0]) <= 100.0     # a percentage, like fastsk.cpp:505,529
 
 
 def test_reference_run_check_auc():
@@ -524,3 +524,96 @@ def test_reference_run_check_auc():
     acc_x, auc_x, _, iters_x = mod.run(train, test, g=10, m=6)
     assert iters_x == 0 and auc_x >= 0.9, f"exact: AUC {auc_x}"
 
+
+
+def test_directory_form_with_64bit_records(FastSK):
+    """More than 65 536 sequences at 16 key bits: 33 bits of key + id, so 64-bit records (and a 32-bit id stream) in the
+    directory form; the register-blocked and the warp-per-rows kernels and the task-list form must agree bit for bit."""
+    import hashlib
+    rng = np.random.default_rng(99)
+    X = rng.integers(1, 5, size=(66000, 18), dtype=np.int32)
+    X[::7] = X[0]                                                          # long runs too
+    queue = np.array([3, 700, 12869], dtype=np.int32)
+    digests = {}
+    for name, (dd, ll) in {"dir_lean": (2, 2), "dir": (2, 1), "task_lean": (1, 2), "task": (1, 1)}.items():
+        f = FastSK(16, 8, combo_sequence=queue, profile=True)
+        f.set_option("acc_path", 2)
+        f.set_option("seg_dir", dd)
+        f.set_option("seg_lean", ll)
+        f.set_option("batch", 2)
+        f.compute_kernel(X[:64], X[64:])
+        st = f.stats()
+        assert st["record_bytes"] == 8 and st["seg_mode"] == (1 if dd == 2 else 0) + (4 if ll == 2 else 0)
+        digests[name] = (hashlib.sha256(f.get_unnormalised().tobytes()).hexdigest(), st["entries"], st["runs"], st["pair_updates"])
+        del f
+    assert len(set(digests.values())) == 1, digests
+
+
+@pytest.mark.parametrize("variant", ["plain", "blocks3", "heavy", "heavy_overflow", "windows", "ids32", "heavy_ids32_windows", "no_prefetch", "unroll4"])
+@pytest.mark.parametrize("shape", ["dna16_skewed", "dna16_uniform", "dna8_lowcomplex", "dna5_15bit_r64", "protein3_15bit"])
+def test_directory_form_of_the_segmentation(FastSK, oracle_mod, shape, variant):
+    """seg_dir = 2: no task is filed per record; the last record of every (run, block of rows) group writes one directory
+    entry and the row CTA looks its windows' tasks up by key (pack_hist_kernel's wkey).  Exact and variance mode, with
+    heavy runs on the tensor cores, column windows, 32-bit ids, 32- and 64-bit records, several block sizes: bit-equal to
+    the oracle and to the task-list form."""
+    rng = np.random.default_rng(zlib.crc32((shape + variant).encode()))
+    if shape == "dna16_skewed":
+        g, m, X = 16, 8, skewed_dna(rng, 700, 100).tolist()
+    elif shape == "dna16_uniform":
+        g, m, X = 16, 8, random_seqs(rng, 400, 4, 16, 90)
+    elif shape == "dna8_lowcomplex":
+        g, m, X = 7, 3, random_seqs(rng, 300, 4, 20, 120, True)
+    elif shape == "dna5_15bit_r64":
+        g, m, X = 9, 4, random_seqs(rng, 200, 5, 9, 80, True)                # 15 key bits
+    else:
+        g, m, X = 6, 3, random_seqs(rng, 200, 21, 16, 150, True)            # 3 x 5 = 15 key bits
+    nc = comb(g, m)
+    queue = rng.permutation(nc)[:min(nc, 10)].astype(np.int32)
+
+    def build(seg_dir, lean=0, **mode):
+        f = FastSK(g, m, combo_sequence=queue, profile=True, **mode)
+        f.set_option("acc_path", 2)
+        f.set_option("seg_dir", seg_dir)
+        f.set_option("seg_lean", lean)
+        f.set_option("batch", 4)
+        f.set_option("heavy_tau", 8 if "heavy" in variant else -1)
+        if variant == "heavy_overflow":
+            f.set_option("heavy_cap", 64)
+        if "windows" in variant:
+            f.set_option("acc_cols", 64)
+        if "ids32" in variant:
+            f.set_option("ids32", 1)
+        if variant == "blocks3":
+            f.set_option("dir_blocks", 3)
+        if variant == "no_prefetch":
+            f.set_option("acc_prefetch", 0)
+        if variant == "unroll4":
+            f.set_option("acc_unroll", 4)
+        f.compute_train(X)
+        return f
+
+    if "windows" in variant and len(X) > 16 * 64:
+        pytest.skip("more than 16 column windows")
+    d, t = build(2), build(1)
+    assert d.stats()["seg_mode"] == 5 and t.stats()["seg_mode"] == 4        # + 4: the register-blocked kernel (auto)
+    assert np.array_equal(d.get_unnormalised(), t.get_unnormalised())
+    for dd, ll in ((2, 1), (1, 1)):                                          # the warp-per-rows kernel, both forms
+        o = build(dd, ll)
+        assert o.stats()["seg_mode"] == (1 if dd == 2 else 0)
+        assert np.array_equal(o.get_unnormalised(), t.get_unnormalised())
+        so = o.stats()
+        assert (so["entries"], so["runs"], so["pair_updates"], so["heavy_runs"]) == tuple(t.stats()[k] for k in ("entries", "runs", "pair_updates", "heavy_runs"))
+    if len(X) <= 1000:
+        _, Ki, _ = oracle_mod.run("c", X, [], g, m, queue)
+        assert np.array_equal(d.get_unnormalised().astype(np.uint64), Ki)
+    sd, st = d.stats(), t.stats()
+    assert (sd["entries"], sd["runs"], sd["pair_updates"]) == (st["entries"], st["runs"], st["pair_updates"])
+    if "heavy" in variant:
+        assert sd["heavy_runs"] == st["heavy_runs"] and (sd["heavy_runs"] > 0 or shape == "dna16_uniform")
+    if variant in ("plain", "windows") and len(X) <= 1000:
+        v = build(2, t=3, approx=True, delta=0.025, max_iters=4)
+        K, _, sdev = oracle_mod.run("c", X, [], g, m, queue, T=3, approx=True, delta=0.025, max_iters=4)
+        np.testing.assert_allclose(v.get_unnormalised(np.float64), K, rtol=RTOL, atol=0)
+        # the variance statistic is one fp64 sum over all train pairs: the reference adds them one after the other, the GPU
+        # block-wise; on the skewed set (terms spread over many orders of magnitude) the two orders differ by ~1e-12
+        np.testing.assert_allclose(v.get_stdevs(), sdev, rtol=4e-12 if shape == "dna16_skewed" else RTOL, atol=0)
