@@ -299,9 +299,10 @@ def run_b200(args):
         nonlocal t_build, t_final
         t0 = time.perf_counter()
         f._call("fsk_build_partial")
+        if world > 1:
+            dist.barrier()                       # every rank's partial kernel is complete (the slowest shard sets the time)
         t1 = time.perf_counter()
         if world > 1:
-            dist.barrier()
             if merge.startswith("NCCL"):
                 dist.all_reduce(f.partial_tensor(), op=dist.ReduceOp.SUM)
                 torch.cuda.synchronize()
@@ -465,8 +466,9 @@ def run_b200(args):
         "parity_ok": None if parity is None else parity["parity_ok"], "gpu_launches": launches,
         "clocks": clock_info, "phase_ms_per_step": phase_ms, "pair_updates_per_s": updates_all / (ms * 1e-3),
         "step_parts_ms": {"build_shard": build_ms, "merge_and_normalise": merge_norm_ms,
-                          "what": "host-timed parts of one step, max over ranks: the shard's pack/sort/segment/accumulate; then barrier + "
-                                  "normalisation of this rank's rows with the merge of all ranks' partial kernels fused into its loads + barrier"},
+                          "what": "host-timed parts of one step, max over ranks: the shard's pack/sort/segment/accumulate up to the barrier "
+                                  "that ends the slowest shard; then the normalisation of this rank's rows with the merge of all ranks' partial "
+                                  "kernels fused into its loads (peer reads over NVLink; the limiting exchange of the step) + closing barrier"},
         "other_workloads": other,
     }
     print(json.dumps(line))
@@ -508,6 +510,12 @@ def other_workloads(device):
                 best = row
             del f
         out[tag] = best
+    ci = fasta_workload("EP300", 10, 6, device, t=1, approx=True, max_iters=50)
+    if ci is not None:
+        ci["workload"] = ("EP300, g=10 m=6, approx with the variance test, t=1, max_iters=50: the reference's own acceptance configuration "
+                          "(test/run_check.py:45); one virtual stream, its 50 iterations speculated in one launch group")
+        ci["combinations_per_s_device"] = ci["combinations_done_this_rank"] / (ci["device_ms"] * 1e-3) if ci["device_ms"] else None
+    out["ep300_approx_t1"] = ci
     prot = fasta_workload("1.1", 10, 6, device)
     if prot is not None:
         prot["workload"] = "protein remote homology 1.1 train+test (BASELINE configs[2]), g=10 m=6 exact, 210 combinations, 5 bits per character"

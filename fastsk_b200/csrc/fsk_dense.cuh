@@ -166,7 +166,7 @@ template <int NA>
 __global__ void __launch_bounds__(DG_THREADS)
 syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restrict__ tile_order, int64_t nseq, uint32_t k_begin,
                uint32_t k_group, uint32_t klen, unsigned long long* __restrict__ K, size_t out_group_stride,
-               const WelfordSpec* __restrict__ wf, const uint32_t* __restrict__ klen_dev) {
+               const uint32_t* __restrict__ klen_dev) {
     // heavy-run contraction: the number of columns is only known on the device (heavy_fill_kernel's list)
     if (klen_dev) {
         klen = (min(*klen_dev, klen) + DG_BK - 1) / DG_BK * DG_BK;     // klen carries the capacity of the list
@@ -257,12 +257,7 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restr
         // row of the packed triangle: coalesced 256-byte accesses instead of 32 rows x 8 bytes.
         float* __restrict__ ts = reinterpret_cast<float*>(dg_smem_raw + (base - raw)) + (warp - 2) * (32 * 33);
         const int64_t j0 = (int64_t)J * DG_TILE;
-        const bool variance = wf != nullptr;
-        double* __restrict__ kh = variance ? wf->khat[blockIdx.y] : nullptr;
-        const double diter = variance ? (double)wf->iter[blockIdx.y] : 1.0;
-        const int64_t n_train = variance ? wf->n_train : 0;
         unsigned long long* __restrict__ Kg = K + (size_t)blockIdx.y * out_group_stride;
-        double acc = 0.0;
 #pragma unroll 1
         for (int t = 0; t < NA; ++t) {
         if ((int64_t)(I + t) * DG_TILE >= nseq || J > I + t) continue;      // nothing of this tile is at or below the diagonal
@@ -277,27 +272,7 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restr
             const int64_t j = j0 + c0 + lane;
 #pragma unroll 1
             for (int r0 = 0; r0 < 32; r0 += 8) {
-                if (variance) {
-                    // variance mode: the tile is this iteration's partial kernel of the slot's stream; the Welford step on the
-                    // stream's running mean happens here (fastsk_kernel.cpp:121-135), eight rows' loads in flight
-                    double k0[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int64_t i = ibase + r0 + u;
-                        k0[u] = (i < nseq && j <= i) ? kh[(size_t)(i * (i + 1) / 2 + j)] : 0.0;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int64_t i = ibase + r0 + u;
-                        if (i < nseq && j <= i) {
-                            const double ks = (double)__float2uint_rn(ts[(r0 + u) * 33 + lane]);
-                            const double delta = __dsub_rn(ks, k0[u]);
-                            const double nh = __dadd_rn(k0[u], __ddiv_rn(delta, diter));
-                            kh[(size_t)(i * (i + 1) / 2 + j)] = nh;
-                            if (i < n_train) acc = __dadd_rn(acc, __dmul_rn(delta, __dsub_rn(ks, nh)));
-                        }
-                    }
-                } else {
+                {
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int64_t i = ibase + r0 + u;
@@ -310,17 +285,169 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restr
             __syncwarp();
         }
         }
-        if (variance) {   // one partial sum of delta * delta2 per epilogue warp, added up in a fixed order by welford_final_kernel
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-            if (lane == 0) wf->sums[(size_t)blockIdx.y * wf->sums_stride + (size_t)blockIdx.x * 4 + q] = acc;
-        }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(DG_TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Variance mode at batch speed (fastsk_kernel.cpp:188-262): grid = (lower-triangle tiles, virtual streams of the round).  A
+// CTA owns one 128 x 128 tile of ONE stream's running mean and walks the stream's slots -- consecutive iterations, speculated
+// past a possible stop -- IN ORDER: per slot, 4 x (nks / 64) MMAs build the tile of this iteration's partial kernel in TMEM
+// and the epilogue applies the Welford step to the tile of the mean (which the same CTA touched a few microseconds ago: L2
+// hits) and adds up delta * delta2.  Two TMEM accumulators: the MMAs of slot d + 1 run under the epilogue of slot d.  One
+// launch does what used to be one launch + one host round trip per iteration.
+constexpr int DW_STAGES = 2;
+constexpr uint32_t DW_STAGE_BYTES = 2 * DG_TILE_BYTES;
+constexpr uint32_t DW_TS_BYTES = 4 * 32 * 33 * 4;                 // one padded 32 x 32 fp32 transpose buffer per epilogue warp
+__host__ __device__ constexpr size_t dw_smem() { return (size_t)DW_STAGES * DW_STAGE_BYTES + DW_TS_BYTES + 1024 + 256; }
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(DG_THREADS, 2)
+syrk_tc_welford_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restrict__ tile_order, int64_t nseq, uint32_t nks,
+                       const WelfordSpec* __restrict__ wf) {
+    extern __shared__ uint8_t dw_smem_raw[];
+    const uint32_t raw = smem_u32(dw_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t ts_base = base + DW_STAGES * DW_STAGE_BYTES;
+    const uint32_t bars = ts_base + DW_TS_BYTES;                  // full[S], empty[S], tmem_full[2], tmem_empty[2], tmem slot
+    const uint32_t full0 = bars, empty0 = bars + 8 * DW_STAGES, tfull0 = bars + 16 * DW_STAGES, tempty0 = tfull0 + 16, tmem_slot = tempty0 + 16;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(dw_smem_raw + (tmem_slot - raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t ij = tile_order[blockIdx.x];
+    const uint32_t I = ij >> 16, J = ij & 0xffffu;
+    const bool diag = I == J;
+    const int g = blockIdx.y;
+    const uint32_t depth = wf->depth[g], slot0 = wf->slot0[g];
+    const uint32_t nkb = nks / DG_BK;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < DW_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+            const uint32_t tx = diag ? DG_TILE_BYTES : DW_STAGE_BYTES;
+            const uint32_t total = depth * nkb;
+            for (uint32_t t = 0; t < total; ++t) {
+                const uint32_t s = t % DW_STAGES, ph = (t / DW_STAGES) & 1u;
+                mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                mbar_arrive_expect_tx(full0 + 8 * s, tx);
+                const uint32_t a = base + s * DW_STAGE_BYTES;
+                const int x = (int)((slot0 + t / nkb) * nks + (t % nkb) * DG_BK);
+                tma_load_2d(a, &tmap, full0 + 8 * s, x, (int)(I * DG_TILE));
+                if (!diag) tma_load_2d(a + DG_TILE_BYTES, &tmap, full0 + 8 * s, x, (int)(J * DG_TILE));
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(DG_TILE, DG_TILE);
+            uint32_t t = 0;
+            for (uint32_t d = 0; d < depth; ++d) {
+                const uint32_t buf = d & 1u;
+                mbar_wait(tempty0 + 8 * buf, ((d >> 1) & 1u) ^ 1u);          // the epilogue has drained this accumulator
+                tc_fence_after();
+                for (uint32_t kb = 0; kb < nkb; ++kb, ++t) {
+                    const uint32_t s = t % DW_STAGES, ph = (t / DW_STAGES) & 1u;
+                    mbar_wait(full0 + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t a = base + s * DW_STAGE_BYTES;
+                    const uint64_t adesc = umma_desc_sw128(a), bdesc = umma_desc_sw128(diag ? a : a + DG_TILE_BYTES);
+#pragma unroll
+                    for (uint32_t k = 0; k < DG_BK / 16; ++k)
+                        tc_mma_f16(tmem_base + buf * 128u, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0u);
+                    tc_commit(empty0 + 8 * s);
+                }
+                tc_commit(tfull0 + 8 * buf);
+            }
+        }
+        __syncwarp();
+    } else {
+        const uint32_t q = (uint32_t)warp & 3u;
+        float* __restrict__ ts = reinterpret_cast<float*>(dw_smem_raw + (ts_base - raw)) + (warp - 2) * (32 * 33);
+        const int64_t j0 = (int64_t)J * DG_TILE;
+        const int64_t ibase = (int64_t)I * DG_TILE + q * 32;
+        const int64_t n_train = wf->n_train;
+        const double* __restrict__ kin = wf->khat_in[g];
+        double* __restrict__ kout = wf->khat_out[g];
+        for (uint32_t d = 0; d < depth; ++d) {
+            const uint32_t buf = d & 1u;
+            const double* __restrict__ ksrc = d == 0 ? kin : kout;
+            const double diter = (double)(wf->iter0[g] + (int32_t)d);
+            double acc = 0.0;
+            // The epilogue is latency-bound (four warps per CTA walk 16 384 cells of the mean per slot), so the 32 cells a lane
+            // owns in a 32-column chunk are fetched together, BEFORE the wait for the accumulator and the TMEM read: the L2
+            // round trip of the mean runs under the MMAs and the transpose.
+            auto fetch = [&](int c0, double (&k0)[32]) {
+                const int64_t j = j0 + c0 + lane;
+#pragma unroll
+                for (int u = 0; u < 32; ++u) {
+                    const int64_t i = ibase + u;
+                    k0[u] = (i < nseq && j <= i) ? ksrc[(size_t)(i * (i + 1) / 2 + j)] : 0.0;
+                }
+            };
+            double k0[32];
+            fetch(0, k0);
+            mbar_wait(tfull0 + 8 * buf, (d >> 1) & 1u);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < DG_TILE; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + (uint32_t)(buf * 128 + c0), v);
+                if (c0 == DG_TILE - 32) {                                     // last read of this accumulator: hand it back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+                }
+#pragma unroll
+                for (int c = 0; c < 32; ++c) ts[lane * 33 + c] = __uint_as_float(v[c]);
+                __syncwarp();
+                const int64_t j = j0 + c0 + lane;
+#pragma unroll
+                for (int u = 0; u < 32; ++u) {
+                    const int64_t i = ibase + u;
+                    if (i < nseq && j <= i) {
+                        const double ks = (double)__float2uint_rn(ts[u * 33 + lane]);
+                        const double delta = __dsub_rn(ks, k0[u]);
+                        const double nh = __dadd_rn(k0[u], __ddiv_rn(delta, diter));
+                        kout[(size_t)(i * (i + 1) / 2 + j)] = nh;
+                        if (i < n_train) acc = __dadd_rn(acc, __dmul_rn(delta, __dsub_rn(ks, nh)));
+                    }
+                }
+                if (c0 + 32 < DG_TILE) fetch(c0 + 32, k0);                    // (in flight under the next TMEM read + transpose)
+                __syncwarp();
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+            if (lane == 0) wf->sums[(size_t)(slot0 + d) * wf->sums_stride + (size_t)blockIdx.x * 4 + q] = acc;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
     }
 }
 

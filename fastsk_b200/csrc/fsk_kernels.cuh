@@ -44,11 +44,15 @@ struct SortPlan {
 // the virtual stream that owns each slot, its iteration number, and where the per-CTA sums of delta * delta2 go.  Lives
 // in device memory; the host rewrites it before every round.
 struct WelfordSpec {
-    double* khat[MAX_BATCH];
-    int32_t iter[MAX_BATCH];
-    double* sums;                // [slot][sums_stride]
+    // per group = one virtual stream of this round: its slots [slot0, slot0 + depth) are CONSECUTIVE iterations of the stream
+    // (speculated past a possible stop; the host rolls a stream back from khat_in when its stop rule fires inside the round)
+    const double* khat_in[MAX_BATCH];   // the stream's running mean when the round starts
+    double* khat_out[MAX_BATCH];        // ... and where the round leaves it (the same buffer when depth is 1)
+    int32_t iter0[MAX_BATCH];           // iteration number of the group's first slot
+    uint16_t slot0[MAX_BATCH], depth[MAX_BATCH];
+    double* sums;                       // [slot][sums_stride]
     uint32_t sums_stride;
-    int64_t n_train;             // rows below n_train are the train x train block (the first n_train_pairs cells)
+    int64_t n_train;                    // rows below n_train are the train x train block (the first n_train_pairs cells)
 };
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
@@ -762,7 +766,13 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
     const int lane = threadIdx.x & 31;
     const uint32_t wb = woff[b], nw = woff[b + 1] - wb;
     const uint32_t cps = (nw + 31) >> 5;                     // chunks of 32 tasks per slot
-    const uint32_t nchunks = cps * (uint32_t)slots_per_group;
+    // integer modes: the slots of the group add into one row, in any order (one phase over all their chunks).  Variance mode:
+    // the group's slots are consecutive iterations of one virtual stream, applied IN ORDER: one phase per slot, each followed by
+    // the Welford step on the stream's running mean.
+    const uint32_t slot_first = wf ? (uint32_t)wf->slot0[group] : (uint32_t)group * (uint32_t)slots_per_group;
+    const uint32_t nphases = wf ? (uint32_t)wf->depth[group] : 1u;
+    const uint32_t phase_chunks = wf ? cps : cps * (uint32_t)slots_per_group;
+    uint32_t nchunks = phase_chunks;                         // end of the current phase's chunk range
     // this CTA holds columns [col0, col0 + ncols) of row b (all b + 1 of them unless N columns exceed shared memory: then the
     // host launches the row once per column window, and every window streams the row's tasks)
     const uint32_t ncols = min(b + 1 - col0, col_width);
@@ -771,11 +781,11 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
     __syncthreads();
     const uint32_t lane_le = 0xffffffffu >> (31 - lane);
     const uint32_t dump = ncols + lane;                      // 32 words behind the row
-    const uint2* __restrict__ task_g = DIR ? nullptr : task + (size_t)group * slots_per_group * n + wb;
-    const uint16_t* __restrict__ wkey_g = DIR ? dir.wkey + (size_t)group * slots_per_group * n + wb : nullptr;
-    const uint2* __restrict__ tdir_g = DIR ? dir.tdir + ((((size_t)group * slots_per_group) * dir.nb + (b >> dir.bshift)) << dir.keybits) : nullptr;
+    const uint2* __restrict__ task_g = DIR ? nullptr : task + (size_t)slot_first * n + wb;
+    const uint16_t* __restrict__ wkey_g = DIR ? dir.wkey + (size_t)slot_first * n + wb : nullptr;
+    const uint2* __restrict__ tdir_g = DIR ? dir.tdir + ((((size_t)slot_first) * dir.nb + (b >> dir.bshift)) << dir.keybits) : nullptr;
     const size_t tdir_slot = DIR ? ((size_t)dir.nb << dir.keybits) : 0;
-    const IdT* __restrict__ ids_g = ids + (size_t)group * slots_per_group * ids_stride;
+    const IdT* __restrict__ ids_g = ids + (size_t)slot_first * ids_stride;
     // chunk c -> (slot, first task); the task of this lane, or an empty one
     auto grab = [&]() -> uint32_t {
         uint32_t c = 0;
@@ -808,7 +818,7 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
     auto settle_task = [&](uint32_t c, uint2 q) -> uint2 {
         if (q.y >> 31) {
             const uint32_t s = c / cps;
-            const uint32_t w = heavy_bits[((size_t)group * slots_per_group + s) * heavy_bits_stride + (q.x >> 5)];
+            const uint32_t w = heavy_bits[((size_t)slot_first + s) * heavy_bits_stride + (q.x >> 5)];
             q.y &= 0x7fffffffu;
             // taken: the task must still own one unit (the expansion below hands positions to consecutive lanes, so no
             // lane in the middle may be empty): the last unit of the slot's id stream, which is always 0xFF.. fill
@@ -820,6 +830,12 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
     // L2 (its tasks were fetched a whole chunk ago, so nothing waits for them), the tasks of c2 are in flight and -- DIR --
     // so are the keys of c3.  The kernel's stalls are memory latency (ncu: ~28 % of the samples on the first use of the id
     // loads, 7 % on the task loads with a two-deep pipeline), and a prefetch holds no register and no scoreboard entry.
+    for (uint32_t phase = 0; phase < nphases; ++phase) {
+    if (phase) {                                             // next slot of the stream: its chunks [phase * cps, + cps)
+        nchunks = (phase + 1) * cps;
+        if (threadIdx.x == 0) next_chunk = phase * cps;
+        __syncthreads();
+    }
     uint32_t c = grab(), c1 = grab(), c2 = grab();
     uint2 q = settle_task(c, load_task(c, load_key(c)));
     uint2 q1 = load_task(c1, load_key(c1));
@@ -882,19 +898,23 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
     }
     __syncthreads();
     if (wf) {
-        // variance mode: the row holds this iteration's partial kernel Ks of the slot's stream; apply the Welford step to the
-        // stream's running mean right here (no Ks in HBM, no separate pass): fastsk_kernel.cpp:121-135
+        // variance mode: the row holds this iteration's partial kernel Ks of the stream; apply the Welford step to the
+        // stream's running mean right here (no Ks in HBM, no separate pass): fastsk_kernel.cpp:121-135.  The first slot of the
+        // round reads the mean the round started from, the later ones what the previous slot left.
         __shared__ double ws[32];
-        double* __restrict__ kh = wf->khat[group] + ((size_t)b * (b + 1) >> 1) + col0;
-        const double diter = (double)wf->iter[group];
+        const size_t roff = ((size_t)b * (b + 1) >> 1) + col0;
+        const double* __restrict__ kin = (phase == 0 ? wf->khat_in[group] : wf->khat_out[group]) + roff;
+        double* __restrict__ kout = wf->khat_out[group] + roff;
+        const double diter = (double)(wf->iter0[group] + (int32_t)phase);
         const bool train = (int64_t)b < wf->n_train;
         double acc = 0.0;
         for (uint32_t i = threadIdx.x; i < ncols; i += blockDim.x) {
             const double ks = (double)row[i];
-            const double k0 = kh[i];
+            const double k0 = kin[i];
             const double delta = __dsub_rn(ks, k0);
             const double nh = __dadd_rn(k0, __ddiv_rn(delta, diter));
-            kh[i] = nh;
+            kout[i] = nh;
+            row[i] = 0;
             if (train) acc = __dadd_rn(acc, __dmul_rn(delta, __dsub_rn(ks, nh)));
         }
 #pragma unroll
@@ -904,10 +924,12 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
         if (threadIdx.x == 0) {
             double t = 0.0;
             for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) t = __dadd_rn(t, ws[w]);
-            wf->sums[(size_t)group * wf->sums_stride + sums_off + b] = t;
+            wf->sums[(size_t)(slot_first + phase) * wf->sums_stride + sums_off + b] = t;
         }
-        return;
+        continue;                                            // (the next phase's barrier orders the row's zeroes)
     }
+    }   // phases
+    if (wf) return;
     AccT* __restrict__ Krow = K + (size_t)group * k_group_stride + ((size_t)b * (b + 1) >> 1) + col0;
     for (uint32_t i = threadIdx.x; i < ncols; i += blockDim.x) {
         const uint32_t v = row[i];

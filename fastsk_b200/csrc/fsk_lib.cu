@@ -175,6 +175,9 @@ struct fsk_handle {
     double *d_block_sums = nullptr, *d_var = nullptr;
     WelfordSpec* d_wf = nullptr;            // variance mode: per-slot running means for the fused Welford flush
     bool wf_active = false;                 // the batch being launched carries d_wf
+    int wf_groups = 0;                      // ... for this many virtual streams (groups of consecutive slots)
+    int wf_depth = 1;                       // variance mode: iterations of a stream speculated per round (1 = none, no second mean buffer)
+    int opt_spec_depth = 0;                 // 0 auto, else forced upper bound
     uint32_t sums_stride = WELFORD_BLOCKS;  // partial sums per slot
     unsigned long long* d_counters = nullptr;   // entries, runs, pair updates
     uint32_t* d_flag = nullptr;                 // set by segment_kernel when a sorted batch is not non-decreasing
@@ -279,6 +282,22 @@ cudaError_t mem_info_with_cache(size_t* free_b, size_t* total_b) {
     for (auto& kv : g_cache.free_blocks)
         if (kv.first.first == dev) *free_b += kv.first.second;
     return cudaSuccess;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel) and only upwards: ~25 of these per upload were
+// a millisecond of a small build
+template <typename F>
+cudaError_t smem_opt_in(F func, int bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, int> have;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    int& cur = have[{dev, (const void*)func}];
+    if (bytes <= cur) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) cur = bytes;
+    return e;
 }
 
 template <typename T>
@@ -442,7 +461,7 @@ int launch_sort(fsk_handle* h, int nb) {
     const size_t smem = sort_smem<RecT, KV, ITEMS>();
     // opt in to more than 48 KB of dynamic shared memory (per device, so not cached across handles)
     auto kernel = h->safe_rank ? onesweep_kernel<RecT, KV, ITEMS, false> : onesweep_kernel<RecT, KV, ITEMS, true>;
-    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(smem_opt_in(kernel, (int)smem));
     const bool fused = h->fused_seg && !h->safe_rank;     // fused: partition by the high digit only (bucket_segment_kernel does the rest)
     for (int p = fused ? h->plan.npass - 1 : 0; p < h->plan.npass; ++p) {
         const int shift = (KV ? 0 : h->idbits) + h->plan.shift[p];
@@ -542,7 +561,8 @@ int launch_accumulate(fsk_handle* h, int nb, unsigned long long* K, size_t slot_
     const IdT* ids = (const IdT*)h->d_ids[h->buf];
     if (h->rows_path) {
         // slot_stride != 0 (variance mode): every slot adds into its own K; else all slots add into one K
-        const int groups = slot_stride ? nb : 1, per_group = slot_stride ? 1 : nb;
+        // variance mode (wf_active): one group per virtual stream, its slots applied in order; else all slots add into one K
+        const int groups = h->wf_active ? h->wf_groups : (slot_stride ? nb : 1), per_group = slot_stride ? 1 : nb;
         const int wave = std::max(1, h->wave_rows / groups);
         // one pass over the rows per column window of K (a single window unless N columns exceed shared memory)
         for (int64_t col0 = 0, win = 0; col0 < h->N; col0 += h->col_width, ++win)
@@ -592,17 +612,16 @@ int run_batch_dense(fsk_handle* h, int nb, const BatchSpec& spec, unsigned long 
         Span sp(h, PC_ACCUMULATE);
         const unsigned T = (unsigned)((h->N + DG_TILE - 1) / DG_TILE);
         const unsigned tiles = T * (T + 1) / 2;
-        if (slot_stride) {   // variance mode: every slot contracts its own k-mer columns into its own Ks
-            syrk_tc_kernel<1><<<dim3(tiles, (unsigned)nb), DG_THREADS, dg_smem(1), h->ls>>>(h->tmap_C, h->d_tile_order, h->N, 0u, h->nks, h->nks, K, slot_stride,
-                                                                                          h->wf_active ? h->d_wf : nullptr, nullptr);
+        if (h->wf_active) {   // variance mode: every stream's tiles walk the stream's slots in order (Welford in the epilogue)
+            syrk_tc_welford_kernel<<<dim3(tiles, (unsigned)h->wf_groups), DG_THREADS, dw_smem(), h->ls>>>(h->tmap_C, h->d_tile_order, h->N, h->nks, h->d_wf);
             h->launches++;
         } else {
             for (int c0 = 0; c0 < nb; c0 += h->dense_chunk) {
                 const int cs = std::min(h->dense_chunk, nb - c0);
                 if (h->opt_gemm_shape != 1 && (h->opt_gemm_shape == 2 || ((uint32_t)cs * h->nks >= 2048 && T >= 4)))
-                    syrk_tc_kernel<2><<<dim3(h->pair_tiles, 1), DG_THREADS, dg_smem(2), h->ls>>>(h->tmap_C, h->d_pair_order, h->N, (uint32_t)c0 * h->nks, 0u, (uint32_t)cs * h->nks, K, 0, nullptr, nullptr);
+                    syrk_tc_kernel<2><<<dim3(h->pair_tiles, 1), DG_THREADS, dg_smem(2), h->ls>>>(h->tmap_C, h->d_pair_order, h->N, (uint32_t)c0 * h->nks, 0u, (uint32_t)cs * h->nks, K, 0, nullptr);
                 else
-                    syrk_tc_kernel<1><<<dim3(tiles, 1), DG_THREADS, dg_smem(1), h->ls>>>(h->tmap_C, h->d_tile_order, h->N, (uint32_t)c0 * h->nks, 0u, (uint32_t)cs * h->nks, K, 0, nullptr, nullptr);
+                    syrk_tc_kernel<1><<<dim3(tiles, 1), DG_THREADS, dg_smem(1), h->ls>>>(h->tmap_C, h->d_tile_order, h->N, (uint32_t)c0 * h->nks, 0u, (uint32_t)cs * h->nks, K, 0, nullptr);
                 h->launches++;
             }
         }
@@ -691,9 +710,9 @@ int run_batch(fsk_handle* h, const int32_t* combos, int nb, unsigned long long* 
                                                                      h->d_H, (size_t)h->heavy_cap, h->d_counters + 3);
         const unsigned T = (unsigned)((h->N + DG_TILE - 1) / DG_TILE);
         if (h->opt_gemm_shape != 1 && (h->opt_gemm_shape == 2 || T >= 4))
-            syrk_tc_kernel<2><<<dim3(h->pair_tiles, 1), DG_THREADS, dg_smem(2), h->ls>>>(h->tmap_H, h->d_pair_order, h->N, 0u, 0u, h->heavy_cap, K, 0, nullptr, cnt);
+            syrk_tc_kernel<2><<<dim3(h->pair_tiles, 1), DG_THREADS, dg_smem(2), h->ls>>>(h->tmap_H, h->d_pair_order, h->N, 0u, 0u, h->heavy_cap, K, 0, cnt);
         else
-            syrk_tc_kernel<1><<<dim3(T * (T + 1) / 2, 1), DG_THREADS, dg_smem(1), h->ls>>>(h->tmap_H, h->d_tile_order, h->N, 0u, 0u, h->heavy_cap, K, 0, nullptr, cnt);
+            syrk_tc_kernel<1><<<dim3(T * (T + 1) / 2, 1), DG_THREADS, dg_smem(1), h->ls>>>(h->tmap_H, h->d_tile_order, h->N, 0u, 0u, h->heavy_cap, K, 0, cnt);
         h->launches += 3;
         CU(cudaGetLastError());
         if (!h->heavy_probe_pending) {   // did this batch have any heavy run?  read back without waiting
@@ -735,8 +754,9 @@ int encode_operand_map(fsk_handle* h, CUtensorMap* map, __half* ptr, size_t ld) 
                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(h, FSK_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
-    CU(cudaFuncSetAttribute(syrk_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dg_smem(1)));
-    CU(cudaFuncSetAttribute(syrk_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dg_smem(2)));
+    CU(smem_opt_in(syrk_tc_kernel<1>, (int)dg_smem(1)));
+    CU(smem_opt_in(syrk_tc_kernel<2>, (int)dg_smem(2)));
+    CU(smem_opt_in(syrk_tc_welford_kernel, (int)dw_smem()));
     return FSK_OK;
 }
 
@@ -940,7 +960,7 @@ void sync_team(fsk_handle* h) {
         w->opt_acc_prefetch = h->opt_acc_prefetch; w->opt_acc_unroll = h->opt_acc_unroll; w->opt_wave = h->opt_wave;
         w->profile = h->profile; w->opt_pad = h->opt_pad; w->opt_acc_cols = h->opt_acc_cols; w->opt_heavy_tau = h->opt_heavy_tau;
         w->opt_ids32 = h->opt_ids32; w->opt_gemm_shape = h->opt_gemm_shape; w->opt_heavy_cap = h->opt_heavy_cap;
-        w->opt_seg_lean = h->opt_seg_lean;
+        w->opt_seg_lean = h->opt_seg_lean; w->opt_spec_depth = h->opt_spec_depth;
         w->opt_seg_dir = h->opt_seg_dir; w->opt_dir_blocks = h->opt_dir_blocks; w->opt_count_updates = h->opt_count_updates;
     }
 }
@@ -1079,6 +1099,9 @@ int fsk_set_option(fsk_handle* h, const char* key, int64_t value) {
     } else if (!strcmp(key, "seg_dir")) {
         if (value < 0 || value > 2) return fail(h, FSK_EINVAL, "seg_dir must be 0 (auto), 1 (off) or 2 (on)");
         h->opt_seg_dir = (int)value;
+    } else if (!strcmp(key, "spec_depth")) {
+        if (value < 0 || value > MAX_BATCH) return fail(h, FSK_EINVAL, "spec_depth must be in [0, %d]", MAX_BATCH);
+        h->opt_spec_depth = (int)value;
     } else if (!strcmp(key, "seg_lean")) {
         if (value < 0 || value > 2) return fail(h, FSK_EINVAL, "seg_lean must be 0 (auto), 1 (off) or 2 (on)");
         h->opt_seg_lean = (int)value;
@@ -1126,30 +1149,56 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         return fail(h, FSK_EINVAL, "g cannot be longer than the shortest sequence in a dataset: g = %d, but shortest test sequence has length %lld", h->g, (long long)shortest_test);
     if (nfeat >= (1LL << 30)) return fail(h, FSK_EINVAL, "too many g-mers (%lld); at most 2^30 - 1", (long long)nfeat);
 
-    // dense re-coding: only equality of characters matters
+    // dense re-coding: only equality of characters matters.  Host threads over slices of the characters (the
+    // 10 M characters of configs[3] took 20 ms on one core: 2 % of an 8-GPU build).
     const int64_t total = offsets[N] - offsets[0];
-    int32_t maxv = 0;
-    for (int64_t i = offsets[0]; i < offsets[N]; ++i) {
-        if (codes[i] < 0) return fail(h, FSK_EINVAL, "negative character code at position %lld", (long long)i);
-        maxv = std::max(maxv, codes[i]);
+    const int32_t* __restrict__ cbase = codes + offsets[0];
+    const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)8, (int64_t)std::thread::hardware_concurrency(), total >> 18}));
+    auto parallel = [&](const std::function<void(int, int64_t, int64_t)>& fn) {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nthr; ++t) th.emplace_back(fn, t, total * t / nthr, total * (t + 1) / nthr);
+        fn(0, 0, total / nthr);
+        for (auto& x : th) x.join();
+    };
+    std::vector<int32_t> tmax((size_t)nthr, 0), tmin((size_t)nthr, 0);
+    parallel([&](int t, int64_t a, int64_t e) {
+        int32_t mx = 0, mn = 0;
+        for (int64_t i = a; i < e; ++i) { mx = std::max(mx, cbase[i]); mn = std::min(mn, cbase[i]); }
+        tmax[(size_t)t] = mx; tmin[(size_t)t] = mn;
+    });
+    const int32_t maxv = *std::max_element(tmax.begin(), tmax.end());
+    if (*std::min_element(tmin.begin(), tmin.end()) < 0) {
+        for (int64_t i = 0; i < total; ++i)
+            if (cbase[i] < 0) return fail(h, FSK_EINVAL, "negative character code at position %lld", (long long)(offsets[0] + i));
     }
     std::vector<int32_t> remap;
     std::vector<uint8_t> dense((size_t)total);
     int A = 0;
     if (maxv < (1 << 22)) {
+        std::vector<std::vector<uint8_t>> seen((size_t)nthr, std::vector<uint8_t>((size_t)maxv + 1, 0));
+        parallel([&](int t, int64_t a, int64_t e) {
+            uint8_t* sn = seen[(size_t)t].data();
+            for (int64_t i = a; i < e; ++i) sn[cbase[i]] = 1;
+        });
         remap.assign((size_t)maxv + 1, -1);
-        for (int64_t i = offsets[0]; i < offsets[N]; ++i) remap[codes[i]] = 0;
-        for (auto& r : remap) if (r == 0) r = A++;
+        for (int32_t v = 0; v <= maxv; ++v) {
+            bool any = false;
+            for (int t = 0; t < nthr; ++t) any |= seen[(size_t)t][(size_t)v] != 0;
+            if (any) remap[(size_t)v] = A++;
+        }
         if (A > 256) return fail(h, FSK_EINVAL, "alphabet of %d distinct characters; at most 256 are supported", A);
-        for (int64_t i = 0; i < total; ++i) dense[(size_t)i] = (uint8_t)remap[codes[offsets[0] + i]];
+        parallel([&](int, int64_t a, int64_t e) {
+            for (int64_t i = a; i < e; ++i) dense[(size_t)i] = (uint8_t)remap[(size_t)cbase[i]];
+        });
     } else {
-        std::vector<int32_t> uniq(codes + offsets[0], codes + offsets[N]);
+        std::vector<int32_t> uniq(cbase, cbase + total);
         std::sort(uniq.begin(), uniq.end());
         uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
         A = (int)uniq.size();
         if (A > 256) return fail(h, FSK_EINVAL, "alphabet of %d distinct characters; at most 256 are supported", A);
-        for (int64_t i = 0; i < total; ++i)
-            dense[(size_t)i] = (uint8_t)(std::lower_bound(uniq.begin(), uniq.end(), codes[offsets[0] + i]) - uniq.begin());
+        parallel([&](int, int64_t a, int64_t e) {
+            for (int64_t i = a; i < e; ++i) dense[(size_t)i] = (uint8_t)(std::lower_bound(uniq.begin(), uniq.end(), cbase[i]) - uniq.begin());
+        });
     }
     tr.lap("length scan + dense re-coding");
     const int b = ceil_log2(A);
@@ -1269,8 +1318,8 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
             const int64_t per_cta = ((int64_t)max_smem + 1024) / 2 - 1024 - 512;
             const int64_t cap_max = ((per_cta - (int64_t)bucket_smem_bytes(0)) * 32 / 66) & ~63LL;
             h->image_cap = (uint32_t)std::max<int64_t>(64, std::min<int64_t>(cap_max, (nfeat + 64 * ((int64_t)1 << lo_bits) + 127) & ~63LL));
-            CU(cudaFuncSetAttribute(bucket_segment_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bucket_smem_bytes(h->image_cap)));
-            CU(cudaFuncSetAttribute(bucket_segment_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bucket_smem_bytes(h->image_cap)));
+            CU(smem_opt_in(bucket_segment_kernel<false>, (int)bucket_smem_bytes(h->image_cap)));
+            CU(smem_opt_in(bucket_segment_kernel<true>, (int)bucket_smem_bytes(h->image_cap)));
         }
     }
     {
@@ -1297,18 +1346,18 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         h->wave_rows = n_sm * per_sm * std::max(1, h->opt_wave);
     }
     if (h->rows_path) {
-        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint16_t, 4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
-        CU(cudaFuncSetAttribute(accumulate_rows_kernel<unsigned long long, uint32_t, 4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rows_smem));
+        CU(smem_opt_in(accumulate_rows_kernel<unsigned long long, uint16_t, 2, false>, (int)h->rows_smem));
+        CU(smem_opt_in(accumulate_rows_kernel<unsigned long long, uint32_t, 2, false>, (int)h->rows_smem));
+        CU(smem_opt_in(accumulate_rows_kernel<unsigned long long, uint16_t, 2>, (int)h->rows_smem));
+        CU(smem_opt_in(accumulate_rows_kernel<unsigned long long, uint16_t, 4>, (int)h->rows_smem));
+        CU(smem_opt_in(accumulate_rows_kernel<unsigned long long, uint32_t, 2>, (int)h->rows_smem));
+        CU(smem_opt_in(accumulate_rows_kernel<unsigned long long, uint32_t, 4>, (int)h->rows_smem));
+        CU(smem_opt_in(accumulate_rows_kernel<unsigned long long, uint16_t, 2, false, true>, (int)h->rows_smem));
+        CU(smem_opt_in(accumulate_rows_kernel<unsigned long long, uint32_t, 2, false, true>, (int)h->rows_smem));
+        CU(smem_opt_in(accumulate_rows_kernel<unsigned long long, uint16_t, 2, true, true>, (int)h->rows_smem));
+        CU(smem_opt_in(accumulate_rows_kernel<unsigned long long, uint16_t, 4, true, true>, (int)h->rows_smem));
+        CU(smem_opt_in(accumulate_rows_kernel<unsigned long long, uint32_t, 2, true, true>, (int)h->rows_smem));
+        CU(smem_opt_in(accumulate_rows_kernel<unsigned long long, uint32_t, 4, true, true>, (int)h->rows_smem));
     }
 
     // batch: combinations per launch group.  The row path flushes every row of K once per batch, so it
@@ -1324,28 +1373,43 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         const int64_t nq = h->user_queue.empty() ? h->ncomb : (int64_t)h->user_queue.size();
         khat_streams = (effective_streams(h, nq) + h->world - 1) / h->world;
     }
-    const int64_t k_bytes = h->n_pairs * 8 * (h->variance_mode ? 2 + khat_streams : 1) + (int64_t)n_train * N * 8;
+    const int64_t k_bytes = h->n_pairs * 8 * (h->variance_mode ? 2 + khat_streams : 1) + (int64_t)n_train * N * 8;   // (+ a second set of means when rounds speculate: checked below)
     int64_t Bsel = h->opt_batch > 0 ? h->opt_batch : MAX_BATCH;
     if (h->opt_batch == 0) {
         if (!h->rows_path) Bsel = std::max<int64_t>(1, (6LL << 20) / std::max<int64_t>(1, nfeat));
         const int64_t budget = ((int64_t)free_b - k_bytes) * 4 / 10;
-        Bsel = std::min(Bsel, std::max<int64_t>(1, budget / std::max<int64_t>(1, per_slot_bytes + (h->variance_mode ? h->n_pairs * 8 : 0))));
+        // (variance mode on the global-RED path keeps this iteration's integer partial kernel of every slot)
+        const bool slot_ks = h->variance_mode && !(h->rows_path || h->dense_path);
+        Bsel = std::min(Bsel, std::max<int64_t>(1, budget / std::max<int64_t>(1, per_slot_bytes + (slot_ks ? h->n_pairs * 8 : 0))));
     }
     Bsel = std::min<int64_t>(Bsel, MAX_BATCH);
     Bsel = std::min<int64_t>(Bsel, std::max<int64_t>(1, (int64_t)(4294967295.0 / ((double)maxwin * (double)maxwin))));
     Bsel = std::min<int64_t>(Bsel, std::max<int64_t>(1, h->user_queue.empty() ? h->ncomb : (int64_t)h->user_queue.size()));
-    if (h->variance_mode) {   // one slot per live virtual stream of this rank is all a round can use
-        const int64_t nq = h->user_queue.empty() ? h->ncomb : (int64_t)h->user_queue.size();
-        const int T = effective_streams(h, nq);
-        Bsel = std::min<int64_t>(Bsel, std::max(1, (T + h->world - 1) / h->world));
+    h->wf_depth = 1;
+    if (h->variance_mode) {
+        // a round gives every live virtual stream of this rank `depth` consecutive slots (iterations speculated past a possible
+        // stop); that needs a second buffer of running means to roll a stream back from.  Without room for it -- or on the
+        // global-RED path, whose Welford pass is not fused -- one slot per stream, as the reference iterates.
+        const int64_t T_local = std::max<int64_t>(1, khat_streams);
+        int64_t depth = (h->rows_path || h->dense_path) ? std::max<int64_t>(1, Bsel / T_local) : 1;
+        if (h->opt_spec_depth) depth = std::min<int64_t>(depth, h->opt_spec_depth);
+        if (h->max_iters > 0) depth = std::min<int64_t>(depth, h->max_iters);
+        if (depth > 1 && (double)free_b * 0.9 < (double)k_bytes + (double)T_local * h->n_pairs * 8 + (double)per_slot_bytes * T_local * 2) depth = 1;
+        h->wf_depth = (int)depth;
+        Bsel = std::min<int64_t>(Bsel, T_local * depth);
     }
     if (h->dense_path) {
         if (h->opt_batch == 0) Bsel = std::min<int64_t>(MAX_BATCH, std::max<int64_t>(1, h->user_queue.empty() ? h->ncomb : (int64_t)h->user_queue.size()));
-        if (h->variance_mode) {
-            const int64_t nq = h->user_queue.empty() ? h->ncomb : (int64_t)h->user_queue.size();
-            Bsel = std::min<int64_t>(Bsel, std::max(1, (effective_streams(h, nq) + h->world - 1) / h->world));
-        }
         Bsel = std::min<int64_t>(Bsel, std::max<int64_t>(1, (4LL << 30) / (N * (int64_t)h->nks * 2)));   // C stays below 4 GB
+        if (h->variance_mode) {
+            const int64_t T_local = std::max<int64_t>(1, khat_streams);
+            int64_t depth = std::max<int64_t>(1, Bsel / T_local);
+            if (h->opt_spec_depth) depth = std::min<int64_t>(depth, h->opt_spec_depth);
+            if (h->max_iters > 0) depth = std::min<int64_t>(depth, h->max_iters);
+            if (depth > 1 && (double)free_b * 0.9 < (double)k_bytes + (double)T_local * h->n_pairs * 8) depth = 1;
+            h->wf_depth = (int)depth;
+            Bsel = std::min<int64_t>(Bsel, T_local * depth);
+        }
         h->dense_chunk = (int)std::max<int64_t>(1, std::min<int64_t>(Bsel, 16777215 / std::max<int64_t>(1, maxwin * maxwin)));
     }
     h->B = (int)Bsel;
@@ -1449,9 +1513,9 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         int rc_ = encode_operand_map(h, &h->tmap_C, h->d_C, h->dense_ld);
         if (rc_) return rc_;
         const int count_smem = DENSE_COUNT_WARPS * (int)h->nks * 2;
-        CU(cudaFuncSetAttribute(dense_count_kernel<uint64_t, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, count_smem));
-        CU(cudaFuncSetAttribute(dense_count_kernel<uint64_t, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, count_smem));
-        CU(cudaFuncSetAttribute(dense_count_kernel<uint32_t, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, count_smem));
+        CU(smem_opt_in(dense_count_kernel<uint64_t, 2>, count_smem));
+        CU(smem_opt_in(dense_count_kernel<uint64_t, 1>, count_smem));
+        CU(smem_opt_in(dense_count_kernel<uint32_t, 1>, count_smem));
     }
     if (h->heavy_tau) {
         // optional stage: it must not be what makes a large upload run out of memory (K and the outputs are still to come)
@@ -1607,85 +1671,127 @@ int build_partial_once(fsk_handle* h) {
         rc = accumulate_one(h, mine.data(), (int64_t)mine.size(), 0);
         if (rc) return rc;
     } else {
-        // variance mode: T independent virtual streams (fastsk_kernel.cpp:188-281), stream tid owned by rank tid % world
-        struct Stream { int tid; int64_t item; int iter; bool working; double* khat; };
+        // variance mode: T independent virtual streams (fastsk_kernel.cpp:188-281), stream tid owned by rank tid % world.
+        // A round gives every live stream up to wf_depth CONSECUTIVE iterations, applied in order by one launch group; the
+        // host then walks each stream's variance statistics in order and applies the stop rule (fastsk_kernel.cpp:243-262).
+        // A stream whose rule fires before the round's last iteration is rolled back: its running mean is rebuilt from the
+        // buffer the round started from (`cur`), with only the iterations it really ran.  One host round trip per round.
+        struct Stream { int tid; int64_t item; int iter; bool working; double *cur, *alt; int depth, used; };
         std::vector<Stream> streams;
         std::vector<int32_t> my_streams;
         shard_work(h, my_streams);
+        const bool fused_wf = h->rows_path || h->dense_path;
+        const bool pingpong = fused_wf && h->wf_depth > 1;
         if (!my_streams.empty()) {   // one allocation for the running means of all local streams (cudaMalloc/cudaFree are slow)
             double* all;
-            ALLOC(all, (size_t)h->n_pairs * my_streams.size());
+            const size_t per = (size_t)h->n_pairs * (pingpong ? 2 : 1);
+            ALLOC(all, per * my_streams.size());
             h->d_Khat.push_back(all);
-            CU(cudaMemsetAsync(all, 0, sizeof(double) * (size_t)h->n_pairs * my_streams.size(), h->stream));
-            for (size_t i = 0; i < my_streams.size(); ++i)
-                streams.push_back({my_streams[i], my_streams[i], 1, true, all + i * (size_t)h->n_pairs});
+            CU(cudaMemsetAsync(all, 0, sizeof(double) * per * my_streams.size(), h->stream));
+            for (size_t i = 0; i < my_streams.size(); ++i) {
+                double* c = all + i * per;
+                streams.push_back({my_streams[i], my_streams[i], 1, true, c, pingpong ? c + h->n_pairs : c, 0, 0});
+            }
         }
         std::vector<double> var_host((size_t)h->B);
+        const int64_t Tt = (h->N + DG_TILE - 1) / DG_TILE;
+        const int n_sums = !fused_wf ? WELFORD_BLOCKS : (h->dense_path ? (int)(2 * Tt * (Tt + 1)) : (int)(h->N * h->col_windows));
+        // one launch group: the given streams, stream i running its next depth[i] iterations
+        auto run_round = [&](const std::vector<Stream*>& grp, int nslots) -> int {
+            int32_t combos[MAX_BATCH];
+            WelfordSpec wf;
+            memset(&wf, 0, sizeof wf);
+            int slot = 0;
+            for (size_t gi = 0; gi < grp.size(); ++gi) {
+                Stream* st = grp[gi];
+                wf.khat_in[gi] = st->cur; wf.khat_out[gi] = st->alt; wf.iter0[gi] = st->iter;
+                wf.slot0[gi] = (uint16_t)slot; wf.depth[gi] = (uint16_t)st->depth;
+                for (int d = 0; d < st->depth; ++d) combos[slot++] = h->queue[(size_t)(st->item + (int64_t)T * d)];
+            }
+            wf.sums = h->d_block_sums; wf.sums_stride = h->sums_stride; wf.n_train = h->n_train;
+            if (fused_wf) CU(cudaMemcpyAsync(h->d_wf, &wf, sizeof wf, cudaMemcpyHostToDevice, h->stream));
+            if (fused_wf && h->rows_path && h->col_windows > 1)   // rows below a column window write no partial sum for it
+                CU(cudaMemsetAsync(h->d_block_sums, 0, sizeof(double) * (size_t)nslots * h->sums_stride, h->stream));
+            h->wf_active = fused_wf;
+            h->wf_groups = (int)grp.size();
+            int rc2 = run_batch(h, combos, nslots, h->d_Kint, (size_t)h->n_pairs);
+            h->wf_active = false;
+            if (rc2) return rc2;
+            Span sp(h, PC_WELFORD);
+            if (!fused_wf) {   // global-RED path: Ks of each slot (zero on entry), a separate Welford pass per stream (depth is 1)
+                for (size_t gi = 0; gi < grp.size(); ++gi) {
+                    welford_kernel<unsigned long long><<<WELFORD_BLOCKS, 256, 0, h->stream>>>(
+                        h->d_Kint + gi * (size_t)h->n_pairs, grp[gi]->cur, h->n_pairs, h->n_train_pairs, grp[gi]->iter,
+                        h->d_block_sums + gi * (size_t)h->sums_stride);
+                    h->launches++;
+                }
+            }
+            welford_final_kernel<<<nslots, 256, 0, h->stream>>>(h->d_block_sums, (size_t)h->sums_stride, n_sums, h->d_var);
+            h->launches++;
+            CU(cudaGetLastError());
+            return FSK_OK;
+        };
         while (true) {
             std::vector<Stream*> active;
             for (auto& s : streams) if (s.working) active.push_back(&s);
             if (active.empty()) break;
-            for (size_t a0 = 0; a0 < active.size(); a0 += (size_t)h->B) {
-                const int nb = (int)std::min<size_t>((size_t)h->B, active.size() - a0);
-                int32_t combos[MAX_BATCH];
-                for (int s = 0; s < nb; ++s) combos[s] = h->queue[(size_t)active[a0 + s]->item];
-                // row path and dense path: the Welford step is the flush / epilogue of the accumulate itself (no Ks in HBM);
-                // global-RED path: Ks of each slot (zero on entry) and a separate Welford pass
-                const bool fused_wf = h->rows_path || h->dense_path;
-                int n_sums = WELFORD_BLOCKS;
-                if (fused_wf) {
-                    WelfordSpec wf;
-                    memset(&wf, 0, sizeof wf);
-                    for (int s = 0; s < nb; ++s) { wf.khat[s] = active[a0 + s]->khat; wf.iter[s] = active[a0 + s]->iter; }
-                    wf.sums = h->d_block_sums;
-                    wf.sums_stride = h->sums_stride;
-                    wf.n_train = h->n_train;
-                    CU(cudaMemcpyAsync(h->d_wf, &wf, sizeof wf, cudaMemcpyHostToDevice, h->stream));
-                    const int64_t Tt = (h->N + DG_TILE - 1) / DG_TILE;
-                    n_sums = h->dense_path ? (int)(2 * Tt * (Tt + 1)) : (int)(h->N * h->col_windows);
+            // groups of streams that fit the batch; every stream of a group gets the same share of the slots
+            const size_t per_group = std::min<size_t>(active.size(), (size_t)h->B);
+            std::vector<Stream*> redo;
+            for (size_t a0 = 0; a0 < active.size(); a0 += per_group) {
+                std::vector<Stream*> grp(active.begin() + (long)a0, active.begin() + (long)std::min(active.size(), a0 + per_group));
+                const int share = fused_wf ? std::max(1, std::min(h->wf_depth, h->B / (int)grp.size())) : 1;
+                int nslots = 0;
+                for (Stream* st : grp) {
+                    int64_t left = (nq - st->item + T - 1) / T;                                  // items left in its strided queue
+                    if (h->max_iters != -1) left = std::min<int64_t>(left, std::max(1, h->max_iters - st->iter + 1));
+                    st->depth = (int)std::max<int64_t>(1, std::min<int64_t>(share, left));
+                    nslots += st->depth;
                 }
-                if (fused_wf && h->rows_path && h->col_windows > 1)   // rows below a column window write no partial sum for it
-                    CU(cudaMemsetAsync(h->d_block_sums, 0, sizeof(double) * (size_t)nb * h->sums_stride, h->stream));
-                h->wf_active = fused_wf;
-                rc = run_batch(h, combos, nb, h->d_Kint, (size_t)h->n_pairs);
-                h->wf_active = false;
+                rc = run_round(grp, nslots);
                 if (rc) return rc;
-                {
-                    Span sp(h, PC_WELFORD);
-                    for (int s = 0; s < nb; ++s) {
-                        Stream* st = active[a0 + s];
-                        if (!fused_wf) {
-                            welford_kernel<unsigned long long><<<WELFORD_BLOCKS, 256, 0, h->stream>>>(
-                                h->d_Kint + (size_t)s * h->n_pairs, st->khat, h->n_pairs, h->n_train_pairs, st->iter,
-                                h->d_block_sums + (size_t)s * h->sums_stride);
-                            h->launches++;
-                        }
-                    }
-                    welford_final_kernel<<<nb, 256, 0, h->stream>>>(h->d_block_sums, (size_t)h->sums_stride, n_sums, h->d_var);
-                    h->launches++;
-                    CU(cudaGetLastError());
-                }
-                CU(cudaMemcpyAsync(var_host.data(), h->d_var, sizeof(double) * (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
+                CU(cudaMemcpyAsync(var_host.data(), h->d_var, sizeof(double) * (size_t)nslots, cudaMemcpyDeviceToHost, h->stream));
                 CU(cudaStreamSynchronize(h->stream));
-                for (int s = 0; s < nb; ++s) {
-                    Stream* st = active[a0 + s];
-                    // fastsk_kernel.cpp:130-142 then 244-256
-                    double v = var_host[(size_t)s] / (double)h->n_train_pairs;
-                    if (st->iter == 1) v = 9999999;
-                    else v /= st->iter - 1;
-                    const double sd = std::sqrt(v / st->iter);
-                    if (st->tid == 0) h->stdevs.push_back(sd);
-                    if (h->delta / sd > 1.96) st->working = false;
-                    if (h->max_iters != -1 && st->iter >= h->max_iters) st->working = false;
-                    st->item += T;
-                    if (st->item >= nq) st->working = false;
-                    st->iter++;
+                int slot = 0;
+                for (Stream* st : grp) {
+                    st->used = 0;
+                    for (int d = 0; d < st->depth && st->working; ++d) {
+                        // fastsk_kernel.cpp:130-142 then 244-256
+                        double v = var_host[(size_t)(slot + d)] / (double)h->n_train_pairs;
+                        if (st->iter == 1) v = 9999999;
+                        else v /= st->iter - 1;
+                        const double sd = std::sqrt(v / st->iter);
+                        if (st->tid == 0) h->stdevs.push_back(sd);
+                        if (h->delta / sd > 1.96) st->working = false;
+                        if (h->max_iters != -1 && st->iter >= h->max_iters) st->working = false;
+                        st->item += T;
+                        if (st->item >= nq) st->working = false;
+                        st->iter++;
+                        st->used++;
+                    }
+                    slot += st->depth;
+                    if (st->used < st->depth) redo.push_back(st);          // stopped inside the round: `alt` ran too far
+                    else std::swap(st->cur, st->alt);
                 }
+            }
+            // roll back: rebuild the mean of every stream that stopped early from where its round started
+            for (size_t a0 = 0; a0 < redo.size();) {
+                std::vector<Stream*> grp;
+                int nslots = 0;
+                while (a0 < redo.size() && nslots + redo[a0]->used <= h->B) {
+                    Stream* st = redo[a0++];
+                    st->item -= (int64_t)T * st->used; st->iter -= st->used; st->depth = st->used;   // as the round found it
+                    nslots += st->depth;
+                    grp.push_back(st);
+                }
+                rc = run_round(grp, nslots);
+                if (rc) return rc;
+                for (Stream* st : grp) { st->item += (int64_t)T * st->used; st->iter += st->used; std::swap(st->cur, st->alt); }
             }
         }
         // merge (fastsk_kernel.cpp:296-313): sum of the streams' running means, in stream order
         for (auto& s : streams) {
-            add_f64_kernel<<<592, 256, 0, h->stream>>>(h->d_Kf, s.khat, h->n_pairs);
+            add_f64_kernel<<<592, 256, 0, h->stream>>>(h->d_Kf, s.cur, h->n_pairs);
             h->launches++;
         }
         CU(cudaGetLastError());

@@ -617,3 +617,62 @@ def test_directory_form_of_the_segmentation(FastSK, oracle_mod, shape, variant):
         # the variance statistic is one fp64 sum over all train pairs: the reference adds them one after the other, the GPU
         # block-wise; on the skewed set (terms spread over many orders of magnitude) the two orders differ by ~1e-12
         np.testing.assert_allclose(v.get_stdevs(), sdev, rtol=4e-12 if shape == "dna16_skewed" else RTOL, atol=0)
+
+
+@pytest.mark.parametrize("acc_path", [2, 3], ids=["rows", "dense_tc"])
+@pytest.mark.parametrize("T,max_iters,delta", [(1, 37, 0.025), (3, -1, 0.4), (4, 9, 2.0), (2, 50, 1.2)])
+def test_speculated_variance_rounds_equal_the_iteration_by_iteration_build(FastSK, oracle_mod, acc_path, T, max_iters, delta):
+    """Variance mode runs several consecutive iterations of every virtual stream per launch group (spec_depth) and rolls a
+    stream back when its stop rule fires inside a round.  Every depth must give the same running means, the same stdevs
+    and the same stopping iteration as depth 1 and as the oracle; the large deltas make streams converge in mid-round."""
+    rng = np.random.default_rng(1000 + T)
+    g, m = 9, 5
+    X = random_seqs(rng, 40, 4, 20, 70)
+    queue = rng.permutation(comb(g, m)).astype(np.int32)
+    K, _, sd = oracle_mod.run("c", X[:28], X[28:], g, m, queue, T=T, approx=True, delta=delta, max_iters=max_iters)
+    base = None
+    for depth in (1, 2, 5, 0):
+        f = FastSK(g, m, T, True, delta, max_iters, False, combo_sequence=queue)
+        f.set_option("acc_path", acc_path)
+        f.set_option("spec_depth", depth)
+        f.compute_kernel(X[:28], X[28:])
+        got = (f.get_unnormalised(np.float64), f.get_stdevs())
+        assert len(got[1]) == len(sd), f"depth {depth}: stopped at another iteration"
+        np.testing.assert_allclose(got[1], sd, rtol=RTOL, atol=0)
+        np.testing.assert_allclose(got[0], K, rtol=RTOL, atol=0)
+        if base is None:
+            base = got
+        else:                    # the Welford steps are the same operations in the same order at every depth
+            assert np.array_equal(got[0], base[0]) and got[1] == base[1], f"depth {depth}"
+
+
+@pytest.mark.parametrize("acc_path", [2, 3], ids=["rows", "dense_tc"])
+@pytest.mark.parametrize("name", ["1.1", "EP300"])
+def test_full_bundled_sets_against_the_reference_fingerprints(FastSK, name, acc_path):
+    """BASELINE configs[1] and [2] at FULL size (4000 / 3574 sequences, all 210 combinations): sha256 of the unnormalised
+    int64 triangle and of the normalised fp64 one, the SURVEY 8c known-answer blocks and sampled cells, all produced once by
+    the unmodified reference (tests/golden/make_fingerprints.py)."""
+    import hashlib
+    import json
+    from fastsk_b200 import FastaUtility
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fingerprints.json")
+    fp = json.load(open(path))[name]
+    if acc_path == 3 and name == "1.1":
+        pytest.skip("20 key bits: not eligible for the dense path")
+    fu = FastaUtility()
+    from conftest import DATA_DIR
+    tr, _ = fu.read_data(os.path.join(DATA_DIR, name + ".train.fasta"))
+    te, _ = fu.read_data(os.path.join(DATA_DIR, name + ".test.fasta"))
+    assert (len(tr), len(te)) == (fp["n_train"], fp["n_test"])
+    f = FastSK(fp["g"], fp["m"], seed=3)                         # exact mode: any order of the combinations
+    f.set_option("acc_path", acc_path)
+    f.compute_kernel(tr, te)
+    Ki = f.get_unnormalised()
+    Kn = f.get_kernel_packed()
+    tri = lambda i, j: i * (i + 1) // 2 + j  # noqa: E731
+    assert [[int(Ki[tri(max(a, b), min(a, b))]) for b in range(3)] for a in range(3)] == fp["kat_3x3_unnormalised"]
+    assert [int(Ki[c]) for c in fp["cells"]] == fp["cells_unnormalised"]
+    assert [float(Kn[c]).hex() for c in fp["cells"]] == fp["cells_normalised_hex"]
+    assert int(Ki.sum()) == fp["sum_unnormalised"]
+    assert hashlib.sha256(Ki.tobytes()).hexdigest() == fp["sha256_unnormalised_int64"]
+    assert hashlib.sha256(Kn.tobytes()).hexdigest() == fp["sha256_normalised_f64"]
