@@ -485,18 +485,24 @@ def other_workloads(device):
     if not (os.path.exists(tr) and os.path.exists(te)):
         return None
     from fastsk_b200 import FastSK, FastaUtility
+    from fastsk_b200.fastsk import pinned_empty
     fu = FastaUtility()
-    Xtr, _ = fu.read_data(tr)
-    Xte, _ = fu.read_data(te)
-    out = {"workload": "EP300 TFBS DNA train+test (BASELINE configs[1]): 4000 sequences x 100 bp, g=10 m=6, exact, 210 combinations"}
+    ctr, otr, _ = fu.read_encoded(tr)              # flat codes + offsets: the ingest path that skips Python lists
+    cte, ote, _ = fu.read_encoded(te)
+    Xtr, Xte = (ctr, otr), (cte, ote)
+    ntr, nte = len(otr) - 1, len(ote) - 1
+    out_tr, out_te = pinned_empty((ntr, ntr)), pinned_empty((nte, ntr))
+    out = {"workload": "EP300 TFBS DNA train+test (BASELINE configs[1]): 4000 sequences x 100 bp, g=10 m=6, exact, 210 combinations; "
+                       "e2e = compute_kernel from flat arrays (FastaUtility.read_encoded) + both kernels into pinned host arrays"}
     for path, tag in ((2, "rows"), (3, "dense_tensor_core")):
         best = None
-        for _ in range(3):
+        for _ in range(4):
             f = FastSK(10, 6, seed=0, device=device, distributed=False, profile=True)
             f.set_option("acc_path", path)
             t0 = time.perf_counter()
             f.compute_kernel(Xtr, Xte)
-            Ktr = f.get_train_kernel()
+            Ktr = f.get_train_kernel(out=out_tr)
+            f.get_test_kernel(out=out_te)
             wall = time.perf_counter() - t0
             st = f.stats()
             dev_ms = st["ms_total"]
@@ -506,7 +512,7 @@ def other_workloads(device):
             if path == 3 and st["ms_accumulate"]:
                 n, kdim = st["n_seq"], 256 * st["combos_done"]
                 row["tensor_tflops"] = 2.0 * (n * (n + 128) / 2.0) * kdim / (st["ms_accumulate"] * 1e-3) / 1e12
-            if best is None or row["device_ms"] < best["device_ms"]:
+            if best is None or row["e2e_s"] < best["e2e_s"]:
                 best = row
             del f
         out[tag] = best

@@ -50,6 +50,7 @@ SIGNATURES = {
     "fsk_host_register": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t]),
     "fsk_host_unregister": (ctypes.c_int, [ctypes.c_void_p]),
     "fsk_trim_cache": (ctypes.c_int, []),
+    "fsk_selftest_division": (ctypes.c_int, [ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]),
     "fsk_set_seed": (ctypes.c_int, [_H, ctypes.c_uint64]),
     "fsk_set_combo_sequence": (ctypes.c_int, [_H, c_i32p, ctypes.c_int64]),
     "fsk_set_shard": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_int]),

@@ -108,6 +108,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) return;
+        // back off: a spinning single-lane warp (TMA producer, MMA issuer) otherwise takes issue slots from the epilogue warps
+        // of its scheduler (ncu: SYNCS + BRA + YIELD were a third of all instructions of the Welford contraction)
+        if (it > 2) __nanosleep(it < 64 ? 40 : 200);
         if (it > (1u << 22)) __trap();
     }
 }
@@ -303,14 +306,16 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restr
 // launch does what used to be one launch + one host round trip per iteration.
 constexpr int DW_STAGES = 2;
 constexpr uint32_t DW_STAGE_BYTES = 2 * DG_TILE_BYTES;
-constexpr uint32_t DW_TS_BYTES = 4 * 32 * 33 * 4;                 // one padded 32 x 32 fp32 transpose buffer per epilogue warp
+constexpr int DW_EPI_WARPS = 8;                                   // two epilogue warps per TMEM lane quarter, 64 columns each
+constexpr int DW_THREADS = 64 + 32 * DW_EPI_WARPS;                // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
+constexpr uint32_t DW_TS_BYTES = DW_EPI_WARPS * 32 * 33 * 4;      // one padded 32 x 32 fp32 transpose buffer per epilogue warp
 __host__ __device__ constexpr size_t dw_smem() { return (size_t)DW_STAGES * DW_STAGE_BYTES + DW_TS_BYTES + 1024 + 256; }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-__global__ void __launch_bounds__(DG_THREADS, 2)
+__global__ void __launch_bounds__(DW_THREADS, 2)
 syrk_tc_welford_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restrict__ tile_order, int64_t nseq, uint32_t nks,
                        const WelfordSpec* __restrict__ wf) {
     extern __shared__ uint8_t dw_smem_raw[];
@@ -331,7 +336,7 @@ syrk_tc_welford_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t*
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < DW_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, DW_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -384,63 +389,88 @@ syrk_tc_welford_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t*
         }
         __syncwarp();
     } else {
-        const uint32_t q = (uint32_t)warp & 3u;
+        // The accumulator comes out of TMEM one row per thread; it goes through a padded shared-memory transpose so that the 32
+        // lanes of a warp touch 32 CONSECUTIVE cells of one row of the packed triangle (coalesced 256-byte accesses; streaming a
+        // row per thread instead measured 40 % slower: 32 sectors per load instruction).  The 32 cells a lane owns in a
+        // 32-column chunk are fetched together and BEFORE the wait for the accumulator / the TMEM read of the chunk, so the L2
+        // round trip of the mean (the same CTA wrote it one slot ago) runs under the MMAs and the transpose.
+        // Eight epilogue warps: a warp reads the TMEM lane quarter (warp % 4) -- the hardware's rule -- and the two warps of a
+        // quarter take 64 columns each.  The running means of this path live TILE-MAJOR (tile (I, J) = 128 x 128 consecutive
+        // cells, row-major): the cell of row r, column c of the tile is at a compile-time offset from the warp's base pointer,
+        // so the inner loop has no address arithmetic at all (the packed triangle cost ~30 of 53 instructions per cell: ncu,
+        // profiles/r02_ncu_welford_*).  welford_untile_kernel adds the tiles into the packed triangle once, at the end.
+        const uint32_t q = (uint32_t)warp & 3u, half = (uint32_t)(warp - 2) >> 2;
         float* __restrict__ ts = reinterpret_cast<float*>(dw_smem_raw + (ts_base - raw)) + (warp - 2) * (32 * 33);
-        const int64_t j0 = (int64_t)J * DG_TILE;
+        const int64_t j0 = (int64_t)J * DG_TILE + half * 64;
         const int64_t ibase = (int64_t)I * DG_TILE + q * 32;
         const int64_t n_train = wf->n_train;
-        const double* __restrict__ kin = wf->khat_in[g];
-        double* __restrict__ kout = wf->khat_out[g];
+        // every cell of the warp's 32 x 64 strip is inside the triangle and the matrix (all but the diagonal and last tiles)
+        const bool inside = ibase + 31 < nseq && j0 + 63 <= ibase;
+        const bool all_train = ibase + 31 < n_train;
+        const size_t tcell = ((size_t)I * (I + 1) / 2 + J) * (size_t)(DG_TILE * DG_TILE) + (size_t)(q * 32) * DG_TILE + half * 64 + lane;
+        const double* __restrict__ kin = wf->khat_in[g] + tcell;
+        double* __restrict__ kout = wf->khat_out[g] + tcell;
         for (uint32_t d = 0; d < depth; ++d) {
             const uint32_t buf = d & 1u;
             const double* __restrict__ ksrc = d == 0 ? kin : kout;
             const double diter = (double)(wf->iter0[g] + (int32_t)d);
+            const double riter = __ddiv_rn(1.0, diter);
             double acc = 0.0;
-            // The epilogue is latency-bound (four warps per CTA walk 16 384 cells of the mean per slot), so the 32 cells a lane
-            // owns in a 32-column chunk are fetched together, BEFORE the wait for the accumulator and the TMEM read: the L2
-            // round trip of the mean runs under the MMAs and the transpose.
-            auto fetch = [&](int c0, double (&k0)[32]) {
-                const int64_t j = j0 + c0 + lane;
+            // rows r0 .. r0 + 15 of the column this lane owns in chunk c0 (cells outside the triangle hold harmless garbage)
+            auto fetch = [&](int c0, int r0, double (&k0)[16]) {
 #pragma unroll
-                for (int u = 0; u < 32; ++u) {
-                    const int64_t i = ibase + u;
-                    k0[u] = (i < nseq && j <= i) ? ksrc[(size_t)(i * (i + 1) / 2 + j)] : 0.0;
-                }
+                for (int u = 0; u < 16; ++u) k0[u] = ksrc[(r0 + u) * DG_TILE + c0];
             };
-            double k0[32];
-            fetch(0, k0);
+            double k0[16];
+            fetch(0, 0, k0);
             mbar_wait(tfull0 + 8 * buf, (d >> 1) & 1u);
             tc_fence_after();
-#pragma unroll 1
-            for (int c0 = 0; c0 < DG_TILE; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + (uint32_t)(buf * 128 + c0), v);
-                if (c0 == DG_TILE - 32) {                                     // last read of this accumulator: hand it back
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
-                }
 #pragma unroll
-                for (int c = 0; c < 32; ++c) ts[lane * 33 + c] = __uint_as_float(v[c]);
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + (uint32_t)(buf * 128 + half * 64 + c0), v);
+                    if (c0 == 32) {                                           // last read of this accumulator: hand it back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) ts[lane * 33 + c] = __uint_as_float(v[c]);
+                }
                 __syncwarp();
                 const int64_t j = j0 + c0 + lane;
 #pragma unroll
-                for (int u = 0; u < 32; ++u) {
-                    const int64_t i = ibase + u;
-                    if (i < nseq && j <= i) {
-                        const double ks = (double)__float2uint_rn(ts[u * 33 + lane]);
-                        const double delta = __dsub_rn(ks, k0[u]);
-                        const double nh = __dadd_rn(k0[u], __ddiv_rn(delta, diter));
-                        kout[(size_t)(i * (i + 1) / 2 + j)] = nh;
-                        if (i < n_train) acc = __dadd_rn(acc, __dmul_rn(delta, __dsub_rn(ks, nh)));
+                for (int r0 = 0; r0 < 32; r0 += 16) {
+                    if (inside && all_train) {
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) {
+                            const double ks = (double)ts[(r0 + u) * 33 + lane];   // an integer below 2^24: exact in fp32 and in fp64
+                            const double delta = __dsub_rn(ks, k0[u]);
+                            const double nh = __dadd_rn(k0[u], div_by_iter(delta, diter, riter));
+                            kout[(r0 + u) * DG_TILE + c0] = nh;
+                            acc = __dadd_rn(acc, __dmul_rn(delta, __dsub_rn(ks, nh)));
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) {
+                            const int64_t i = ibase + r0 + u;
+                            const double ks = (double)ts[(r0 + u) * 33 + lane];
+                            const double delta = __dsub_rn(ks, k0[u]);
+                            const double nh = __dadd_rn(k0[u], div_by_iter(delta, diter, riter));
+                            kout[(r0 + u) * DG_TILE + c0] = nh;
+                            if (i < n_train && j <= i) acc = __dadd_rn(acc, __dmul_rn(delta, __dsub_rn(ks, nh)));   // (n_train <= nseq)
+                        }
                     }
+                    // the next 16 rows (or the next chunk's first 16) are in flight under this half's stores and the next TMEM read
+                    if (r0 == 0) fetch(c0, 16, k0);
+                    else if (c0 == 0) fetch(32, 0, k0);
                 }
-                if (c0 + 32 < DG_TILE) fetch(c0 + 32, k0);                    // (in flight under the next TMEM read + transpose)
                 __syncwarp();
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-            if (lane == 0) wf->sums[(size_t)(slot0 + d) * wf->sums_stride + (size_t)blockIdx.x * 4 + q] = acc;
+            if (lane == 0) wf->sums[(size_t)(slot0 + d) * wf->sums_stride + (size_t)blockIdx.x * 8 + half * 4 + q] = acc;
         }
     }
     tc_fence_before();
@@ -448,6 +478,21 @@ syrk_tc_welford_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t*
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+    }
+}
+
+// dst (packed lower triangle) += src (tile-major running mean of one stream): Ksfinal += K_hat (fastsk_kernel.cpp:296-313)
+__global__ void __launch_bounds__(256)
+welford_untile_kernel(double* __restrict__ dst, const double* __restrict__ src, const uint32_t* __restrict__ tile_order, int64_t nseq) {
+    const uint32_t ij = tile_order[blockIdx.x];
+    const int64_t I = ij >> 16, J = ij & 0xffffu;
+    const double* __restrict__ t = src + ((size_t)I * (I + 1) / 2 + J) * (size_t)(DG_TILE * DG_TILE);
+    for (int e = threadIdx.x; e < DG_TILE * DG_TILE; e += 256) {
+        const int64_t i = I * DG_TILE + (e >> 7), j = J * DG_TILE + (e & 127);
+        if (i < nseq && j <= i) {
+            const size_t p = (size_t)(i * (i + 1) / 2 + j);
+            dst[p] = __dadd_rn(dst[p], t[e]);
+        }
     }
 }
 

@@ -64,6 +64,33 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v));
 }
 
+// a / b, correctly rounded, for the Welford step's division by the iteration number (fastsk_kernel.cpp:124: K_hat += d / iter):
+// with rb = RN(1 / b) computed once per slot, q0 = RN(a * rb) is within one ulp of the quotient, the remainder a - q0 * b is
+// exact in one FMA, and q0 + rem * rb rounds to RN(a / b) (Markstein's theorem; b is a small positive integer, so its
+// significand is never the all-ones exception).  ~4 instructions instead of the ~45 of the general division routine, same
+// bits: fsk_selftest_division compares the two on the device.
+__device__ __forceinline__ double div_by_iter(double a, double b, double rb) {
+    const double q0 = __dmul_rn(a, rb);
+    const double rem = __fma_rn(-q0, b, a);
+    return __fma_rn(rem, rb, q0);
+}
+__global__ void division_selftest_kernel(uint64_t seed, uint64_t n, unsigned long long* __restrict__ mismatches) {
+    unsigned long long bad = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t x = (i + 1) * 0x9E3779B97F4A7C15ull + seed;                 // splitmix64
+        x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull; x ^= x >> 31;
+        uint64_t y = (x + 0x9E3779B97F4A7C15ull); y = (y ^ (y >> 30)) * 0xBF58476D1CE4E5B9ull; y = (y ^ (y >> 27)) * 0x94D049BB133111EBull; y ^= y >> 31;
+        const double b = (double)(1 + (x % ((i & 7) == 0 ? 2000000000ull : 4096ull)));       // iteration numbers
+        // numerators: integers (counts minus a mean), fractions of every magnitude, both signs
+        double a = (double)(int64_t)(y >> ((i >> 3) & 31)) * (((i >> 8) & 1) ? 1.0 : 1.0 / 1048576.0);
+        if ((i >> 9) & 1) a = -a;
+        if ((i & 0xff) == 0) a = __longlong_as_double((long long)((y & 0x800fffffffffffffull) | ((uint64_t)(1023 + (int)(x % 200) - 100) << 52)));
+        const double rb = __ddiv_rn(1.0, b);
+        if (__double_as_longlong(div_by_iter(a, b, rb)) != __double_as_longlong(__ddiv_rn(a, b))) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 // exclusive scan of one value per thread over a 256-thread block; `total` gets the block sum
 __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* warp_sums /* >= 8 */, uint32_t& total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -749,6 +776,7 @@ struct DirSpec {
     const uint2* tdir;           // [slot][block][key]
     int bshift, keybits;
     uint32_t nb;
+    uint32_t pf_stride;          // experiment: 64 = one L2 prefetch per 64 bytes of a task's id range instead of per 128-byte line
 };
 template <typename AccT, typename IdT, int UNROLL, bool PREFETCH = true, bool DIR = false>
 __global__ void __launch_bounds__(1024)
@@ -850,9 +878,15 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
         if (PREFETCH && q1.y) {                      // per-lane prefetches (the bulk form is warp-uniform: 32 serial issues)
             const char* p = reinterpret_cast<const char*>(ids_g + (size_t)(c1 / cps) * ids_stride) + (size_t)q1.x * 16;
             const uint32_t bytes = q1.y * (uint32_t)sizeof(IdT);
+            if (dir.pf_stride == 64u) {
 #pragma unroll
-            for (uint32_t o = 0; o < PF_LINES * PF_STRIDE; o += PF_STRIDE)
-                if (bytes > o + PF_SKIP) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+                for (uint32_t o = 0; o < PF_LINES * PF_STRIDE; o += 64u)
+                    if (bytes > o) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+            } else {
+#pragma unroll
+                for (uint32_t o = 0; o < PF_LINES * PF_STRIDE; o += PF_STRIDE)
+                    if (bytes > o + PF_SKIP) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+            }
             // long ranges (skewed inputs): up to PF_REACH bytes; the uniform workload never gets here
             for (uint32_t o = PF_LINES * PF_STRIDE; o < min(bytes, PF_REACH); o += PF_STRIDE)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
@@ -906,13 +940,14 @@ accumulate_rows_kernel(const IdT* __restrict__ ids, size_t ids_stride, const uin
         const double* __restrict__ kin = (phase == 0 ? wf->khat_in[group] : wf->khat_out[group]) + roff;
         double* __restrict__ kout = wf->khat_out[group] + roff;
         const double diter = (double)(wf->iter0[group] + (int32_t)phase);
+        const double riter = __ddiv_rn(1.0, diter);
         const bool train = (int64_t)b < wf->n_train;
         double acc = 0.0;
         for (uint32_t i = threadIdx.x; i < ncols; i += blockDim.x) {
             const double ks = (double)row[i];
             const double k0 = kin[i];
             const double delta = __dsub_rn(ks, k0);
-            const double nh = __dadd_rn(k0, __ddiv_rn(delta, diter));
+            const double nh = __dadd_rn(k0, div_by_iter(delta, diter, riter));
             kout[i] = nh;
             row[i] = 0;
             if (train) acc = __dadd_rn(acc, __dmul_rn(delta, __dsub_rn(ks, nh)));
@@ -1071,6 +1106,7 @@ welford_kernel(AccT* __restrict__ Ks, double* __restrict__ K_hat, int64_t n_pair
                double* __restrict__ block_sums) {
     __shared__ double ws[8];
     const double diter = (double)iter;
+    const double riter = __ddiv_rn(1.0, diter);
     double acc = 0.0;
     // four independent element loads per array in flight per thread; a thread still visits its elements in increasing
     // order, so the per-thread partial sums (and the result) do not depend on the unrolling
@@ -1088,7 +1124,7 @@ welford_kernel(AccT* __restrict__ Ks, double* __restrict__ K_hat, int64_t n_pair
             const int64_t q = p + u * stride;
             Ks[q] = 0;
             const double delta = __dsub_rn(ks[u], kh[u]);
-            const double nh = __dadd_rn(kh[u], __ddiv_rn(delta, diter));
+            const double nh = __dadd_rn(kh[u], div_by_iter(delta, diter, riter));
             K_hat[q] = nh;
             if (q < n_train_pairs) acc = __dadd_rn(acc, __dmul_rn(delta, __dsub_rn(ks[u], nh)));
         }
@@ -1098,7 +1134,7 @@ welford_kernel(AccT* __restrict__ Ks, double* __restrict__ K_hat, int64_t n_pair
         Ks[p] = 0;
         double kh = K_hat[p];
         const double delta = __dsub_rn(ks, kh);
-        kh = __dadd_rn(kh, __ddiv_rn(delta, diter));
+        kh = __dadd_rn(kh, div_by_iter(delta, diter, riter));
         K_hat[p] = kh;
         if (p < n_train_pairs) acc = __dadd_rn(acc, __dmul_rn(delta, __dsub_rn(ks, kh)));
     }

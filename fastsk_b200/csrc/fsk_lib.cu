@@ -125,6 +125,8 @@ struct fsk_handle {
     uint32_t dir_nb = 0;
     uint16_t* d_wkey = nullptr;
     uint2* d_tdir[2] = {nullptr, nullptr};
+    int opt_fit_smem = 1;                              // accumulate launches ask for the shared memory of their longest row only
+    int opt_pf_stride = 128;                           // L2 prefetch granularity of the accumulate's id ranges (64 or 128 bytes)
     int opt_seg_lean = 0;                              // 0 auto (on for records that carry the id), 1 off, 2 on: register-blocked segmentation
     bool lean_seg = false;
     uint32_t lean_tiles = 0;
@@ -575,8 +577,12 @@ int launch_accumulate(fsk_handle* h, int nb, unsigned long long* K, size_t slot_
                         : h->opt_acc_unroll == 4 ? accumulate_rows_kernel<unsigned long long, IdT, 4>
                                                  : accumulate_rows_kernel<unsigned long long, IdT, 2>;
             DirSpec dir;
-            dir.wkey = h->d_wkey; dir.tdir = h->d_tdir[h->buf]; dir.bshift = h->dir_bshift; dir.keybits = h->keybits; dir.nb = h->dir_nb;
-            kern<<<grid, h->rows_threads, h->rows_smem, h->ls>>>(
+            dir.wkey = h->d_wkey; dir.tdir = h->d_tdir[h->buf]; dir.bshift = h->dir_bshift; dir.keybits = h->keybits; dir.nb = h->dir_nb; dir.pf_stride = (uint32_t)h->opt_pf_stride;
+            // shared memory of the launch = its longest row (the launches walk the rows from the longest down): the shorter half of
+            // the rows then fits two CTAs per SM
+            const size_t smem_launch = h->opt_fit_smem ? std::min(h->rows_smem, (size_t)(std::min<int64_t>(hi - col0 + 1, h->col_width) + 32) * 4)
+                                                       : h->rows_smem;
+            kern<<<grid, h->rows_threads, smem_launch, h->ls>>>(
                 ids, h->ids_stride, h->d_task[h->buf], h->d_woff32, n, (uint32_t)hi, per_group, K, slot_stride,
                 h->wf_active ? h->d_wf : nullptr, (uint32_t)col0, (uint32_t)h->col_width, (uint32_t)(win * h->N), h->d_heavy_bits,
                 h->heavy_bits_stride, dir);
@@ -613,7 +619,7 @@ int run_batch_dense(fsk_handle* h, int nb, const BatchSpec& spec, unsigned long 
         const unsigned T = (unsigned)((h->N + DG_TILE - 1) / DG_TILE);
         const unsigned tiles = T * (T + 1) / 2;
         if (h->wf_active) {   // variance mode: every stream's tiles walk the stream's slots in order (Welford in the epilogue)
-            syrk_tc_welford_kernel<<<dim3(tiles, (unsigned)h->wf_groups), DG_THREADS, dw_smem(), h->ls>>>(h->tmap_C, h->d_tile_order, h->N, h->nks, h->d_wf);
+            syrk_tc_welford_kernel<<<dim3(tiles, (unsigned)h->wf_groups), DW_THREADS, dw_smem(), h->ls>>>(h->tmap_C, h->d_tile_order, h->N, h->nks, h->d_wf);
             h->launches++;
         } else {
             for (int c0 = 0; c0 < nb; c0 += h->dense_chunk) {
@@ -960,7 +966,7 @@ void sync_team(fsk_handle* h) {
         w->opt_acc_prefetch = h->opt_acc_prefetch; w->opt_acc_unroll = h->opt_acc_unroll; w->opt_wave = h->opt_wave;
         w->profile = h->profile; w->opt_pad = h->opt_pad; w->opt_acc_cols = h->opt_acc_cols; w->opt_heavy_tau = h->opt_heavy_tau;
         w->opt_ids32 = h->opt_ids32; w->opt_gemm_shape = h->opt_gemm_shape; w->opt_heavy_cap = h->opt_heavy_cap;
-        w->opt_seg_lean = h->opt_seg_lean; w->opt_spec_depth = h->opt_spec_depth;
+        w->opt_seg_lean = h->opt_seg_lean; w->opt_spec_depth = h->opt_spec_depth; w->opt_pf_stride = h->opt_pf_stride; w->opt_fit_smem = h->opt_fit_smem;
         w->opt_seg_dir = h->opt_seg_dir; w->opt_dir_blocks = h->opt_dir_blocks; w->opt_count_updates = h->opt_count_updates;
     }
 }
@@ -1099,6 +1105,11 @@ int fsk_set_option(fsk_handle* h, const char* key, int64_t value) {
     } else if (!strcmp(key, "seg_dir")) {
         if (value < 0 || value > 2) return fail(h, FSK_EINVAL, "seg_dir must be 0 (auto), 1 (off) or 2 (on)");
         h->opt_seg_dir = (int)value;
+    } else if (!strcmp(key, "fit_smem")) {
+        h->opt_fit_smem = value != 0;
+    } else if (!strcmp(key, "pf_stride")) {
+        if (value != 64 && value != 128) return fail(h, FSK_EINVAL, "pf_stride must be 64 or 128");
+        h->opt_pf_stride = (int)value;
     } else if (!strcmp(key, "spec_depth")) {
         if (value < 0 || value > MAX_BATCH) return fail(h, FSK_EINVAL, "spec_depth must be in [0, %d]", MAX_BATCH);
         h->opt_spec_depth = (int)value;
@@ -1552,7 +1563,7 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         // partial sums of the variance per slot: one per Welford block, per row (fused flush of the row path) or per epilogue
         // warp of every tile (fused epilogue of the dense path)
         const int64_t Tt = (N + DG_TILE - 1) / DG_TILE;
-        h->sums_stride = (uint32_t)std::max<int64_t>(WELFORD_BLOCKS, h->dense_path ? 2 * Tt * (Tt + 1) : N * h->col_windows);
+        h->sums_stride = (uint32_t)std::max<int64_t>(WELFORD_BLOCKS, h->dense_path ? 4 * Tt * (Tt + 1) : N * h->col_windows);
         ALLOC(h->d_block_sums, (size_t)B * h->sums_stride);
         ALLOC(h->d_var, B);
         ALLOC(h->d_wf, 1);
@@ -1682,20 +1693,23 @@ int build_partial_once(fsk_handle* h) {
         shard_work(h, my_streams);
         const bool fused_wf = h->rows_path || h->dense_path;
         const bool pingpong = fused_wf && h->wf_depth > 1;
+        // (the tensor-core path keeps its running means tile-major: 128 x 128 cells per lower-triangle tile, fsk_dense.cuh)
+        const int64_t Ttiles = (h->N + DG_TILE - 1) / DG_TILE;
+        const size_t khat_elems = h->dense_path ? (size_t)(Ttiles * (Ttiles + 1) / 2) * (size_t)(DG_TILE * DG_TILE) : (size_t)h->n_pairs;
         if (!my_streams.empty()) {   // one allocation for the running means of all local streams (cudaMalloc/cudaFree are slow)
             double* all;
-            const size_t per = (size_t)h->n_pairs * (pingpong ? 2 : 1);
+            const size_t per = khat_elems * (pingpong ? 2 : 1);
             ALLOC(all, per * my_streams.size());
             h->d_Khat.push_back(all);
             CU(cudaMemsetAsync(all, 0, sizeof(double) * per * my_streams.size(), h->stream));
             for (size_t i = 0; i < my_streams.size(); ++i) {
                 double* c = all + i * per;
-                streams.push_back({my_streams[i], my_streams[i], 1, true, c, pingpong ? c + h->n_pairs : c, 0, 0});
+                streams.push_back({my_streams[i], my_streams[i], 1, true, c, pingpong ? c + khat_elems : c, 0, 0});
             }
         }
         std::vector<double> var_host((size_t)h->B);
         const int64_t Tt = (h->N + DG_TILE - 1) / DG_TILE;
-        const int n_sums = !fused_wf ? WELFORD_BLOCKS : (h->dense_path ? (int)(2 * Tt * (Tt + 1)) : (int)(h->N * h->col_windows));
+        const int n_sums = !fused_wf ? WELFORD_BLOCKS : (h->dense_path ? (int)(4 * Tt * (Tt + 1)) : (int)(h->N * h->col_windows));
         // one launch group: the given streams, stream i running its next depth[i] iterations
         auto run_round = [&](const std::vector<Stream*>& grp, int nslots) -> int {
             int32_t combos[MAX_BATCH];
@@ -1791,7 +1805,8 @@ int build_partial_once(fsk_handle* h) {
         }
         // merge (fastsk_kernel.cpp:296-313): sum of the streams' running means, in stream order
         for (auto& s : streams) {
-            add_f64_kernel<<<592, 256, 0, h->stream>>>(h->d_Kf, s.cur, h->n_pairs);
+            if (h->dense_path) welford_untile_kernel<<<(unsigned)(Ttiles * (Ttiles + 1) / 2), 256, 0, h->stream>>>(h->d_Kf, s.cur, h->d_tile_order, h->N);
+            else add_f64_kernel<<<592, 256, 0, h->stream>>>(h->d_Kf, s.cur, h->n_pairs);
             h->launches++;
         }
         CU(cudaGetLastError());
@@ -2083,6 +2098,20 @@ int fsk_host_register(void* p, size_t bytes) {
 int fsk_host_unregister(void* p) {
     cudaHostUnregister(p);
     cudaGetLastError();
+    return FSK_OK;
+}
+int fsk_selftest_division(int device, uint64_t seed, uint64_t n, uint64_t* mismatches) {
+    if (!mismatches) return FSK_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); g_create_error = "no usable CUDA device"; return FSK_ECUDA; }
+    unsigned long long* d = nullptr;
+    if (cudaMalloc((void**)&d, sizeof *d) != cudaSuccess) { cudaGetLastError(); return FSK_ENOMEM; }
+    cudaMemset(d, 0, sizeof *d);
+    division_selftest_kernel<<<148 * 8, 256>>>(seed, n, d);
+    unsigned long long hm = 0;
+    const cudaError_t e = cudaMemcpy(&hm, d, sizeof hm, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { cudaGetLastError(); g_create_error = std::string("division self-test failed: ") + cudaGetErrorString(e); return FSK_ECUDA; }
+    *mismatches = hm;
     return FSK_OK;
 }
 int fsk_trim_cache(void) {

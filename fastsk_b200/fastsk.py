@@ -420,6 +420,104 @@ class FastSK:
         self._call("fsk_get_stats", ctypes.byref(st))
         return st.as_dict()
 
+    # ------------------------------------------------------------------ learner hand-off on the device
+    def fit_linear_gpu(self, Ytrain, C=1.0, tol=1e-6, max_newton=60, max_cg=200):
+        """The reference's real consumer -- a linear SVM on the ROWS of the train kernel (empirical kernel map,
+        test/run_check.py:48-61, examples/run.py:113-118) -- trained on the device-resident kernel, so the n_train x n_train
+        matrix never crosses PCIe (16 GB at N = 50 000).  Same model as ``LinearSVC(C=C)`` (L2-regularised squared hinge,
+        intercept as a regularised constant feature): minimise 1/2 |w|^2 + C sum_i max(0, 1 - y_i (K_i . w))^2 by a
+        trust-region-free Newton method with conjugate gradients (every product is one fp64 GEMV over the kernel).  torch is
+        used for the GEMVs only.  Needs all train rows on this handle's device (not a sharded finalisation)."""
+        import torch
+        if self._sharded:
+            raise RuntimeError("fit_linear_gpu needs the whole train kernel on one device (reduce='allreduce' under torchrun)")
+        K = self.get_train_kernel_tensor()
+        n = K.shape[0]
+        y = torch.as_tensor(np.where(np.asarray(Ytrain).ravel() > 0, 1.0, -1.0), dtype=torch.float64, device=K.device)
+        if y.numel() != n:
+            raise ValueError("Ytrain has %d labels for %d train sequences" % (y.numel(), n))
+        w = torch.zeros(n + 1, dtype=torch.float64, device=K.device)          # [weights | intercept]
+
+        def X(v):          # rows of [K | 1] times v
+            return K @ v[:n] + v[n]
+
+        def XT(u):
+            return torch.cat([K.t() @ u, u.sum().reshape(1)])
+
+        def objective(wv, z):
+            return 0.5 * float(wv @ wv) + C * float(torch.clamp(1 - y * z, min=0).pow(2).sum())
+
+        z = X(w)
+        f = objective(w, z)
+        for _ in range(max_newton):
+            act = (1 - y * z) > 0
+            a = act.to(torch.float64)
+            grad = w + 2 * C * XT(a * (z - y))
+            gn = float(grad.norm())
+            if gn <= tol * max(1.0, float(n) ** 0.5):
+                break
+            # Newton direction: (I + 2C X_I^T X_I) d = -grad, by conjugate gradients
+            d = torch.zeros_like(w)
+            r = -grad.clone()
+            p = r.clone()
+            rs = float(r @ r)
+            for _ in range(max_cg):
+                Hp = p + 2 * C * XT(a * X(p))
+                alpha = rs / float(p @ Hp)
+                d += alpha * p
+                r -= alpha * Hp
+                rs_new = float(r @ r)
+                if rs_new ** 0.5 <= 0.1 * gn:
+                    break
+                p = r + (rs_new / rs) * p
+                rs = rs_new
+            Xd = X(d)
+            step, gd = 1.0, float(grad @ d)
+            while True:                                  # backtracking on the exact objective
+                z_new = z + step * Xd
+                f_new = objective(w + step * d, z_new)
+                if f_new <= f + 1e-4 * step * gd or step < 1e-10:
+                    break
+                step *= 0.5
+            w, z = w + step * d, z_new
+            if f - f_new <= 1e-12 * max(1.0, abs(f)):
+                f = f_new
+                break
+            f = f_new
+        self._w_gpu = w
+        return self
+
+    def decision_function_gpu(self, which="test"):
+        """K_test . w + b (or the train rows) as a device tensor."""
+        if getattr(self, "_w_gpu", None) is None:
+            raise RuntimeError("decision_function_gpu called before fit_linear_gpu")
+        K = self.get_test_kernel_tensor() if which == "test" else self.get_train_kernel_tensor()
+        n = K.shape[1]
+        return K @ self._w_gpu[:n] + self._w_gpu[n]
+
+    def score_gpu(self, Ytest, metric="auc"):
+        """Accuracy (a percentage, like fastsk.cpp:505,529) or AUC of the device-trained SVM; only n_test scores cross PCIe."""
+        if metric not in ("accuracy", "auc"):
+            raise ValueError("metric argument must be 'accuracy' or 'auc'")
+        s = self.decision_function_gpu("test").cpu().numpy()
+        yt = np.where(np.asarray(Ytest).ravel() > 0, 1, 0)
+        if metric == "accuracy":
+            return 100.0 * float(((s > 0).astype(int) == yt).mean())
+        order = np.argsort(s, kind="mergesort")            # AUC by ranks (ties get the average rank)
+        ranks = np.empty(len(s), dtype=np.float64)
+        ss = s[order]
+        i = 0
+        while i < len(ss):
+            j = i
+            while j + 1 < len(ss) and ss[j + 1] == ss[i]:
+                j += 1
+            ranks[order[i:j + 1]] = 0.5 * (i + j) + 1
+            i = j + 1
+        npos, nneg = int(yt.sum()), int(len(yt) - yt.sum())
+        if npos == 0 or nneg == 0:
+            raise ValueError("AUC needs both classes in Ytest")
+        return float((ranks[yt == 1].sum() - npos * (npos + 1) / 2) / (npos * nneg))
+
     # ------------------------------------------------------------------ learner hand-off
     def set_labels(self, Ytrain, Ytest=None):
         self._labels = (None if Ytrain is None else np.asarray(Ytrain).ravel(),

@@ -162,6 +162,9 @@ int fsk_host_free(void* p);
 int fsk_host_register(void* p, size_t bytes);
 int fsk_host_unregister(void* p);
 int fsk_trim_cache(void);
+/* self-test: the variance mode divides by the iteration number with a reciprocal + two fused multiply-adds instead of the
+ * general division routine; this compares the two on `n` pseudo-random operand pairs on the device (must report 0) */
+int fsk_selftest_division(int device, uint64_t seed, uint64_t n, uint64_t* mismatches);
 
 /* ---- statistics --------------------------------------------------------------------------- */
 

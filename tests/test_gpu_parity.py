@@ -676,3 +676,38 @@ def test_full_bundled_sets_against_the_reference_fingerprints(FastSK, name, acc_
     assert int(Ki.sum()) == fp["sum_unnormalised"]
     assert hashlib.sha256(Ki.tobytes()).hexdigest() == fp["sha256_unnormalised_int64"]
     assert hashlib.sha256(Kn.tobytes()).hexdigest() == fp["sha256_normalised_f64"]
+
+
+def test_linear_svm_on_the_device_matches_liblinear(FastSK):
+    """fit_linear_gpu (Newton + CG on the device-resident kernel rows) solves the objective of LinearSVC(C=1): the decision
+    values on the test rows agree with liblinear's, and the AUC passes the reference's acceptance bar (test/run_check.py:64)."""
+    from sklearn.metrics import roc_auc_score
+    from sklearn.svm import LinearSVC
+    from fastsk_b200 import FastaUtility
+    from conftest import DATA_DIR
+    fu = FastaUtility()
+    tr, ytr = fu.read_data(os.path.join(DATA_DIR, "EP300.train.fasta"))
+    te, yte = fu.read_data(os.path.join(DATA_DIR, "EP300.test.fasta"))
+    tr, ytr, te, yte = tr[::3], ytr[::3], te[::5], yte[::5]                 # (the files list one class after the other)
+    f = FastSK(10, 6, seed=0)
+    f.compute_kernel(tr, te)
+    f.fit_linear_gpu(ytr, C=1.0)
+    s_gpu = f.decision_function_gpu().cpu().numpy()
+    svc = LinearSVC(C=1.0, tol=1e-8, max_iter=200000).fit(f.get_train_kernel(), ytr)
+    s_cpu = svc.decision_function(f.get_test_kernel())
+    assert np.corrcoef(s_gpu, s_cpu)[0, 1] > 0.9999
+    assert np.abs(s_gpu - s_cpu).max() < 5e-3 * max(1.0, np.abs(s_cpu).max())
+    auc = f.score_gpu(yte, "auc")
+    assert abs(auc - roc_auc_score(yte, s_cpu)) < 1e-3 and auc >= 0.9
+    assert 50.0 < f.score_gpu(yte, "accuracy") <= 100.0
+
+
+def test_division_by_the_iteration_number_is_correctly_rounded():
+    """The Welford step's d / iter uses a reciprocal and two FMAs (div_by_iter); it must give the bits of the IEEE division."""
+    import ctypes
+    from fastsk_b200 import _lib
+    lib = _lib.load()
+    bad = ctypes.c_uint64(123)
+    for seed in (1, 2, 3):
+        assert lib.fsk_selftest_division(0, seed, 200_000_000, ctypes.byref(bad)) == 0
+        assert bad.value == 0
