@@ -1034,14 +1034,20 @@ __device__ __forceinline__ double norm_entry(double v, double di, double dj) {
 // square block rows [r0, r0+nr) x cols [0, nc) of the symmetric matrix -> out (row-major, ld = nc).
 // 32x32 tiles; tiles above the diagonal are read transposed through shared memory so that the
 // packed triangle is always read along its contiguous direction.
+// Two launches: pass 0 does the tiles on or below the diagonal with the tile COLUMN in blockIdx.x (neighbouring CTAs walk
+// along a row of K), pass 1 the tiles above it with the tile ROW in blockIdx.x (neighbouring CTAs read neighbouring 256-byte
+// pieces of the SAME rows j of K: 8 x 157 of them in a row at 8 ranks instead of 256 bytes here and there -- the mirrored
+// half is most of rank 0's share, and it is read from seven peers over NVLink).
 template <typename T>
 __global__ void __launch_bounds__(256)
 normalise_block_kernel(const __grid_constant__ PeerParts<T> parts, const double* __restrict__ diag, int64_t r0, int64_t nr, int64_t nc,
-                       double* __restrict__ out) {
+                       double* __restrict__ out, int pass) {
     __shared__ double tile[32][33];
-    const int64_t ti = (int64_t)blockIdx.y * 32, tj = (int64_t)blockIdx.x * 32;   // tile origin (row offset within block, col)
+    // tile origin (row offset within block, col)
+    const int64_t ti = (int64_t)(pass ? blockIdx.x : blockIdx.y) * 32, tj = (int64_t)(pass ? blockIdx.y : blockIdx.x) * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const bool upper = (r0 + ti + 31) < tj;   // whole tile strictly above the diagonal: read mirrored
+    if (upper != (pass != 0)) return;
     if (!upper) {
         for (int y = ty; y < 32; y += 8) {
             const int64_t i = r0 + ti + y, j = tj + tx;

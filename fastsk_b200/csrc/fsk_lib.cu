@@ -9,6 +9,10 @@
 #include "fsk_segment.cuh"
 
 #include <algorithm>
+#if defined(__linux__)
+#include <sys/syscall.h>
+#include <unistd.h>
+#endif
 #include <chrono>
 #include <cstdlib>
 #include <cmath>
@@ -226,11 +230,13 @@ struct DevCache {
     std::multimap<std::pair<int, size_t>, void*> free_blocks;       // (device, bytes) -> block
     std::unordered_map<void*, std::pair<int, size_t>> live;
     size_t cached_bytes = 0;
-    void trim(int device) {                                           // device < 0: all devices (caller holds mu)
+    std::unordered_map<void*, int> exported;                         // blocks other processes may have mapped (CUDA IPC)
+    void trim(int device, bool exported_too = false) {                // device < 0: all devices (caller holds mu)
         int cur = 0;
         cudaGetDevice(&cur);
         for (auto it = free_blocks.begin(); it != free_blocks.end();) {
-            if (device < 0 || it->first.first == device) {
+            // a block whose IPC handle went out stays allocated until fsk_trim_cache: a peer may still have it mapped
+            if ((device < 0 || it->first.first == device) && (exported_too || !exported.count(it->second))) {
                 cudaSetDevice(it->first.first);
                 cudaFree(it->second);
                 cached_bytes -= it->first.second;
@@ -334,7 +340,6 @@ void release_device(fsk_handle* h) {
     dev_free(h->d_Kint); dev_free(h->d_Kf);
     for (auto& p : h->d_Khat) dev_free(p);
     h->d_Khat.clear();
-    for (void* q : h->ipc_opened) cudaIpcCloseMemHandle(q);
     h->ipc_opened.clear();
     h->peer_parts.clear();
     h->sharded = false;
@@ -866,14 +871,16 @@ int finalize_typed(fsk_handle* h, const T* K) {
     const PeerParts<T> parts = make_parts<T>(h, K);
     diag_kernel<T><<<(unsigned)((h->N + 255) / 256), 256, 0, h->stream>>>(parts, h->N, h->d_diag);
     h->launches++;
+    const unsigned tcols = (unsigned)((h->n_train + 31) / 32);
     if (h->tr_nr > 0) {
-        dim3 gtrain((unsigned)((h->n_train + 31) / 32), (unsigned)((h->tr_nr + 31) / 32));
-        normalise_block_kernel<T><<<gtrain, 256, 0, h->stream>>>(parts, h->d_diag, h->tr_r0, h->tr_nr, h->n_train, h->d_train);
-        h->launches++;
+        const unsigned trows = (unsigned)((h->tr_nr + 31) / 32);
+        normalise_block_kernel<T><<<dim3(tcols, trows), 256, 0, h->stream>>>(parts, h->d_diag, h->tr_r0, h->tr_nr, h->n_train, h->d_train, 0);
+        normalise_block_kernel<T><<<dim3(trows, tcols), 256, 0, h->stream>>>(parts, h->d_diag, h->tr_r0, h->tr_nr, h->n_train, h->d_train, 1);
+        h->launches += 2;
     }
-    if (h->te_nr > 0) {
-        dim3 gtest((unsigned)((h->n_train + 31) / 32), (unsigned)((h->te_nr + 31) / 32));
-        normalise_block_kernel<T><<<gtest, 256, 0, h->stream>>>(parts, h->d_diag, h->n_train + h->te_r0, h->te_nr, h->n_train, h->d_test);
+    if (h->te_nr > 0) {       // (test rows lie below every train column: no mirrored tiles)
+        const unsigned trows = (unsigned)((h->te_nr + 31) / 32);
+        normalise_block_kernel<T><<<dim3(tcols, trows), 256, 0, h->stream>>>(parts, h->d_diag, h->n_train + h->te_r0, h->te_nr, h->n_train, h->d_test, 0);
         h->launches++;
     }
     CU(cudaGetLastError());
@@ -898,8 +905,15 @@ int build_one(fsk_handle* h);
 int finalize_one(fsk_handle* h);
 int sync_one(fsk_handle* h);
 void* own_part(const fsk_handle* h) { return h->variance_mode ? (void*)h->d_Kf : (void*)h->d_Kint; }
+// Peer mappings opened with cudaIpcOpenMemHandle are kept for the life of the process (until fsk_trim_cache), keyed by the
+// 64 handle bytes: mapping a 10 GB partial kernel costs ~0.1 s, the ranks' partial buffers are the same cached blocks from
+// one compute to the next, and seven such opens per compute were most of an 8-rank job's fixed cost.
+struct IpcCache {
+    std::mutex mu;
+    std::map<std::pair<int, std::string>, void*> open;     // (device, handle bytes) -> mapping
+};
+IpcCache g_ipc;
 void release_peers(fsk_handle* h) {
-    for (void* q : h->ipc_opened) cudaIpcCloseMemHandle(q);
     h->ipc_opened.clear();
     h->peer_parts.clear();
 }
@@ -1872,6 +1886,10 @@ int fsk_ipc_export_partial(fsk_handle* h, void* handle_out) {
     cudaIpcMemHandle_t mh;
     CU(cudaIpcGetMemHandle(&mh, own_part(h)));
     memcpy(handle_out, &mh, sizeof mh);
+    {
+        std::lock_guard<std::mutex> lk(g_cache.mu);
+        g_cache.exported[own_part(h)] = h->device;
+    }
     return FSK_OK;
 }
 
@@ -1886,12 +1904,21 @@ int fsk_set_peer_partials(fsk_handle* h, const void* handles, int world) {
         if (r == h->rank) { h->peer_parts[(size_t)r] = own_part(h); continue; }
         cudaIpcMemHandle_t mh;
         memcpy(&mh, (const char*)handles + (size_t)r * FSK_IPC_HANDLE_BYTES, sizeof mh);
+        const std::pair<int, std::string> key(h->device, std::string((const char*)&mh, sizeof mh));
         void* q = nullptr;
-        cudaError_t e = cudaIpcOpenMemHandle(&q, mh, cudaIpcMemLazyEnablePeerAccess);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            release_peers(h);
-            return fail(h, FSK_ECUDA, "cudaIpcOpenMemHandle of rank %d's partial kernel failed: %s", r, cudaGetErrorString(e));
+        {
+            std::lock_guard<std::mutex> lk(g_ipc.mu);
+            auto it = g_ipc.open.find(key);
+            if (it != g_ipc.open.end()) q = it->second;
+            else {
+                const cudaError_t e = cudaIpcOpenMemHandle(&q, mh, cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) {
+                    cudaGetLastError();
+                    release_peers(h);
+                    return fail(h, FSK_ECUDA, "cudaIpcOpenMemHandle of rank %d's partial kernel failed: %s", r, cudaGetErrorString(e));
+                }
+                g_ipc.open[key] = q;
+            }
         }
         h->ipc_opened.push_back(q);
         h->peer_parts[(size_t)r] = q;
@@ -2077,9 +2104,41 @@ int fsk_get_unnormalised_f64(fsk_handle* h, double* out) {
 
 /* pinned host memory for inputs and outputs (the getters and fsk_compute then run at PCIe speed, and -- in a team -- every
  * GPU copies its rows over its own link at the same time); no torch needed */
+}  // extern "C"
+namespace {
+// Pages of the big host buffers are interleaved over the NUMA nodes while they are allocated / pinned: eight GPUs copying
+// their rows at once then write to the memory of both sockets instead of one (set_mempolicy(MPOL_INTERLEAVE); a no-op where
+// the call is not permitted or there is one node).
+struct Interleave {
+    bool on = false;
+    Interleave() {
+#if defined(__linux__) && defined(SYS_set_mempolicy)
+        unsigned long mask[16];
+        memset(mask, 0, sizeof mask);
+        int nodes = 0;
+        for (int n = 0; n < 1024; ++n) {
+            char path[64];
+            snprintf(path, sizeof path, "/sys/devices/system/node/node%d", n);
+            if (access(path, F_OK) != 0) break;
+            mask[n / (8 * sizeof(unsigned long))] |= 1ul << (n % (8 * sizeof(unsigned long)));
+            ++nodes;
+        }
+        if (nodes > 1) on = syscall(SYS_set_mempolicy, 3 /* MPOL_INTERLEAVE */, mask, (unsigned long)(nodes + 1)) == 0;
+#endif
+    }
+    ~Interleave() {
+#if defined(__linux__) && defined(SYS_set_mempolicy)
+        if (on) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+#endif
+    }
+};
+}  // namespace
+extern "C" {
+
 int fsk_host_alloc(void** out, size_t bytes) {
     if (!out) return FSK_EINVAL;
     *out = nullptr;
+    Interleave il;
     const cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
     if (e != cudaSuccess) { cudaGetLastError(); g_create_error = std::string("cudaHostAlloc failed: ") + cudaGetErrorString(e); return e == cudaErrorMemoryAllocation ? FSK_ENOMEM : FSK_ECUDA; }
     return FSK_OK;
@@ -2090,6 +2149,7 @@ int fsk_host_free(void* p) {
 }
 /* make an existing host range (e.g. a shared-memory mapping all ranks write their rows into) DMA-able */
 int fsk_host_register(void* p, size_t bytes) {
+    Interleave il;
     const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
     if (e != cudaSuccess && e != cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); g_create_error = std::string("cudaHostRegister failed: ") + cudaGetErrorString(e); return FSK_ECUDA; }
     cudaGetLastError();
@@ -2115,8 +2175,14 @@ int fsk_selftest_division(int device, uint64_t seed, uint64_t n, uint64_t* misma
     return FSK_OK;
 }
 int fsk_trim_cache(void) {
+    {
+        std::lock_guard<std::mutex> lk(g_ipc.mu);
+        for (auto& kv : g_ipc.open) { cudaSetDevice(kv.first.first); cudaIpcCloseMemHandle(kv.second); }
+        g_ipc.open.clear();
+    }
     std::lock_guard<std::mutex> lk(g_cache.mu);
-    g_cache.trim(-1);
+    g_cache.trim(-1, true);
+    g_cache.exported.clear();
     return FSK_OK;
 }
 
@@ -2161,9 +2227,15 @@ int fsk_save_kernel(fsk_handle* h, const char* path) {
     for (int64_t i0 = 0; i0 < h->N && rc == FSK_OK; i0 += rows_per) {
         const int64_t nr = std::min(rows_per, h->N - i0);
         dim3 grid((unsigned)((h->N + 31) / 32), (unsigned)((nr + 31) / 32));
-        if (h->variance_mode) normalise_block_kernel<double><<<grid, 256, 0, h->stream>>>(make_parts<double>(h, h->d_Kf), h->d_diag, i0, nr, h->N, d_stage);
-        else normalise_block_kernel<unsigned long long><<<grid, 256, 0, h->stream>>>(make_parts<unsigned long long>(h, h->d_Kint), h->d_diag, i0, nr, h->N, d_stage);
-        h->launches++;
+        const dim3 grid_t(grid.y, grid.x);
+        if (h->variance_mode) {
+            normalise_block_kernel<double><<<grid, 256, 0, h->stream>>>(make_parts<double>(h, h->d_Kf), h->d_diag, i0, nr, h->N, d_stage, 0);
+            normalise_block_kernel<double><<<grid_t, 256, 0, h->stream>>>(make_parts<double>(h, h->d_Kf), h->d_diag, i0, nr, h->N, d_stage, 1);
+        } else {
+            normalise_block_kernel<unsigned long long><<<grid, 256, 0, h->stream>>>(make_parts<unsigned long long>(h, h->d_Kint), h->d_diag, i0, nr, h->N, d_stage, 0);
+            normalise_block_kernel<unsigned long long><<<grid_t, 256, 0, h->stream>>>(make_parts<unsigned long long>(h, h->d_Kint), h->d_diag, i0, nr, h->N, d_stage, 1);
+        }
+        h->launches += 2;
         cudaError_t e = cudaMemcpyAsync(rows.data(), d_stage, sizeof(double) * (size_t)nr * h->N, cudaMemcpyDeviceToHost, h->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) { rc = fail(h, FSK_ECUDA, "kernel rows copy failed: %s", cudaGetErrorString(e)); break; }

@@ -236,7 +236,16 @@ class FastSK:
             return
         # one process per GPU: every rank builds the partial kernel of its shard of the combinations
         # (virtual streams in variance mode)
+        import time
         import torch
+        trace = os.environ.get("FSK_TRACE")
+        t = [time.perf_counter()]
+
+        def lap(what):
+            if trace:
+                t.append(time.perf_counter())
+                print("[py] rank %d %s %.3f ms" % (rank, what, (t[-1] - t[-2]) * 1e3), flush=True)
+
         nccl = dist.get_backend() == "nccl"
         if nccl:
             self._call("fsk_set_device", torch.cuda.current_device())
@@ -244,14 +253,20 @@ class FastSK:
         self._call("fsk_release_peers")
         self._call("fsk_set_shard", rank, world)
         self._call("fsk_upload", cp, op, n_train, n_test)
+        lap("upload")
         self._call("fsk_build_partial")
+        lap("build_partial")
         if nccl and self._reduce == "peer" and self._exchange_peers(dist, world):
+            lap("exchange of the IPC handles + mapping")
             dist.barrier()                      # every rank's partial is complete before anybody reads it
+            lap("barrier (slowest shard)")
             self._call("fsk_finalize")          # this rank's rows, summing all partials over NVLink
+            lap("finalize (merge + normalise)")
             dist.barrier()                      # nobody resets its partial while a peer still reads it
             if not self._keep_peers:
                 self._call("fsk_release_peers")
             self._sharded = True
+            lap("closing barrier")
             return
         self.reduce_partial(self.partial_tensor(), dist)
         torch.cuda.current_stream().synchronize()

@@ -74,8 +74,10 @@ int fsk_set_shard(fsk_handle* h, int rank, int world);
  * fsk_set_peer_partials maps the other ranks' buffers over NVLink, and -- after a barrier: every rank's build must be
  * complete -- fsk_finalize then normalises only this rank's share of the output rows (fsk_output_rows), summing the partial
  * kernels of all ranks as it reads them: the merge of fastsk_kernel.cpp:285-315 fused into the normalisation, no reduced
- * copy of K, no collective library.  fsk_release_peers unmaps (also done by the next upload and by fsk_destroy); a rank
- * must not upload again or be destroyed while another rank still reads its partial (barrier first). */
+ * copy of K, no collective library.  fsk_release_peers forgets the peers (also done by the next upload and by fsk_destroy); a
+ * rank must not upload again or be destroyed while another rank still reads its partial (barrier first).  The mappings
+ * themselves are cached per process and re-used when the same buffers come back (they do: the device blocks are cached
+ * too); fsk_trim_cache closes them -- call it on every rank, after a barrier, before a rank's memory should really be freed. */
 #define FSK_IPC_HANDLE_BYTES 64
 int fsk_ipc_export_partial(fsk_handle* h, void* handle_out);
 int fsk_set_peer_partials(fsk_handle* h, const void* handles /* world x FSK_IPC_HANDLE_BYTES, rank order */, int world);
