@@ -96,8 +96,12 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Bounded wait: a protocol error must end in a trap (an error code at the next synchronise), never in a hung GPU.
+// Bounded wait: a protocol error must never hang the GPU -- and must not kill the CUDA context of the host process either
+// (a trap would).  A wait that runs out raises a device-side flag and returns; every later wait of the kernel returns at once,
+// the kernel finishes with garbage, and the host turns the flag into FSK_ECUDA at the build's next check (sort_was_unstable).
+__device__ unsigned int fsk_dev_fault = 0;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (*(volatile unsigned int*)&fsk_dev_fault) return;
     for (uint32_t it = 0;; ++it) {
         uint32_t done;
         asm volatile(
@@ -111,7 +115,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         // back off: a spinning single-lane warp (TMA producer, MMA issuer) otherwise takes issue slots from the epilogue warps
         // of its scheduler (ncu: SYNCS + BRA + YIELD were a third of all instructions of the Welford contraction)
         if (it > 2) __nanosleep(it < 64 ? 40 : 200);
-        if (it > (1u << 22)) __trap();
+        if (it > (1u << 20)) { atomicExch(&fsk_dev_fault, 1u); return; }     // ~0.2 s of back-off: far beyond any legitimate wait
     }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {

@@ -894,6 +894,15 @@ int sort_was_unstable(fsk_handle* h, bool* bad) {
     CU(cudaMemcpyAsync(&f, h->d_flag, sizeof f, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     *bad = f != 0;
+    if (h->dense_path || h->heavy_tau) {     // the tensor-core kernels' barrier waits are bounded: did one run out?
+        unsigned int fault = 0;
+        CU(cudaMemcpyFromSymbol(&fault, fsk_dev_fault, sizeof fault));
+        if (fault) {
+            const unsigned int zero = 0;
+            cudaMemcpyToSymbol(fsk_dev_fault, &zero, sizeof zero);
+            return fail(h, FSK_ECUDA, "a tensor-core kernel gave up waiting on a barrier (TMA / MMA pipeline protocol error); the result is invalid");
+        }
+    }
     return FSK_OK;
 }
 
