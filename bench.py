@@ -45,10 +45,9 @@ sys.path.insert(0, ROOT)
 
 G, M, N_SEQ, N_TRAIN, SEQ_LEN = 16, 8, 50000, 40000, 200
 METRIC, UNIT = "gkm_kernel_build_combinations_per_s", "combinations/s"
-# dram__bytes_read.sum + dram__bytes_write.sum of accumulate_rows_kernel for one batch of 96 combinations of this workload
-# (all rows in one launch, option wave=400), from the ncu --set full capture profiles/r01_ncu_accumulate_rows_batch96_prefetch.txt
-# (the L2 prefetch of whole 128-byte lines moves 195 GB where the demand loads alone moved 169 GB)
-TRAFFIC_ACC_BATCH96 = 194.906825e9 + 10.006337e9
+# dram__bytes_read.sum + dram__bytes_write.sum of accumulate_rows_kernel for one batch of 48 combinations of this workload
+# (all rows in one launch, option wave=400), from the ncu --set full capture profiles/r02_ncu_accumulate_final.txt
+TRAFFIC_ACC_BATCH48 = 97.352445e9 + 10.004478e9
 
 
 def synthetic(n=N_SEQ):
@@ -354,7 +353,7 @@ def run_b200(args):
     # of a run prefix (2 B as u16) and every batch adds each 8-byte cell of the packed triangle once (RED = read + write)
     acc_bytes = float(id_bytes) * updates + 16.0 * n_pairs * batches
     acc_s = d["ms_accumulate"] * 1e-3
-    traffic_batch = (TRAFFIC_ACC_BATCH96 - 16.0 * n_pairs) * st1["batch"] / 96.0 + 16.0 * n_pairs
+    traffic_batch = (TRAFFIC_ACC_BATCH48 - 16.0 * n_pairs) * st1["batch"] / 48.0 + 16.0 * n_pairs
     gw_bytes = 4 if G * st1["bits_per_char"] <= 32 else 8
     # pre-pass bytes per window and combination.  pack: the g-mer word and window -> sequence table are shared by all
     # slots of a batch and come from L2 (ncu: 0.07 GB of DRAM reads per batch), so its HBM traffic is the record it writes;
@@ -366,7 +365,7 @@ def run_b200(args):
     roofline = {"kernel": "accumulate_rows_kernel", "bound": "hbm", "achieved": acc_bytes / acc_s / 1e9 if acc_s else None,
                 "peak": peak, "unit": "GB/s", "frac": (acc_bytes / acc_s / 1e9 / peak) if acc_s else None,
                 "traffic": traffic_batch,
-                "traffic_unit": "bytes per batch (ncu dram read + write at batch 96; the id-stream part scaled to this batch, the 16 B x cells flush part not)",
+                "traffic_unit": "bytes per batch (ncu dram read + write at batch 48; the id-stream part scaled to this batch, the 16 B x cells flush part not)",
                 "frac_measured_traffic": (traffic_batch * batches / acc_s / 1e9 / peak) if acc_s else None,
                 "achieved_per_launch_bytes": acc_bytes / batches,
                 "peak_source": peak_src, "share_of_step": d["ms_accumulate"] / d["ms_total"] if d["ms_total"] else None,
