@@ -358,7 +358,7 @@ def run_b200(args):
     # pre-pass bytes per window and combination.  pack: the g-mer word and window -> sequence table are shared by all
     # slots of a batch and come from L2 (ncu: 0.07 GB of DRAM reads per batch), so its HBM traffic is the record it writes;
     # sort: one read + one write per pass; segment: read the sorted record, write the id (+ the task of the task-list form)
-    seg_bytes = rec + id_bytes + (8 if st1.get("seg_mode", 0) == 0 else 0)
+    seg_bytes = rec + id_bytes + (8 if (st1.get("seg_mode", 0) & 3) != 1 else 0)      # (the directory form files no task per record)
     stage_bytes = {"pack": rec, "sort": 2 * rec * st1["sort_passes"], "segment": seg_bytes}
     sort_bytes = combos_rank * nfeat * sum(stage_bytes.values())
     sort_s = (d["ms_pack"] + d["ms_sort"] + d["ms_segment"]) * 1e-3
@@ -548,7 +548,8 @@ def fasta_workload(name, g, m, device, dist=None, **kw):
         row = {"e2e_s": wall, "device_ms": st["ms_total"], "combinations_done_this_rank": st["combos_done"],
                "combinations_per_s_e2e_this_rank": st["combos_done"] / wall, "acc_path": st["acc_path"], "n_seq": st["n_seq"],
                "nfeat": st["nfeat"], "key_bits": st["key_bits"], "sort_passes": st["sort_passes"], "kernel_launches": st["kernel_launches"],
-               "stdevs": len(f.get_stdevs()), "last_stdev": (f.get_stdevs() or [None])[-1], "trace": float(np.trace(Ktr))}
+               "stdevs": len(f.get_stdevs()), "last_stdev": (f.get_stdevs() or [None])[-1], "trace": float(np.trace(Ktr)),
+               "phase_ms": {k[3:]: round(st[k], 3) for k in st if k.startswith("ms_") and k != "ms_total"}}
         if best is None or row["e2e_s"] < best["e2e_s"]:
             best = row
         del f
