@@ -21,7 +21,7 @@
 namespace fsk {
 
 constexpr int MAX_K = 32;        // kept positions per combination
-constexpr int MAX_BATCH = 192;   // combinations per launch group (BatchSpec travels in kernel-parameter space: 12.5 KB of the 32 KB)
+constexpr int MAX_BATCH = 384;   // combinations per launch group (BatchSpec travels in kernel-parameter space: 25 KB of the 32 KB)
 constexpr int MAX_PASS = 8;      // 64 key bits / 8
 constexpr int RADIX = 256;
 constexpr int SORT_THREADS = 256;

@@ -66,8 +66,9 @@ int fsk_set_seed(fsk_handle* h, uint64_t seed);
  * getCombinations, shared.cpp:347-360).  n may be smaller than C(g,m).  n == 0 clears it. */
 int fsk_set_combo_sequence(fsk_handle* h, const int32_t* combos, int64_t n);
 /* Multi-GPU: this handle builds shard `rank` of `world` (combinations in the integer modes,
- * virtual streams in the variance mode).  Default 0 of 1.  The caller sums the partial
- * buffers of all ranks (one NCCL reduction) between fsk_build_partial and fsk_finalize. */
+ * virtual streams in the variance mode).  Default 0 of 1.  Between fsk_build_partial and fsk_finalize
+ * the caller either hands every rank the others' partial buffers (fsk_set_peer_partials: the merge then
+ * happens inside the normalisation, see below) or sums the buffers itself (one NCCL all-reduce). */
 int fsk_set_shard(fsk_handle* h, int rank, int world);
 /* One process per GPU (torchrun): after fsk_build_partial every rank exports its partial kernel (a CUDA IPC handle of
  * FSK_IPC_HANDLE_BYTES bytes), the caller gathers the handles of all ranks (any transport: torch.distributed, MPI, a file),

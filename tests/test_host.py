@@ -55,8 +55,8 @@ def test_option_validation_needs_no_device():
     from fastsk_b200 import FastSK
     f = FastSK(10, 6)
     for key, good, bad in (("acc_path", 3, 4), ("seg_fused", 2, 3), ("heavy_tau", -1, -2), ("heavy_cap", 128, 100),
-                           ("acc_cols", 64, 48), ("batch", 192, 193), ("seg_dir", 2, 3), ("seg_lean", 2, 3), ("dir_blocks", 64, 0),
-                           ("spec_depth", 192, 193), ("pf_stride", 64, 96)):
+                           ("acc_cols", 64, 48), ("batch", 384, 385), ("seg_dir", 2, 3), ("seg_lean", 2, 3), ("dir_blocks", 64, 0),
+                           ("spec_depth", 384, 385), ("pf_stride", 64, 96)):
         f.set_option(key, good)
         with pytest.raises(ValueError):
             f.set_option(key, bad)

@@ -18,13 +18,14 @@ for cfg in configs:
     for k, v in cfg.items():
         f.set_option(k, v)
     f._call("fsk_upload", codes.ctypes.data_as(_lib.c_i32p), offsets.ctypes.data_as(_lib.c_i64p), N_TRAIN, N_SEQ - N_TRAIN)
-    a = np.ascontiguousarray(q[:384]); b = np.ascontiguousarray(q[384:768])
-    f._call("fsk_accumulate_combos", a.ctypes.data_as(_lib.c_i32p), 384, 1)
+    NC = int(os.environ.get("NCOMB", "384"))
+    a = np.ascontiguousarray(q[:NC]); b = np.ascontiguousarray(q[NC:2 * NC])
+    f._call("fsk_accumulate_combos", a.ctypes.data_as(_lib.c_i32p), NC, 1)
     s0 = f.stats()
     t0 = time.perf_counter()
-    f._call("fsk_accumulate_combos", b.ctypes.data_as(_lib.c_i32p), 384, 1)
+    f._call("fsk_accumulate_combos", b.ctypes.data_as(_lib.c_i32p), NC, 1)
     wall = time.perf_counter() - t0
     s1 = f.stats()
     d = {k: round(s1[k] - s0[k], 2) for k in s1 if k.startswith("ms_")}
-    print(json.dumps({"cfg": cfg, "wall_ms": round(wall * 1e3, 1), "combos_per_s": round(384 / wall, 1), **d, "seg_mode": s1["seg_mode"], "batch": s1["batch"]}), flush=True)
+    print(json.dumps({"cfg": cfg, "wall_ms": round(wall * 1e3, 1), "combos_per_s": round(NC / wall, 1), **d, "seg_mode": s1["seg_mode"], "batch": s1["batch"]}), flush=True)
     del f
