@@ -1446,6 +1446,12 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         }
         h->dense_chunk = (int)std::max<int64_t>(1, std::min<int64_t>(Bsel, 16777215 / std::max<int64_t>(1, maxwin * maxwin)));
     }
+    if (h->rows_path && !h->variance_mode && h->mode != MODE_KV && maxwin <= 2048 && h->opt_heavy_tau >= 0 && h->opt_batch == 0) {
+        // the heavy-run stage needs every fp32 accumulator of its contraction below 2^24 (slots x maxwin^2): a somewhat smaller
+        // batch keeps the stage available (it is worth 6x on skewed inputs; the last 100 slots of a batch are worth < 1 %)
+        const int64_t b_heavy = (int64_t)(16777215.0 / ((double)maxwin * (double)maxwin));
+        if (b_heavy >= 64 && b_heavy < Bsel) Bsel = b_heavy;
+    }
     h->B = (int)Bsel;
     {
         // heavy runs -> tensor cores: integer modes of the row path, records that carry the sequence id, counts exact in fp16
