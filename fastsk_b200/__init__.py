@@ -4,8 +4,8 @@
 
 mirrors ``from fastsk import FastSK, FastaUtility`` (reference src/fastsk/__init__.py:1-2).
 """
-from .fastsk import FastSK
+from .fastsk import FastSK, pinned_empty, shard_rows, shared_output
 from .utils import FastaUtility, Vocabulary
 
-__version__ = "0.1"
-__all__ = ["FastSK", "FastaUtility", "Vocabulary"]
+__version__ = "0.2"
+__all__ = ["FastSK", "FastaUtility", "Vocabulary", "pinned_empty", "shared_output", "shard_rows"]

@@ -368,7 +368,9 @@ class FastSK:
         return shared_output(shape[0], shape[1], dist)
 
     def get_train_kernel(self, out=None):
-        """bindings.cpp:32 / fastsk.cpp:190-200: n_train x n_train (float64 ndarray)."""
+        """bindings.cpp:32 / fastsk.cpp:190-200: n_train x n_train (float64 ndarray).  Under torchrun with the sharded
+        finalisation the call is COLLECTIVE (every rank calls it): each rank copies its rows into one shared-memory array all
+        ranks map -- created here, or pass ``out=shared_output(...)`` (the same buffer on every rank) to re-use one."""
         return self._get_kernel("fsk_get_train_kernel", self._shape()[0], out)
 
     def get_test_kernel(self, out=None):
@@ -416,7 +418,8 @@ class FastSK:
         return out[:n.value]
 
     def get_train_kernel_tensor(self):
-        """Device-resident train kernel as a zero-copy torch tensor (DLPack-style hand-off)."""
+        """Device-resident train kernel as a zero-copy torch tensor (DLPack-style hand-off).  After a sharded finalisation
+        (torchrun, ``reduce="peer"``) it holds this rank's rows only: ``output_rows()`` says which."""
         return self._device_kernel("fsk_train_kernel_device", 0)
 
     def get_test_kernel_tensor(self):
@@ -427,7 +430,11 @@ class FastSK:
         n_train, n_test, _, _ = self._shape()
         ptr = ctypes.c_void_p()
         self._call(fn, ctypes.byref(ptr))
-        rows = n_test if which else n_train
+        tr0, trn, te0, ten = self.output_rows()
+        rows = (ten if which else trn) if self._sharded else (n_test if which else n_train)
+        if self.stats()["n_devices"] > 1:
+            raise RuntimeError("a team of in-process GPUs holds the kernel in row shares, one per device; use device=<one GPU> "
+                               "for a device-resident result")
         return torch.as_tensor(_DeviceArray(ptr.value, (rows, n_train), "<f8", self), device="cuda")
 
     def stats(self):
