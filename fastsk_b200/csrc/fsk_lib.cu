@@ -963,6 +963,7 @@ void destroy_one(fsk_handle* h) {
 // (re)create the team members 1 .. n-1 as copies of the leader's configuration
 void sync_team(fsk_handle* h) {
     if (h->devices.size() < 2) {
+        if (h->team.size() > 1) { h->rank = 0; h->world = 1; }      // (the leader was member 0 of n)
         for (size_t i = 1; i < h->team.size(); ++i) destroy_one(h->team[i]);
         h->team.clear();
         return;
@@ -1062,7 +1063,7 @@ int fsk_set_devices(fsk_handle* h, const int* devices, int n) {
         for (size_t j = 0; j < i; ++j) if (dev[j] == dev[i]) return fail(h, FSK_EINVAL, "device %d listed twice", dev[i]);
     }
     if (dev.empty()) return fail(h, FSK_ECUDA, "no CUDA device is visible");
-    if (h->world > 1) return fail(h, FSK_ESTATE, "fsk_set_devices and fsk_set_shard are alternatives (one process per GPU, or one process for all)");
+    if (h->world > 1 && !is_team(h)) return fail(h, FSK_ESTATE, "fsk_set_devices and fsk_set_shard are alternatives (one process per GPU, or one process for all)");
     int rc = fsk_set_device(h, dev[0]);
     if (rc) return rc;
     if (dev.size() > 1) {
@@ -1879,6 +1880,28 @@ int sync_one(fsk_handle* h) {
     }
     return FSK_OK;
 }
+
+// peer access between all devices of the team, and every member's list of the partial kernels of all members
+int team_link_peers(fsk_handle* h) {
+    for (fsk_handle* w : h->team) {
+        cudaSetDevice(w->device);
+        for (fsk_handle* o : h->team) {
+            if (o == w) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, w->device, o->device);
+            if (!can) { cudaSetDevice(h->device); return fail(h, FSK_ECUDA, "device %d cannot access device %d's memory", w->device, o->device); }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaSetDevice(h->device); return fail(h, FSK_ECUDA, "cudaDeviceEnablePeerAccess failed: %s", cudaGetErrorString(e)); }
+            cudaGetLastError();
+        }
+    }
+    cudaSetDevice(h->device);
+    for (fsk_handle* w : h->team) {
+        w->peer_parts.clear();
+        for (fsk_handle* o : h->team) w->peer_parts.push_back(own_part(o));
+    }
+    return FSK_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -1973,22 +1996,8 @@ int fsk_finalize(fsk_handle* h) {
     if (!h->uploaded) return fail(h, FSK_ESTATE, "nothing uploaded");
     if (!is_team(h)) return finalize_one(h);
     // every member normalises its rows of the outputs, reading the partial kernels of all members over NVLink
-    for (fsk_handle* w : h->team) {
-        cudaSetDevice(w->device);
-        for (fsk_handle* o : h->team) {
-            if (o == w) continue;
-            int can = 0;
-            cudaDeviceCanAccessPeer(&can, w->device, o->device);
-            if (!can) { cudaSetDevice(h->device); return fail(h, FSK_ECUDA, "device %d cannot access device %d's memory", w->device, o->device); }
-            const cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
-            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaSetDevice(h->device); return fail(h, FSK_ECUDA, "cudaDeviceEnablePeerAccess failed: %s", cudaGetErrorString(e)); }
-            cudaGetLastError();
-        }
-    }
-    for (fsk_handle* w : h->team) {
-        w->peer_parts.clear();
-        for (fsk_handle* o : h->team) w->peer_parts.push_back(own_part(o));
-    }
+    int rc = team_link_peers(h);
+    if (rc) return rc;
     return team_run(h, finalize_one);
 }
 
@@ -2109,10 +2118,12 @@ extern "C" {
 int fsk_get_unnormalised_i64(fsk_handle* h, int64_t* out) {
     if (!h->uploaded) return fail(h, FSK_ESTATE, "nothing uploaded");
     if (h->variance_mode) return fail(h, FSK_ESTATE, "the integer kernel exists only in the exact and skip_variance modes");
+    if (is_team(h) && h->peer_parts.empty()) { int rc = team_link_peers(h); if (rc) return rc; }
     return get_summed<unsigned long long, long long>(h, h->d_Kint, (long long*)out);
 }
 int fsk_get_unnormalised_f64(fsk_handle* h, double* out) {
     if (!h->uploaded) return fail(h, FSK_ESTATE, "nothing uploaded");
+    if (is_team(h) && h->peer_parts.empty()) { int rc = team_link_peers(h); if (rc) return rc; }
     if (h->variance_mode) return get_summed<double, double>(h, h->d_Kf, out);
     return get_summed<unsigned long long, double>(h, h->d_Kint, out);
 }

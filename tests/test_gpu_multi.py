@@ -113,6 +113,7 @@ def test_team_in_process_matches_one_gpu(mode, tmp_path):
     assert open(tmp_path / "k.txt").read() == open(tmp_path / "k1.txt").read()
     # a second compute on the same object, unseeded: the members must still agree on one queue
     h = FastSK(g, m, devices=[0, 1], distributed=False)
+    h.compute_kernel(Xte, Xtr)
     h.compute_kernel(Xtr, Xte)
     e = FastSK(g, m, device=0, distributed=False)
     e.compute_kernel(Xtr, Xte)

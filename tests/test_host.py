@@ -190,3 +190,11 @@ def test_set_devices_validation_and_team_options():
     assert lib.fsk_set_devices(f._h, None, 0) == _lib.FSK_EINVAL
     st = f.stats()
     assert st["n_devices"] == 1
+    two = (ctypes.c_int * 2)(0, 1)
+    for _ in range(2):                                                   # configuring a team twice (every compute does) is fine
+        assert lib.fsk_set_devices(f._h, two, 2) == _lib.FSK_OK
+    assert f.stats()["n_devices"] == 2
+    assert lib.fsk_set_shard(f._h, 1, 2) == _lib.FSK_ESTATE              # a team shards by itself
+    one = (ctypes.c_int * 1)(0)
+    assert lib.fsk_set_devices(f._h, one, 1) == _lib.FSK_OK              # back to one GPU: shard 0 of 1 again
+    assert f.stats()["n_devices"] == 1 and lib.fsk_set_shard(f._h, 1, 2) == _lib.FSK_OK
