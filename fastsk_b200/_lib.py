@@ -57,6 +57,8 @@ SIGNATURES = {
     "fsk_set_option": (ctypes.c_int, [_H, ctypes.c_char_p, ctypes.c_int64]),
     "fsk_compute": (ctypes.c_int, [_H, c_i32p, c_i64p, ctypes.c_int64, ctypes.c_int64]),
     "fsk_upload": (ctypes.c_int, [_H, c_i32p, c_i64p, ctypes.c_int64, ctypes.c_int64]),
+    "fsk_upload_split": (ctypes.c_int, [_H, c_i32p, c_i64p, ctypes.c_int64, c_i32p, c_i64p, ctypes.c_int64]),
+    "fsk_compute_split": (ctypes.c_int, [_H, c_i32p, c_i64p, ctypes.c_int64, c_i32p, c_i64p, ctypes.c_int64]),
     "fsk_build_partial": (ctypes.c_int, [_H]),
     "fsk_partial_buffer": (ctypes.c_int, [_H, c_voidpp, c_i64p, ctypes.POINTER(ctypes.c_int)]),
     "fsk_finalize": (ctypes.c_int, [_H]),

@@ -907,7 +907,8 @@ int sort_was_unstable(fsk_handle* h, bool* bad) {
 }
 
 int build_partial_once(fsk_handle* h);
-int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int64_t n_train, int64_t n_test);
+int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int64_t n_train, int64_t n_test,
+               const int32_t* codes_test = nullptr, const int64_t* offsets_test = nullptr);
 int reset_one(fsk_handle* h);
 int accumulate_one(fsk_handle* h, const int32_t* combos, int64_t n, int sync);
 int build_one(fsk_handle* h);
@@ -1161,8 +1162,13 @@ int fsk_set_option(fsk_handle* h, const char* key, int64_t value) {
 }  // extern "C"
 
 namespace {
-int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int64_t n_train, int64_t n_test) {
+// (codes, offsets) hold all N sequences back to back -- or, when codes_test is given, the train sequences only, and the test
+// sequences come from (codes_test, offsets_test): the two halves of compute_kernel(Xtrain, Xtest) need no concatenation
+int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int64_t n_train, int64_t n_test,
+               const int32_t* codes_test, const int64_t* offsets_test) {
     if (!codes || !offsets) return fail(h, FSK_EINVAL, "codes/offsets is NULL");
+    if ((codes_test == nullptr) != (offsets_test == nullptr)) return fail(h, FSK_EINVAL, "codes_test and offsets_test go together");
+    const bool split = codes_test != nullptr;
     Trace tr("upload");
     // the reference dereferences Xtrain[0] / Xtest[0] unconditionally (fastsk.cpp:33,41); compute_train passes no test set
     if (n_train < 1 || n_test < 0) return fail(h, FSK_EINVAL, "need at least one train sequence (n_train = %lld, n_test = %lld)", (long long)n_train, (long long)n_test);
@@ -1170,9 +1176,12 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     if (N >= (1LL << 31)) return fail(h, FSK_EINVAL, "too many sequences");
     // fastsk.cpp:53-58: g longer than the shortest sequence is fatal (exit(1) there, an error code here)
     int64_t shortest_train = INT64_MAX, shortest_test = INT64_MAX, nfeat = 0, maxwin = 0;
+    std::vector<int64_t> off0((size_t)N + 1);      // offsets of the sequences in the (virtual) concatenation, from 0
+    off0[0] = 0;
     for (int64_t i = 0; i < N; ++i) {
-        const int64_t len = offsets[i + 1] - offsets[i];
+        const int64_t len = (split && i >= n_train) ? offsets_test[i - n_train + 1] - offsets_test[i - n_train] : offsets[i + 1] - offsets[i];
         if (len < 0) return fail(h, FSK_EINVAL, "offsets must be non-decreasing");
+        off0[(size_t)i + 1] = off0[(size_t)i] + len;
         if (i < n_train) shortest_train = std::min(shortest_train, len);
         else shortest_test = std::min(shortest_test, len);
         nfeat += len - h->g + 1;
@@ -1186,34 +1195,39 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
 
     // dense re-coding: only equality of characters matters.  Host threads over slices of the characters (the
     // 10 M characters of configs[3] took 20 ms on one core: 2 % of an 8-GPU build).
-    const int64_t total = offsets[N] - offsets[0];
-    const int32_t* __restrict__ cbase = codes + offsets[0];
+    const int64_t total = off0[(size_t)N];
+    const int64_t total_a = split ? off0[(size_t)n_train] : total;          // characters of the first source array
+    const int32_t* __restrict__ src_a = codes + offsets[0];
+    const int32_t* __restrict__ src_b = split ? codes_test + offsets_test[0] : nullptr;
     const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)8, (int64_t)std::thread::hardware_concurrency(), total >> 18}));
-    auto parallel = [&](const std::function<void(int, int64_t, int64_t)>& fn) {
+    // fn(thread, source pointer, first position in the concatenation, count) over slices of the characters
+    auto parallel = [&](const std::function<void(int, const int32_t*, int64_t, int64_t)>& fn) {
+        auto piece = [&](int t, int64_t a, int64_t e) {
+            if (a < total_a) fn(t, src_a + a, a, std::min(e, total_a) - a);
+            if (e > total_a) { const int64_t a2 = std::max(a, total_a); fn(t, src_b + (a2 - total_a), a2, e - a2); }
+        };
         std::vector<std::thread> th;
-        for (int t = 1; t < nthr; ++t) th.emplace_back(fn, t, total * t / nthr, total * (t + 1) / nthr);
-        fn(0, 0, total / nthr);
+        for (int t = 1; t < nthr; ++t) th.emplace_back(piece, t, total * t / nthr, total * (t + 1) / nthr);
+        piece(0, 0, total / nthr);
         for (auto& x : th) x.join();
     };
     std::vector<int32_t> tmax((size_t)nthr, 0), tmin((size_t)nthr, 0);
-    parallel([&](int t, int64_t a, int64_t e) {
-        int32_t mx = 0, mn = 0;
-        for (int64_t i = a; i < e; ++i) { mx = std::max(mx, cbase[i]); mn = std::min(mn, cbase[i]); }
+    parallel([&](int t, const int32_t* c, int64_t, int64_t cnt) {
+        int32_t mx = tmax[(size_t)t], mn = tmin[(size_t)t];
+        for (int64_t i = 0; i < cnt; ++i) { mx = std::max(mx, c[i]); mn = std::min(mn, c[i]); }
         tmax[(size_t)t] = mx; tmin[(size_t)t] = mn;
     });
     const int32_t maxv = *std::max_element(tmax.begin(), tmax.end());
-    if (*std::min_element(tmin.begin(), tmin.end()) < 0) {
-        for (int64_t i = 0; i < total; ++i)
-            if (cbase[i] < 0) return fail(h, FSK_EINVAL, "negative character code at position %lld", (long long)(offsets[0] + i));
-    }
+    if (*std::min_element(tmin.begin(), tmin.end()) < 0)
+        return fail(h, FSK_EINVAL, "negative character code in the input");
     std::vector<int32_t> remap;
     std::vector<uint8_t> dense((size_t)total);
     int A = 0;
     if (maxv < (1 << 22)) {
         std::vector<std::vector<uint8_t>> seen((size_t)nthr, std::vector<uint8_t>((size_t)maxv + 1, 0));
-        parallel([&](int t, int64_t a, int64_t e) {
+        parallel([&](int t, const int32_t* c, int64_t, int64_t cnt) {
             uint8_t* sn = seen[(size_t)t].data();
-            for (int64_t i = a; i < e; ++i) sn[cbase[i]] = 1;
+            for (int64_t i = 0; i < cnt; ++i) sn[c[i]] = 1;
         });
         remap.assign((size_t)maxv + 1, -1);
         for (int32_t v = 0; v <= maxv; ++v) {
@@ -1222,17 +1236,18 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
             if (any) remap[(size_t)v] = A++;
         }
         if (A > 256) return fail(h, FSK_EINVAL, "alphabet of %d distinct characters; at most 256 are supported", A);
-        parallel([&](int, int64_t a, int64_t e) {
-            for (int64_t i = a; i < e; ++i) dense[(size_t)i] = (uint8_t)remap[(size_t)cbase[i]];
+        parallel([&](int, const int32_t* c, int64_t at, int64_t cnt) {
+            for (int64_t i = 0; i < cnt; ++i) dense[(size_t)(at + i)] = (uint8_t)remap[(size_t)c[i]];
         });
     } else {
-        std::vector<int32_t> uniq(cbase, cbase + total);
+        std::vector<int32_t> uniq(src_a, src_a + total_a);
+        if (split) uniq.insert(uniq.end(), src_b, src_b + (total - total_a));
         std::sort(uniq.begin(), uniq.end());
         uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
         A = (int)uniq.size();
         if (A > 256) return fail(h, FSK_EINVAL, "alphabet of %d distinct characters; at most 256 are supported", A);
-        parallel([&](int, int64_t a, int64_t e) {
-            for (int64_t i = a; i < e; ++i) dense[(size_t)i] = (uint8_t)(std::lower_bound(uniq.begin(), uniq.end(), cbase[i]) - uniq.begin());
+        parallel([&](int, const int32_t* c, int64_t at, int64_t cnt) {
+            for (int64_t i = 0; i < cnt; ++i) dense[(size_t)(at + i)] = (uint8_t)(std::lower_bound(uniq.begin(), uniq.end(), c[i]) - uniq.begin());
         });
     }
     tr.lap("length scan + dense re-coding");
@@ -1486,8 +1501,7 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     // device inputs
     uint8_t* d_codes = nullptr;
     int64_t *d_off = nullptr, *d_woff = nullptr;
-    std::vector<int64_t> off0((size_t)N + 1), woff((size_t)N + 1);
-    for (int64_t i = 0; i <= N; ++i) off0[(size_t)i] = offsets[i] - offsets[0];
+    std::vector<int64_t> woff((size_t)N + 1);
     woff[0] = 0;
     for (int64_t i = 0; i < N; ++i) woff[(size_t)i + 1] = woff[(size_t)i] + (off0[(size_t)i + 1] - off0[(size_t)i] - h->g + 1);
     ALLOC(d_codes, total);
@@ -1616,13 +1630,18 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
 extern "C" {
 
 int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int64_t n_train, int64_t n_test) {
-    if (!is_team(h)) return upload_one(h, codes, offsets, n_train, n_test);
+    return fsk_upload_split(h, codes, offsets, n_train, nullptr, nullptr, n_test);
+}
+
+int fsk_upload_split(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int64_t n_train, const int32_t* codes_test,
+                     const int64_t* offsets_test, int64_t n_test) {
+    if (!is_team(h)) return upload_one(h, codes, offsets, n_train, n_test, codes_test, offsets_test);
     // every member must work through the same combination order: the leader draws the wall-clock seed of an unseeded
     // shuffle (fastsk_kernel.cpp:36-38) once for the whole team
     sync_team(h);
     const uint64_t seed = (uint64_t)std::time(0);
     for (fsk_handle* w : h->team) { w->run_seed_set = true; w->run_seed = seed; }
-    return team_run(h, [&](fsk_handle* w) { return upload_one(w, codes, offsets, n_train, n_test); });
+    return team_run(h, [&](fsk_handle* w) { return upload_one(w, codes, offsets, n_train, n_test, codes_test, offsets_test); });
 }
 
 int fsk_reset_partial(fsk_handle* h) {
@@ -2002,7 +2021,12 @@ int fsk_finalize(fsk_handle* h) {
 }
 
 int fsk_compute(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int64_t n_train, int64_t n_test) {
-    int rc = fsk_upload(h, codes, offsets, n_train, n_test);
+    return fsk_compute_split(h, codes, offsets, n_train, nullptr, nullptr, n_test);
+}
+
+int fsk_compute_split(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int64_t n_train, const int32_t* codes_test,
+                      const int64_t* offsets_test, int64_t n_test) {
+    int rc = fsk_upload_split(h, codes, offsets, n_train, codes_test, offsets_test, n_test);
     if (rc) return rc;
     rc = fsk_build_partial(h);
     if (rc) return rc;

@@ -192,9 +192,7 @@ class FastSK:
         """bindings.cpp:23-27 / fastsk.cpp:30-118.  Blocks until the normalised kernels are on the device."""
         ctr, otr = _flatten(Xtrain)
         cte, ote = _flatten(Xtest)
-        codes = np.concatenate([ctr, cte])
-        offsets = np.concatenate([otr, ote[1:] + otr[-1]])
-        self._compute_flat(codes, offsets, len(otr) - 1, len(ote) - 1)
+        self._compute_flat(ctr, otr, len(otr) - 1, len(ote) - 1, cte, ote)     # (the two halves go down as they are)
 
     def compute_train(self, Xtrain):
         """bindings.cpp:28-31 / fastsk.cpp:120-188."""
@@ -225,14 +223,16 @@ class FastSK:
             arr = (ctypes.c_int * len(dev))(*[int(d) for d in dev])
             self._call("fsk_set_devices", arr, len(dev))
 
-    def _compute_flat(self, codes, offsets, n_train, n_test):
+    def _compute_flat(self, codes, offsets, n_train, n_test, codes_test=None, offsets_test=None):
         self._clf = None
         self._sharded = False
         rank, world, dist = self._dist()
         cp, op = codes.ctypes.data_as(c_i32p), offsets.ctypes.data_as(c_i64p)
+        cp2 = codes_test.ctypes.data_as(c_i32p) if codes_test is not None else None
+        op2 = offsets_test.ctypes.data_as(c_i64p) if codes_test is not None else None
         if dist is None:
-            self._pick_devices(len(codes))
-            self._call("fsk_compute", cp, op, n_train, n_test)
+            self._pick_devices(len(codes) + (len(codes_test) if codes_test is not None else 0))
+            self._call("fsk_compute_split", cp, op, n_train, cp2, op2, n_test)
             return
         # one process per GPU: every rank builds the partial kernel of its shard of the combinations
         # (virtual streams in variance mode)
@@ -252,7 +252,7 @@ class FastSK:
         self._agree_on_queue(dist, rank)
         self._call("fsk_release_peers")
         self._call("fsk_set_shard", rank, world)
-        self._call("fsk_upload", cp, op, n_train, n_test)
+        self._call("fsk_upload_split", cp, op, n_train, cp2, op2, n_test)
         lap("upload")
         self._call("fsk_build_partial")
         lap("build_partial")

@@ -112,6 +112,14 @@ int fsk_set_option(fsk_handle* h, const char* key, int64_t value);
  * FSK_EINVAL if g is longer than the shortest sequence (reference: exit(1), fastsk.cpp:53-58). */
 int fsk_compute(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int64_t n_train, int64_t n_test);
 
+/* The same with the two arguments of compute_kernel(Xtrain, Xtest) as they come: train sequences in (codes, offsets[0..n_train]),
+ * test sequences in (codes_test, offsets_test[0..n_test]) -- no concatenation on the caller's side (codes_test == NULL: all N
+ * sequences are in codes, as above). */
+int fsk_compute_split(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int64_t n_train, const int32_t* codes_test,
+                      const int64_t* offsets_test, int64_t n_test);
+int fsk_upload_split(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int64_t n_train, const int32_t* codes_test,
+                     const int64_t* offsets_test, int64_t n_test);
+
 /* staged form of the same call (multi-GPU, benchmarking with resident inputs) */
 int fsk_upload(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int64_t n_train, int64_t n_test);
 int fsk_build_partial(fsk_handle* h);   /* KernelFunction::kernel_build_parallel for this shard, fastsk_kernel.cpp:145-322 */
