@@ -2174,6 +2174,7 @@ struct Interleave {
             ++nodes;
         }
         if (nodes > 1) on = syscall(SYS_set_mempolicy, 3 /* MPOL_INTERLEAVE */, mask, (unsigned long)(nodes + 1)) == 0;
+        if (getenv("FSK_TRACE")) fprintf(stderr, "[fsk] host buffer: %d NUMA node(s), interleave %s\n", nodes, on ? "on" : "off");
 #endif
     }
     ~Interleave() {
