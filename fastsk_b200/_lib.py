@@ -44,6 +44,8 @@ SIGNATURES = {
     "fsk_set_peer_partials": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_int]),
     "fsk_set_peer_pointers": (ctypes.c_int, [_H, c_voidpp, ctypes.c_int]),
     "fsk_release_peers": (ctypes.c_int, [_H]),
+    "fsk_set_output_weights": (ctypes.c_int, [_H, c_f64p, ctypes.c_int]),
+    "fsk_probe_d2h": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t, c_f64p]),
     "fsk_output_rows": (ctypes.c_int, [_H, c_i64p, c_i64p, c_i64p, c_i64p]),
     "fsk_host_alloc": (ctypes.c_int, [c_voidpp, ctypes.c_size_t]),
     "fsk_host_free": (ctypes.c_int, [ctypes.c_void_p]),

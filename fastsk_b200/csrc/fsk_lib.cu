@@ -66,6 +66,8 @@ struct fsk_handle {
     // sharded finalisation: the partial kernels of all ranks in rank order (own buffer included), and the output rows held here
     std::vector<const void*> peer_parts;
     std::vector<void*> ipc_opened;   // peer mappings this handle opened with cudaIpcOpenMemHandle
+    bool weights_auto = false;       // out_weights came from the team's own probe (dropped when the team changes)
+    std::vector<double> out_weights; // share of the output rows per rank (empty: equal shares); 0 = this rank hands no rows back
     bool sharded = false;            // d_train / d_test hold only the rows [tr_r0, +tr_nr) / [te_r0, +te_nr)
     int64_t tr_r0 = 0, tr_nr = 0, te_r0 = 0, te_nr = 0;
     size_t train_cap = 0, test_cap = 0;
@@ -963,6 +965,7 @@ void destroy_one(fsk_handle* h) {
 
 // (re)create the team members 1 .. n-1 as copies of the leader's configuration
 void sync_team(fsk_handle* h) {
+    if (h->weights_auto) { h->out_weights.clear(); h->weights_auto = false; }
     if (h->devices.size() < 2) {
         if (h->team.size() > 1) { h->rank = 0; h->world = 1; }      // (the leader was member 0 of n)
         for (size_t i = 1; i < h->team.size(); ++i) destroy_one(h->team[i]);
@@ -991,6 +994,7 @@ void sync_team(fsk_handle* h) {
         w->opt_acc_prefetch = h->opt_acc_prefetch; w->opt_acc_unroll = h->opt_acc_unroll; w->opt_wave = h->opt_wave;
         w->profile = h->profile; w->opt_pad = h->opt_pad; w->opt_acc_cols = h->opt_acc_cols; w->opt_heavy_tau = h->opt_heavy_tau;
         w->opt_ids32 = h->opt_ids32; w->opt_gemm_shape = h->opt_gemm_shape; w->opt_heavy_cap = h->opt_heavy_cap;
+        w->out_weights = h->out_weights;
         w->opt_seg_lean = h->opt_seg_lean; w->opt_spec_depth = h->opt_spec_depth; w->opt_pf_stride = h->opt_pf_stride; w->opt_fit_smem = h->opt_fit_smem;
         w->opt_seg_dir = h->opt_seg_dir; w->opt_dir_blocks = h->opt_dir_blocks; w->opt_count_updates = h->opt_count_updates;
     }
@@ -1874,8 +1878,18 @@ int finalize_one(fsk_handle* h) {
     const int W = (int)h->peer_parts.size();
     h->sharded = W > 1;
     const int64_t r = h->sharded ? h->rank : 0, w = h->sharded ? W : 1;
-    h->tr_r0 = h->n_train * r / w; h->tr_nr = h->n_train * (r + 1) / w - h->tr_r0;
-    h->te_r0 = h->n_test * r / w; h->te_nr = h->n_test * (r + 1) / w - h->te_r0;
+    // rows [n * cum(r) / total, n * cum(r + 1) / total): equal shares, or by the ranks' weights (a box whose GPUs do not reach
+    // the host equally fast hands the results back through the fast ones: fsk_set_output_weights)
+    double before = (double)r, total = (double)w, mine = 1.0;
+    if (h->sharded && (int)h->out_weights.size() == W) {
+        before = 0; total = 0;
+        for (int q = 0; q < W; ++q) { if (q < r) before += h->out_weights[(size_t)q]; total += h->out_weights[(size_t)q]; }
+        mine = h->out_weights[(size_t)r];
+    }
+    auto cut = [&](int64_t n, double c) { return (int64_t)std::min<double>((double)n, std::floor((double)n * (c / total) + 1e-9)); };
+    const bool last = before + mine >= total - 1e-12;
+    h->tr_r0 = cut(h->n_train, before); h->tr_nr = (last ? h->n_train : cut(h->n_train, before + mine)) - h->tr_r0;
+    h->te_r0 = cut(h->n_test, before); h->te_nr = (last ? h->n_test : cut(h->n_test, before + mine)) - h->te_r0;
     if (!h->d_diag) ALLOC(h->d_diag, h->N);
     const size_t need_tr = (size_t)h->tr_nr * h->n_train, need_te = (size_t)h->te_nr * h->n_train;
     if (!h->d_train || need_tr > h->train_cap) { dev_free(h->d_train); ALLOC(h->d_train, need_tr); h->train_cap = need_tr; }
@@ -1897,6 +1911,58 @@ int sync_one(fsk_handle* h) {
         if (rc) return rc;
         if (bad) return fail(h, FSK_ECUDA, "sort verification failed: records out of order after the optimistic ranking; set option safe_rank = 1");
     }
+    return FSK_OK;
+}
+
+// Which members should hand the results back to the host?  All of them, unless the box's GPUs reach host memory unequally:
+// probe a device -> host copy on all members at once, then on the faster half alone; if the half alone moves clearly more
+// bytes per second than all together, only those members take output rows.  Once per process and device list.
+int team_output_weights(fsk_handle* h) {
+    if (!h->out_weights.empty() || h->team.size() < 4 || getenv("FSK_EQUAL_OUTPUT_SHARES")) return FSK_OK;
+    static std::mutex mu;
+    static std::map<std::string, std::vector<double>> known;
+    std::string key;
+    for (fsk_handle* w : h->team) key += std::to_string(w->device) + ",";
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = known.find(key);
+        if (it != known.end()) { h->out_weights = it->second; h->weights_auto = true; for (fsk_handle* w : h->team) w->out_weights = it->second; return FSK_OK; }
+    }
+    const size_t n = h->team.size(), bytes = (size_t)256 << 20;
+    std::vector<double> t_all(n, 0.0), t_sub(n, 0.0);
+    std::vector<char> in_sub(n, 0);
+    auto probe = [&](std::vector<double>& t, bool subset) {
+        return team_run(h, [&](fsk_handle* w) {
+            if (subset && !in_sub[(size_t)w->rank]) return (int)FSK_OK;
+            return fsk_probe_d2h(w->device, bytes, &t[(size_t)w->rank]);
+        });
+    };
+    int rc = probe(t_all, false);            // (first touch of the scratch buffers)
+    if (rc == FSK_OK) rc = probe(t_all, false);
+    if (rc) return FSK_OK;                   // no probe, equal shares
+    std::vector<size_t> order(n);
+    for (size_t i = 0; i < n; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return t_all[a] < t_all[b]; });
+    for (size_t i = 0; i < n / 2; ++i) in_sub[order[i]] = 1;
+    if (probe(t_sub, true)) return FSK_OK;
+    const double agg_all = (double)n * bytes / *std::max_element(t_all.begin(), t_all.end());
+    double worst_sub = 0;
+    for (size_t i = 0; i < n; ++i) if (in_sub[i]) worst_sub = std::max(worst_sub, t_sub[i]);
+    const double agg_sub = (double)(n / 2) * bytes / worst_sub;
+    std::vector<double> wts(n, 1.0);
+    if (agg_sub > 1.25 * agg_all) for (size_t i = 0; i < n; ++i) wts[i] = in_sub[i] ? 1.0 : 0.0;
+    if (getenv("FSK_TRACE")) {
+        fprintf(stderr, "[fsk] device -> host, all %zu GPUs at once: %.1f GB/s; the faster half alone: %.1f GB/s; output rows from:", n, agg_all / 1e9, agg_sub / 1e9);
+        for (size_t i = 0; i < n; ++i) if (wts[i] > 0) fprintf(stderr, " %d", h->team[i]->device);
+        fprintf(stderr, "\n");
+    }
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        known[key] = wts;
+    }
+    h->out_weights = wts;
+    h->weights_auto = true;
+    for (fsk_handle* w : h->team) w->out_weights = wts;
     return FSK_OK;
 }
 
@@ -2002,6 +2068,50 @@ int fsk_release_peers(fsk_handle* h) {
     return FSK_OK;
 }
 
+int fsk_set_output_weights(fsk_handle* h, const double* weights, int world) {
+    if (!weights || world < 1) { h->out_weights.clear(); for (fsk_handle* w : h->team) w->out_weights.clear(); return FSK_OK; }
+    if (world > MAX_PEERS) return fail(h, FSK_EINVAL, "at most %d ranks", MAX_PEERS);
+    double tot = 0;
+    for (int r = 0; r < world; ++r) {
+        if (!(weights[r] >= 0)) return fail(h, FSK_EINVAL, "output weights must be non-negative");
+        tot += weights[r];
+    }
+    if (!(tot > 0)) return fail(h, FSK_EINVAL, "at least one rank must hand rows back");
+    h->out_weights.assign(weights, weights + world);
+    for (fsk_handle* w : h->team) w->out_weights = h->out_weights;
+    return FSK_OK;
+}
+
+int fsk_probe_d2h(int device, size_t bytes, double* seconds) {
+    if (!seconds || bytes == 0) return FSK_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); g_create_error = "no usable CUDA device"; return FSK_ECUDA; }
+    // scratch per device, kept for the life of the process (a probe is a few hundred MB, once per launch)
+    static std::mutex mu;
+    static std::map<int, std::pair<void*, void*>> scratch;
+    static std::map<int, size_t> cap;
+    void *d = nullptr, *hst = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (cap[device] < bytes) {
+            if (scratch[device].first) { cudaFree(scratch[device].first); cudaFreeHost(scratch[device].second); }
+            if (cudaMalloc(&d, bytes) != cudaSuccess || cudaHostAlloc(&hst, bytes, cudaHostAllocPortable) != cudaSuccess) {
+                cudaGetLastError();
+                if (d) cudaFree(d);
+                scratch[device] = {nullptr, nullptr}; cap[device] = 0;
+                return FSK_ENOMEM;
+            }
+            scratch[device] = {d, hst}; cap[device] = bytes;
+        }
+        d = scratch[device].first; hst = scratch[device].second;
+    }
+    cudaDeviceSynchronize();
+    const auto t0 = std::chrono::steady_clock::now();
+    const cudaError_t e = cudaMemcpy(hst, d, bytes, cudaMemcpyDeviceToHost);
+    *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (e != cudaSuccess) { cudaGetLastError(); return FSK_ECUDA; }
+    return FSK_OK;
+}
+
 int fsk_output_rows(fsk_handle* h, int64_t* train_r0, int64_t* train_nr, int64_t* test_r0, int64_t* test_nr) {
     if (!h->finalized) return fail(h, FSK_ESTATE, "no kernel computed yet");
     if (train_r0) *train_r0 = h->tr_r0;
@@ -2017,6 +2127,7 @@ int fsk_finalize(fsk_handle* h) {
     // every member normalises its rows of the outputs, reading the partial kernels of all members over NVLink
     int rc = team_link_peers(h);
     if (rc) return rc;
+    team_output_weights(h);
     return team_run(h, finalize_one);
 }
 

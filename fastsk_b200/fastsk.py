@@ -81,10 +81,62 @@ _BIG_OUTPUT = 64 << 20      # outputs at least this large are allocated pinned
 _SHM_KEEP = []              # shared-memory segments stay mapped for the life of the process (arrays may outlive any object)
 
 
-def shard_rows(n, rank, world):
-    """Rows [r0, r0 + nr) of an n-row output that rank `rank` of `world` normalises and holds (fsk_finalize, sharded)."""
-    r0 = n * rank // world
-    return r0, n * (rank + 1) // world - r0
+def shard_rows(n, rank, world, weights=None):
+    """Rows [r0, r0 + nr) of an n-row output that rank `rank` of `world` normalises and holds (fsk_finalize, sharded): equal
+    shares, or shares by the ranks' output weights (fsk_set_output_weights; the same arithmetic as the library's)."""
+    import math
+    w = [1.0] * world if weights is None else [float(x) for x in weights]
+    total, before, mine = sum(w), sum(w[:rank]), w[rank]
+    cut = lambda c: int(min(float(n), math.floor(n * (c / total) + 1e-9)))   # noqa: E731
+    r0 = cut(before)
+    end = n if before + mine >= total - 1e-12 else cut(before + mine)
+    return r0, end - r0
+
+
+_WEIGHTS = {}
+
+
+def output_weights(dist):
+    """COLLECTIVE.  Which ranks hand the results back to the host: all of them (None), unless the box's GPUs reach host memory
+    unequally -- then only the faster half gets output rows (weights 1 / 0).  Found by timing a 256 MB device -> host copy on
+    all ranks at once and on the faster half alone (fsk_probe_d2h); once per process.  FSK_EQUAL_OUTPUT_SHARES=1 skips it."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if world in _WEIGHTS:
+        return _WEIGHTS[world]
+    wts = None
+    if world >= 4 and dist.get_backend() == "nccl" and not os.environ.get("FSK_EQUAL_OUTPUT_SHARES"):
+        lib = _lib.load()
+        dev, nbytes = torch.cuda.current_device(), 256 << 20
+
+        def probe(active):
+            t = ctypes.c_double(0.0)
+            torch.cuda.synchronize()
+            dist.barrier()
+            if active:
+                rc = lib.fsk_probe_d2h(dev, nbytes, ctypes.byref(t))
+                if rc:
+                    t.value = float("inf")
+            out = torch.zeros(world, dtype=torch.float64, device="cuda")
+            mine = torch.tensor([t.value], dtype=torch.float64, device="cuda")
+            dist.all_gather_into_tensor(out, mine)
+            return out.cpu().tolist()
+
+        probe(True)                                       # (first touch of the scratch buffers)
+        t_all = probe(True)
+        if all(x > 0 and x != float("inf") for x in t_all):
+            order = sorted(range(world), key=lambda r: t_all[r])
+            sub = set(order[:world // 2])
+            t_sub = probe(rank in sub)
+            agg_all = world * nbytes / max(t_all)
+            agg_sub = len(sub) * nbytes / max(t_sub[r] for r in sub)
+            if agg_sub > 1.25 * agg_all:
+                wts = [1.0 if r in sub else 0.0 for r in range(world)]
+            if rank == 0 and os.environ.get("FSK_TRACE"):
+                print("[py] device -> host, all %d ranks at once: %.1f GB/s; the faster half alone: %.1f GB/s; output rows from ranks %s"
+                      % (world, agg_all / 1e9, agg_sub / 1e9, sorted(sub) if wts else "all"), flush=True)
+    _WEIGHTS[world] = wts
+    return wts
 
 
 def shared_output(rows, cols, dist=None):
@@ -119,7 +171,7 @@ def shared_output(rows, cols, dist=None):
     dist.barrier()
     if rank == 0:
         shm.unlink()                            # the mappings stay valid; nothing is left behind in /dev/shm
-    r0, nr = shard_rows(rows, rank, world)
+    r0, nr = shard_rows(rows, rank, world, output_weights(dist))
     if nr:
         lib = _lib.load()
         base = arr.ctypes.data
@@ -257,6 +309,10 @@ class FastSK:
         self._call("fsk_build_partial")
         lap("build_partial")
         if nccl and self._reduce == "peer" and self._exchange_peers(dist, world):
+            wts = output_weights(dist)
+            if wts is not None:
+                arr = (ctypes.c_double * world)(*wts)
+                self._call("fsk_set_output_weights", arr, world)
             lap("exchange of the IPC handles + mapping")
             dist.barrier()                      # every rank's partial is complete before anybody reads it
             lap("barrier (slowest shard)")

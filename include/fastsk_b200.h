@@ -86,6 +86,13 @@ int fsk_set_peer_partials(fsk_handle* h, const void* handles /* world x FSK_IPC_
  * from fsk_partial_buffer, peer access already enabled by the caller where the devices differ */
 int fsk_set_peer_pointers(fsk_handle* h, void* const* parts /* world pointers, rank order */, int world);
 int fsk_release_peers(fsk_handle* h);
+/* Share of the output rows per rank in a sharded finalisation (default: equal).  On a box whose GPUs do not reach host memory
+ * equally fast (measured here: GPUs 4-7 together 173 GB/s, GPUs 0-3 together 71 GB/s, all eight 91 GB/s) the results are handed
+ * back through the fast ones: weight 0 = this rank normalises and copies no rows (its partial kernel is still read by the
+ * others over NVLink).  fsk_probe_d2h times one device -> host copy of `bytes` from `device` into pinned memory; run it on
+ * all ranks at once (and on subsets) to find the weights -- fastsk_b200/fastsk.py::output_weights does. */
+int fsk_set_output_weights(fsk_handle* h, const double* weights /* world values, or NULL for equal shares */, int world);
+int fsk_probe_d2h(int device, size_t bytes, double* seconds);
 /* rows of the train / test kernels this handle holds after fsk_finalize (all of them unless the finalisation was sharded;
  * a team of in-process devices reports all rows: its getters collect every member's share) */
 int fsk_output_rows(fsk_handle* h, int64_t* train_r0, int64_t* train_nr, int64_t* test_r0, int64_t* test_nr);

@@ -40,9 +40,9 @@ def one_gpu(FastSK, Xtr, Xte, g, m, queue, **kw):
 
 
 @pytest.mark.parametrize("mode", list(MODES))
-@pytest.mark.parametrize("world", [2, 3])
-def test_shards_on_one_gpu_sharded_finalise(mode, world):
-    from fastsk_b200 import FastSK
+@pytest.mark.parametrize("world,weights", [(2, None), (3, None), (3, [2.0, 0.0, 1.0]), (4, [0.0, 1.0, 0.0, 1.0])])
+def test_shards_on_one_gpu_sharded_finalise(mode, world, weights):
+    from fastsk_b200 import FastSK, shard_rows
     from fastsk_b200.fastsk import _flatten
     Xtr, Xte, g, m, queue = make_inputs()
     ref = one_gpu(FastSK, Xtr, Xte, g, m, queue, **MODES[mode])
@@ -68,8 +68,13 @@ def test_shards_on_one_gpu_sharded_finalise(mode, world):
     rows = []
     for f in hs:
         f._call("fsk_set_peer_pointers", ptrs, world)
+        if weights is not None:                  # unequal shares of the output rows (a rank with weight 0 hands nothing back)
+            f._call("fsk_set_output_weights", (ctypes.c_double * world)(*weights), world)
         f._call("fsk_finalize")
         rows.append(f.output_rows())
+        r = len(rows) - 1
+        assert (rows[r][0], rows[r][1]) == shard_rows(len(Xtr), r, world, weights)
+        assert (rows[r][2], rows[r][3]) == shard_rows(len(Xte), r, world, weights)
         f.get_train_kernel(out=tr)
         f.get_test_kernel(out=te)
     assert sum(r[1] for r in rows) == len(Xtr) and sum(r[3] for r in rows) == len(Xte)     # the shares partition the rows
