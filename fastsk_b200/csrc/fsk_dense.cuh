@@ -151,6 +151,17 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // Shared-memory matrix descriptor of a K-major operand tile staged by TMA with 128-byte swizzle: rows of 128 bytes,
 // 8-row groups 1024 bytes apart (stride byte offset), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -308,26 +319,35 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restr
 // and the epilogue applies the Welford step to the tile of the mean (which the same CTA touched a few microseconds ago: L2
 // hits) and adds up delta * delta2.  Two TMEM accumulators: the MMAs of slot d + 1 run under the epilogue of slot d.  One
 // launch does what used to be one launch + one host round trip per iteration.
-constexpr int DW_STAGES = 2;
+constexpr int DW_STAGES = 2, DW_STAGES_REGS = 4;
 constexpr uint32_t DW_STAGE_BYTES = 2 * DG_TILE_BYTES;
 constexpr int DW_EPI_WARPS = 8;                                   // two epilogue warps per TMEM lane quarter, 64 columns each
 constexpr int DW_THREADS = 64 + 32 * DW_EPI_WARPS;                // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
 constexpr uint32_t DW_TS_BYTES = DW_EPI_WARPS * 32 * 33 * 4;      // one padded 32 x 32 fp32 transpose buffer per epilogue warp
-__host__ __device__ constexpr size_t dw_smem() { return (size_t)DW_STAGES * DW_STAGE_BYTES + DW_TS_BYTES + 1024 + 256; }
+__host__ __device__ constexpr size_t dw_smem(bool regs) { return (size_t)(regs ? DW_STAGES_REGS : DW_STAGES) * DW_STAGE_BYTES + DW_TS_BYTES + 1024 + 256; }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-__global__ void __launch_bounds__(DW_THREADS, 2)
+// REGS: the 64 cells a thread owns (its row of the TMEM lane quarter x the 64 columns of its half) stay in REGISTERS for all
+// the slots of the launch: the means are read once before the first slot and written once after the last, and a slot costs
+// one TMEM read and eight fp64 operations per cell -- no shared-memory transpose, no L2 round trip per iteration (the
+// streaming form moved 2 x 8 bytes per cell and iteration: 6.8 GB for 50 iterations of EP300, all of the kernel's time).
+// The means are then stored STRIP-MAJOR inside a tile: cell (row 32 q + lane, column 64 half + c) at
+// ((2 q + half) * 64 + c) * 32 + lane, so that the one load and the one store are coalesced (welford_untile_kernel knows).
+// One CTA per SM (128 of a thread's registers are means); !REGS is the streaming form, two CTAs per SM.
+template <bool REGS>
+__global__ void __launch_bounds__(DW_THREADS, REGS ? 1 : 2)
 syrk_tc_welford_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restrict__ tile_order, int64_t nseq, uint32_t nks,
                        const WelfordSpec* __restrict__ wf) {
     extern __shared__ uint8_t dw_smem_raw[];
+    constexpr int S = REGS ? DW_STAGES_REGS : DW_STAGES;          // operand stages (one CTA per SM has room for more)
     const uint32_t raw = smem_u32(dw_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
-    const uint32_t ts_base = base + DW_STAGES * DW_STAGE_BYTES;
+    const uint32_t ts_base = base + S * DW_STAGE_BYTES;
     const uint32_t bars = ts_base + DW_TS_BYTES;                  // full[S], empty[S], tmem_full[2], tmem_empty[2], tmem slot
-    const uint32_t full0 = bars, empty0 = bars + 8 * DW_STAGES, tfull0 = bars + 16 * DW_STAGES, tempty0 = tfull0 + 16, tmem_slot = tempty0 + 16;
+    const uint32_t full0 = bars, empty0 = bars + 8 * S, tfull0 = bars + 16 * S, tempty0 = tfull0 + 16, tmem_slot = tempty0 + 16;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(dw_smem_raw + (tmem_slot - raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -339,7 +359,7 @@ syrk_tc_welford_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t*
     const uint32_t nkb = nks / DG_BK;
 
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < DW_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, DW_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -359,7 +379,7 @@ syrk_tc_welford_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t*
             const uint32_t tx = diag ? DG_TILE_BYTES : DW_STAGE_BYTES;
             const uint32_t total = depth * nkb;
             for (uint32_t t = 0; t < total; ++t) {
-                const uint32_t s = t % DW_STAGES, ph = (t / DW_STAGES) & 1u;
+                const uint32_t s = t % S, ph = (t / S) & 1u;
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
                 mbar_arrive_expect_tx(full0 + 8 * s, tx);
                 const uint32_t a = base + s * DW_STAGE_BYTES;
@@ -378,7 +398,7 @@ syrk_tc_welford_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t*
                 mbar_wait(tempty0 + 8 * buf, ((d >> 1) & 1u) ^ 1u);          // the epilogue has drained this accumulator
                 tc_fence_after();
                 for (uint32_t kb = 0; kb < nkb; ++kb, ++t) {
-                    const uint32_t s = t % DW_STAGES, ph = (t / DW_STAGES) & 1u;
+                    const uint32_t s = t % S, ph = (t / S) & 1u;
                     mbar_wait(full0 + 8 * s, ph);
                     tc_fence_after();
                     const uint32_t a = base + s * DW_STAGE_BYTES;
@@ -408,6 +428,60 @@ syrk_tc_welford_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t*
         const int64_t j0 = (int64_t)J * DG_TILE + half * 64;
         const int64_t ibase = (int64_t)I * DG_TILE + q * 32;
         const int64_t n_train = wf->n_train;
+        if constexpr (REGS) {
+            const size_t tcell = ((size_t)I * (I + 1) / 2 + J) * (size_t)(DG_TILE * DG_TILE) + (size_t)((q * 2 + half) * 64) * 32 + lane;
+            const double* __restrict__ kin = wf->khat_in[g] + tcell;
+            double* __restrict__ kout = wf->khat_out[g] + tcell;
+            const int64_t i = ibase + lane;                               // this thread's row of the kernel matrix
+            // cells of the strip that count for the variance: training rows, columns up to the diagonal
+            const bool whole = ibase + 31 < n_train && j0 + 63 <= ibase;
+            const int64_t ncount = i < n_train ? i - j0 + 1 : 0;          // columns c < ncount count
+            double m[64];
+#pragma unroll
+            for (int c = 0; c < 64; ++c) m[c] = kin[c * 32];
+            for (uint32_t d = 0; d < depth; ++d) {
+                const uint32_t buf = d & 1u;
+                const double diter = (double)(wf->iter0[g] + (int32_t)d);
+                const double riter = __ddiv_rn(1.0, diter);
+                double acc = 0.0;
+                mbar_wait(tfull0 + 8 * buf, (d >> 1) & 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld_32x16(tmem_base + ((q * 32u) << 16) + (uint32_t)(buf * 128 + half * 64 + c0), v);
+                    if (c0 == 48) {                                           // last read of this accumulator: hand it back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+                    }
+                    if (whole) {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            const double ks = (double)__uint_as_float(v[c]);  // an integer below 2^24: exact in fp32 and in fp64
+                            const double delta = __dsub_rn(ks, m[c0 + c]);
+                            const double nh = __dadd_rn(m[c0 + c], div_by_iter(delta, diter, riter));
+                            m[c0 + c] = nh;
+                            acc = __dadd_rn(acc, __dmul_rn(delta, __dsub_rn(ks, nh)));
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            const double ks = (double)__uint_as_float(v[c]);
+                            const double delta = __dsub_rn(ks, m[c0 + c]);
+                            const double nh = __dadd_rn(m[c0 + c], div_by_iter(delta, diter, riter));
+                            m[c0 + c] = nh;
+                            if (c0 + c < ncount) acc = __dadd_rn(acc, __dmul_rn(delta, __dsub_rn(ks, nh)));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+                if (lane == 0) wf->sums[(size_t)(slot0 + d) * wf->sums_stride + (size_t)blockIdx.x * 8 + half * 4 + q] = acc;
+            }
+#pragma unroll
+            for (int c = 0; c < 64; ++c) kout[c * 32] = m[c];
+        } else {
         // every cell of the warp's 32 x 64 strip is inside the triangle and the matrix (all but the diagonal and last tiles)
         const bool inside = ibase + 31 < nseq && j0 + 63 <= ibase;
         const bool all_train = ibase + 31 < n_train;
@@ -476,6 +550,7 @@ syrk_tc_welford_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t*
             for (int o = 16; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
             if (lane == 0) wf->sums[(size_t)(slot0 + d) * wf->sums_stride + (size_t)blockIdx.x * 8 + half * 4 + q] = acc;
         }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -485,17 +560,37 @@ syrk_tc_welford_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t*
     }
 }
 
-// dst (packed lower triangle) += src (tile-major running mean of one stream): Ksfinal += K_hat (fastsk_kernel.cpp:296-313)
+// dst (packed lower triangle) += src (tile-major running mean of one stream): Ksfinal += K_hat (fastsk_kernel.cpp:296-313).
+// strips = 0: tiles stored row-major; 1: strip-major (syrk_tc_welford_kernel<true>), transposed through shared memory so
+// that both the reads and the updates of the triangle's rows are coalesced.
 __global__ void __launch_bounds__(256)
-welford_untile_kernel(double* __restrict__ dst, const double* __restrict__ src, const uint32_t* __restrict__ tile_order, int64_t nseq) {
+welford_untile_kernel(double* __restrict__ dst, const double* __restrict__ src, const uint32_t* __restrict__ tile_order, int64_t nseq, int strips) {
+    __shared__ double sm[64 * 33];
     const uint32_t ij = tile_order[blockIdx.x];
     const int64_t I = ij >> 16, J = ij & 0xffffu;
     const double* __restrict__ t = src + ((size_t)I * (I + 1) / 2 + J) * (size_t)(DG_TILE * DG_TILE);
-    for (int e = threadIdx.x; e < DG_TILE * DG_TILE; e += 256) {
-        const int64_t i = I * DG_TILE + (e >> 7), j = J * DG_TILE + (e & 127);
-        if (i < nseq && j <= i) {
-            const size_t p = (size_t)(i * (i + 1) / 2 + j);
-            dst[p] = __dadd_rn(dst[p], t[e]);
+    if (!strips) {
+        for (int e = threadIdx.x; e < DG_TILE * DG_TILE; e += 256) {
+            const int64_t i = I * DG_TILE + (e >> 7), j = J * DG_TILE + (e & 127);
+            if (i < nseq && j <= i) {
+                const size_t p = (size_t)(i * (i + 1) / 2 + j);
+                dst[p] = __dadd_rn(dst[p], t[e]);
+            }
+        }
+        return;
+    }
+    for (int strip = 0; strip < 8; ++strip) {
+        const int q = strip >> 1, half = strip & 1;
+        __syncthreads();
+        for (int e = threadIdx.x; e < 2048; e += 256) sm[(e >> 5) * 33 + (e & 31)] = t[strip * 2048 + e];   // [column][row]
+        __syncthreads();
+        for (int e = threadIdx.x; e < 2048; e += 256) {
+            const int r = e >> 6, c = e & 63;
+            const int64_t i = I * DG_TILE + q * 32 + r, j = J * DG_TILE + half * 64 + c;
+            if (i < nseq && j <= i) {
+                const size_t p = (size_t)(i * (i + 1) / 2 + j);
+                dst[p] = __dadd_rn(dst[p], sm[c * 33 + r]);
+            }
         }
     }
 }

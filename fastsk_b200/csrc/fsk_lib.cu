@@ -131,6 +131,7 @@ struct fsk_handle {
     uint32_t dir_nb = 0;
     uint16_t* d_wkey = nullptr;
     uint2* d_tdir[2] = {nullptr, nullptr};
+    int opt_wf_regs = 1;                               // tensor-core variance mode: running means in registers across a round's slots (0: streamed through L2)
     int opt_fit_smem = 1;                              // accumulate launches ask for the shared memory of their longest row only
     int opt_pf_stride = 128;                           // L2 prefetch granularity of the accumulate's id ranges (64 or 128 bytes)
     int opt_seg_lean = 0;                              // 0 auto (on for records that carry the id), 1 off, 2 on: register-blocked segmentation
@@ -626,7 +627,8 @@ int run_batch_dense(fsk_handle* h, int nb, const BatchSpec& spec, unsigned long 
         const unsigned T = (unsigned)((h->N + DG_TILE - 1) / DG_TILE);
         const unsigned tiles = T * (T + 1) / 2;
         if (h->wf_active) {   // variance mode: every stream's tiles walk the stream's slots in order (Welford in the epilogue)
-            syrk_tc_welford_kernel<<<dim3(tiles, (unsigned)h->wf_groups), DW_THREADS, dw_smem(), h->ls>>>(h->tmap_C, h->d_tile_order, h->N, h->nks, h->d_wf);
+            if (h->opt_wf_regs) syrk_tc_welford_kernel<true><<<dim3(tiles, (unsigned)h->wf_groups), DW_THREADS, dw_smem(true), h->ls>>>(h->tmap_C, h->d_tile_order, h->N, h->nks, h->d_wf);
+            else syrk_tc_welford_kernel<false><<<dim3(tiles, (unsigned)h->wf_groups), DW_THREADS, dw_smem(false), h->ls>>>(h->tmap_C, h->d_tile_order, h->N, h->nks, h->d_wf);
             h->launches++;
         } else {
             for (int c0 = 0; c0 < nb; c0 += h->dense_chunk) {
@@ -769,7 +771,8 @@ int encode_operand_map(fsk_handle* h, CUtensorMap* map, __half* ptr, size_t ld) 
     if (cr != CUDA_SUCCESS) return fail(h, FSK_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
     CU(smem_opt_in(syrk_tc_kernel<1>, (int)dg_smem(1)));
     CU(smem_opt_in(syrk_tc_kernel<2>, (int)dg_smem(2)));
-    CU(smem_opt_in(syrk_tc_welford_kernel, (int)dw_smem()));
+    CU(smem_opt_in(syrk_tc_welford_kernel<true>, (int)dw_smem(true)));
+    CU(smem_opt_in(syrk_tc_welford_kernel<false>, (int)dw_smem(false)));
     return FSK_OK;
 }
 
@@ -995,7 +998,7 @@ void sync_team(fsk_handle* h) {
         w->profile = h->profile; w->opt_pad = h->opt_pad; w->opt_acc_cols = h->opt_acc_cols; w->opt_heavy_tau = h->opt_heavy_tau;
         w->opt_ids32 = h->opt_ids32; w->opt_gemm_shape = h->opt_gemm_shape; w->opt_heavy_cap = h->opt_heavy_cap;
         w->out_weights = h->out_weights;
-        w->opt_seg_lean = h->opt_seg_lean; w->opt_spec_depth = h->opt_spec_depth; w->opt_pf_stride = h->opt_pf_stride; w->opt_fit_smem = h->opt_fit_smem;
+        w->opt_seg_lean = h->opt_seg_lean; w->opt_spec_depth = h->opt_spec_depth; w->opt_pf_stride = h->opt_pf_stride; w->opt_fit_smem = h->opt_fit_smem; w->opt_wf_regs = h->opt_wf_regs;
         w->opt_seg_dir = h->opt_seg_dir; w->opt_dir_blocks = h->opt_dir_blocks; w->opt_count_updates = h->opt_count_updates;
     }
 }
@@ -1136,6 +1139,8 @@ int fsk_set_option(fsk_handle* h, const char* key, int64_t value) {
         h->opt_seg_dir = (int)value;
     } else if (!strcmp(key, "fit_smem")) {
         h->opt_fit_smem = value != 0;
+    } else if (!strcmp(key, "wf_regs")) {
+        h->opt_wf_regs = value != 0;
     } else if (!strcmp(key, "pf_stride")) {
         if (value != 64 && value != 128) return fail(h, FSK_EINVAL, "pf_stride must be 64 or 128");
         h->opt_pf_stride = (int)value;
@@ -1858,7 +1863,7 @@ int build_partial_once(fsk_handle* h) {
         }
         // merge (fastsk_kernel.cpp:296-313): sum of the streams' running means, in stream order
         for (auto& s : streams) {
-            if (h->dense_path) welford_untile_kernel<<<(unsigned)(Ttiles * (Ttiles + 1) / 2), 256, 0, h->stream>>>(h->d_Kf, s.cur, h->d_tile_order, h->N);
+            if (h->dense_path) welford_untile_kernel<<<(unsigned)(Ttiles * (Ttiles + 1) / 2), 256, 0, h->stream>>>(h->d_Kf, s.cur, h->d_tile_order, h->N, h->opt_wf_regs);
             else add_f64_kernel<<<592, 256, 0, h->stream>>>(h->d_Kf, s.cur, h->n_pairs);
             h->launches++;
         }

@@ -646,6 +646,33 @@ def test_speculated_variance_rounds_equal_the_iteration_by_iteration_build(FastS
             assert np.array_equal(got[0], base[0]) and got[1] == base[1], f"depth {depth}"
 
 
+@pytest.mark.parametrize("T,depth", [(1, 0), (3, 0), (2, 1), (1, 7)])
+def test_running_means_kept_in_registers_equal_the_streamed_form(FastSK, oracle_mod, T, depth):
+    """Tensor-core variance mode, wf_regs = 1 (default): a thread keeps its 64 cells of the running mean in registers over all
+    the slots of a round and the tiles are stored strip-major.  Same Welford steps per cell as the streamed form (wf_regs =
+    0): the means must be bit-equal, the stdevs equal up to the order of one fp64 sum, both equal to the oracle.  300
+    sequences: full, diagonal and ragged tiles, test rows below the training rows."""
+    rng = np.random.default_rng(77 + T)
+    g, m = 9, 5
+    X = random_seqs(rng, 300, 4, 20, 70)
+    queue = rng.permutation(comb(g, m)).astype(np.int32)
+    K, _, sd = oracle_mod.run("c", X[:210], X[210:], g, m, queue, T=T, approx=True, delta=0.05, max_iters=23)
+    got = []
+    for regs in (1, 0):
+        f = FastSK(g, m, T, True, 0.05, 23, False, combo_sequence=queue)
+        f.set_option("acc_path", 3)
+        f.set_option("wf_regs", regs)
+        f.set_option("spec_depth", depth)
+        f.compute_kernel(X[:210], X[210:])
+        got.append((f.get_unnormalised(np.float64), f.get_stdevs(), f.get_train_kernel(), f.get_test_kernel()))
+        assert len(got[-1][1]) == len(sd)
+        np.testing.assert_allclose(got[-1][1], sd, rtol=RTOL, atol=0)
+        np.testing.assert_allclose(got[-1][0], K, rtol=RTOL, atol=0)
+    assert np.array_equal(got[0][0], got[1][0])
+    assert np.array_equal(got[0][2], got[1][2]) and np.array_equal(got[0][3], got[1][3])
+    np.testing.assert_allclose(got[0][1], got[1][1], rtol=RTOL, atol=0)
+
+
 @pytest.mark.parametrize("acc_path", [2, 3], ids=["rows", "dense_tc"])
 @pytest.mark.parametrize("name", ["1.1", "EP300"])
 def test_full_bundled_sets_against_the_reference_fingerprints(FastSK, name, acc_path):
