@@ -322,7 +322,8 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restr
 constexpr int DW_STAGES = 2, DW_STAGES_REGS = 4;
 constexpr uint32_t DW_STAGE_BYTES = 2 * DG_TILE_BYTES;
 constexpr int DW_EPI_WARPS = 8;                                   // two epilogue warps per TMEM lane quarter, 64 columns each
-constexpr int DW_THREADS = 64 + 32 * DW_EPI_WARPS;                // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
+constexpr int DW_THREADS = 64 + 32 * DW_EPI_WARPS;                // streamed form: warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int DW_THREADS_REGS = 128 + 32 * DW_EPI_WARPS;         // register form: one producer warpgroup (TMA, MMA, TMEM allocation, idle) + two epilogue warpgroups
 constexpr uint32_t DW_TS_BYTES = DW_EPI_WARPS * 32 * 33 * 4;      // one padded 32 x 32 fp32 transpose buffer per epilogue warp
 __host__ __device__ constexpr size_t dw_smem(bool regs) { return (size_t)(regs ? DW_STAGES_REGS : DW_STAGES) * DW_STAGE_BYTES + DW_TS_BYTES + 1024 + 256; }
 
@@ -336,9 +337,12 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // streaming form moved 2 x 8 bytes per cell and iteration: 6.8 GB for 50 iterations of EP300, all of the kernel's time).
 // The means are then stored STRIP-MAJOR inside a tile: cell (row 32 q + lane, column 64 half + c) at
 // ((2 q + half) * 64 + c) * 32 + lane, so that the one load and the one store are coalesced (welford_untile_kernel knows).
-// One CTA per SM (128 of a thread's registers are means); !REGS is the streaming form, two CTAs per SM.
+// One CTA per SM; 128 of an epilogue thread's registers are means, so the epilogue warpgroups take 232 registers and the
+// producer warpgroup gives its own back (setmaxnreg): with the 168 registers a 12-warp CTA starts with, ptxas ran the eight
+// dependent fp64 operations of one cell after the other (r2s35: fp64 pipe 33 %, stall_wait 3.5 per issue); with room for
+// eight cells in flight the two epilogue warps of a scheduler keep the fp64 pipe busy.  !REGS is the streaming form.
 template <bool REGS>
-__global__ void __launch_bounds__(DW_THREADS, REGS ? 1 : 2)
+__global__ void __launch_bounds__(REGS ? DW_THREADS_REGS : DW_THREADS, REGS ? 1 : 2)
 syrk_tc_welford_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restrict__ tile_order, int64_t nseq, uint32_t nks,
                        const WelfordSpec* __restrict__ wf) {
     extern __shared__ uint8_t dw_smem_raw[];
@@ -372,7 +376,9 @@ syrk_tc_welford_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t*
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
-
+    constexpr int EPI0 = REGS ? 4 : 2;                            // first epilogue warp
+    if (warp < EPI0) {                                            // the producer warps: all of their code inside this branch,
+        if constexpr (REGS) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");   // so that ptxas budgets each side
     if (warp == 0) {
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
@@ -412,7 +418,9 @@ syrk_tc_welford_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t*
             }
         }
         __syncwarp();
+    }
     } else {
+        if constexpr (REGS) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
         // The accumulator comes out of TMEM one row per thread; it goes through a padded shared-memory transpose so that the 32
         // lanes of a warp touch 32 CONSECUTIVE cells of one row of the packed triangle (coalesced 256-byte accesses; streaming a
         // row per thread instead measured 40 % slower: 32 sectors per load instruction).  The 32 cells a lane owns in a
@@ -423,8 +431,8 @@ syrk_tc_welford_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t*
         // cells, row-major): the cell of row r, column c of the tile is at a compile-time offset from the warp's base pointer,
         // so the inner loop has no address arithmetic at all (the packed triangle cost ~30 of 53 instructions per cell: ncu,
         // profiles/r02_ncu_welford_*).  welford_untile_kernel adds the tiles into the packed triangle once, at the end.
-        const uint32_t q = (uint32_t)warp & 3u, half = (uint32_t)(warp - 2) >> 2;
-        float* __restrict__ ts = reinterpret_cast<float*>(dw_smem_raw + (ts_base - raw)) + (warp - 2) * (32 * 33);
+        const uint32_t q = (uint32_t)warp & 3u, half = (uint32_t)(warp - EPI0) >> 2;
+        float* __restrict__ ts = reinterpret_cast<float*>(dw_smem_raw + (ts_base - raw)) + (warp - EPI0) * (32 * 33);
         const int64_t j0 = (int64_t)J * DG_TILE + half * 64;
         const int64_t ibase = (int64_t)I * DG_TILE + q * 32;
         const int64_t n_train = wf->n_train;
@@ -433,9 +441,12 @@ syrk_tc_welford_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t*
             const double* __restrict__ kin = wf->khat_in[g] + tcell;
             double* __restrict__ kout = wf->khat_out[g] + tcell;
             const int64_t i = ibase + lane;                               // this thread's row of the kernel matrix
-            // cells of the strip that count for the variance: training rows, columns up to the diagonal
+            // cells of the strip that count for the variance: training rows, columns up to the diagonal.  Warp-uniform cases:
+            // all 32 x 64 of them, none of them (test rows -- most tiles when the test set is large -- and strips above the
+            // diagonal: the mean is still updated, the variance terms are not even computed), or some (select, no branches)
             const bool whole = ibase + 31 < n_train && j0 + 63 <= ibase;
-            const int64_t ncount = i < n_train ? i - j0 + 1 : 0;          // columns c < ncount count
+            const bool none = ibase >= n_train || j0 > ibase + 31;
+            const int ncount = i < n_train ? (int)max((int64_t)0, min((int64_t)64, i - j0 + 1)) : 0;   // columns c < ncount count
             double m[64];
 #pragma unroll
             for (int c = 0; c < 64; ++c) m[c] = kin[c * 32];
@@ -443,7 +454,9 @@ syrk_tc_welford_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t*
                 const uint32_t buf = d & 1u;
                 const double diter = (double)(wf->iter0[g] + (int32_t)d);
                 const double riter = __ddiv_rn(1.0, diter);
-                double acc = 0.0;
+                double acc8[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc8[u] = 0.0;
                 mbar_wait(tfull0 + 8 * buf, (d >> 1) & 1u);
                 tc_fence_after();
 #pragma unroll
@@ -455,26 +468,34 @@ syrk_tc_welford_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t*
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
                     }
-                    if (whole) {
+                    // eight cells at a time, stage by stage: eight independent chains for the fp64 pipe
 #pragma unroll
-                        for (int c = 0; c < 16; ++c) {
-                            const double ks = (double)__uint_as_float(v[c]);  // an integer below 2^24: exact in fp32 and in fp64
-                            const double delta = __dsub_rn(ks, m[c0 + c]);
-                            const double nh = __dadd_rn(m[c0 + c], div_by_iter(delta, diter, riter));
-                            m[c0 + c] = nh;
-                            acc = __dadd_rn(acc, __dmul_rn(delta, __dsub_rn(ks, nh)));
-                        }
-                    } else {
+                    for (int h = 0; h < 16; h += 8) {
+                        double ks[8], delta[8], t[8];
 #pragma unroll
-                        for (int c = 0; c < 16; ++c) {
-                            const double ks = (double)__uint_as_float(v[c]);
-                            const double delta = __dsub_rn(ks, m[c0 + c]);
-                            const double nh = __dadd_rn(m[c0 + c], div_by_iter(delta, diter, riter));
-                            m[c0 + c] = nh;
-                            if (c0 + c < ncount) acc = __dadd_rn(acc, __dmul_rn(delta, __dsub_rn(ks, nh)));
+                        for (int u = 0; u < 8; ++u) ks[u] = (double)__uint_as_float(v[h + u]);   // integers below 2^24: exact
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) delta[u] = __dsub_rn(ks[u], m[c0 + h + u]);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) t[u] = __dmul_rn(delta[u], riter);            // div_by_iter, staged
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) t[u] = __fma_rn(__fma_rn(-t[u], diter, delta[u]), riter, t[u]);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) m[c0 + h + u] = __dadd_rn(m[c0 + h + u], t[u]);
+                        if (none) continue;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) t[u] = __dmul_rn(delta[u], __dsub_rn(ks[u], m[c0 + h + u]));
+                        if (whole) {
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) acc8[u] = __dadd_rn(acc8[u], t[u]);
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) acc8[u] = __dadd_rn(acc8[u], c0 + h + u < ncount ? t[u] : 0.0);
                         }
                     }
                 }
+                double acc = __dadd_rn(__dadd_rn(__dadd_rn(acc8[0], acc8[1]), __dadd_rn(acc8[2], acc8[3])),
+                                       __dadd_rn(__dadd_rn(acc8[4], acc8[5]), __dadd_rn(acc8[6], acc8[7])));
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
                 if (lane == 0) wf->sums[(size_t)(slot0 + d) * wf->sums_stride + (size_t)blockIdx.x * 8 + half * 4 + q] = acc;

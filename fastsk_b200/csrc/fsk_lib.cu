@@ -627,7 +627,7 @@ int run_batch_dense(fsk_handle* h, int nb, const BatchSpec& spec, unsigned long 
         const unsigned T = (unsigned)((h->N + DG_TILE - 1) / DG_TILE);
         const unsigned tiles = T * (T + 1) / 2;
         if (h->wf_active) {   // variance mode: every stream's tiles walk the stream's slots in order (Welford in the epilogue)
-            if (h->opt_wf_regs) syrk_tc_welford_kernel<true><<<dim3(tiles, (unsigned)h->wf_groups), DW_THREADS, dw_smem(true), h->ls>>>(h->tmap_C, h->d_tile_order, h->N, h->nks, h->d_wf);
+            if (h->opt_wf_regs) syrk_tc_welford_kernel<true><<<dim3(tiles, (unsigned)h->wf_groups), DW_THREADS_REGS, dw_smem(true), h->ls>>>(h->tmap_C, h->d_tile_order, h->N, h->nks, h->d_wf);
             else syrk_tc_welford_kernel<false><<<dim3(tiles, (unsigned)h->wf_groups), DW_THREADS, dw_smem(false), h->ls>>>(h->tmap_C, h->d_tile_order, h->N, h->nks, h->d_wf);
             h->launches++;
         } else {
