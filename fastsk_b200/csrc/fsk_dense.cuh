@@ -41,7 +41,9 @@ constexpr int DENSE_MAX_KEYS = 4096;
 // maxwin <= 2048) and writes the slot's row segment as fp16 (padding columns zero).  Warp-level synchronisation only.
 constexpr int DENSE_COUNT_WARPS = 8;
 constexpr int DENSE_MAX_SEG = 12;          // at most 12 key bits, so at most 12 stretches of kept characters
-template <typename GwT, int NW>
+// U8: the counts are written as bytes (the caller knows that no sequence has more than 255 windows): operands of the
+// kind::i8 contraction of syrk_tc_welford_kernel, half the bytes per k-mer column; ld is then in bytes.
+template <typename GwT, int NW, bool U8 = false>
 __global__ void __launch_bounds__(DENSE_COUNT_WARPS * 32)
 dense_count_kernel(const GwT* __restrict__ gw0, const uint64_t* __restrict__ gw1, const uint32_t* __restrict__ woff,
                    uint32_t nks, size_t ld, int nb, __half* __restrict__ C, const __grid_constant__ BatchSpec spec) {
@@ -77,10 +79,18 @@ dense_count_kernel(const GwT* __restrict__ gw0, const uint64_t* __restrict__ gw1
             atomicAdd(&hist[kk >> 1], 1u << ((kk & 1u) << 4));
         }
         __syncwarp();
+        if constexpr (U8) {
+            unsigned short* __restrict__ out = reinterpret_cast<unsigned short*>(reinterpret_cast<uint8_t*>(C) + (size_t)seq * ld + (size_t)slot * nks);
+            for (uint32_t i = lane; i < words; i += 32) {
+                const uint32_t w = hist[i];
+                out[i] = (unsigned short)((w & 0xffu) | ((w >> 16) << 8));
+            }
+        } else {
         __half2* __restrict__ out = reinterpret_cast<__half2*>(C + (size_t)seq * ld + (size_t)slot * nks);
         for (uint32_t i = lane; i < words; i += 32) {
             const uint32_t w = hist[i];
             out[i] = __halves2half2(__ushort2half_rn((unsigned short)(w & 0xffffu)), __ushort2half_rn((unsigned short)(w >> 16)));
+        }
         }
         __syncwarp();
     }
@@ -136,6 +146,15 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// kind::i8: A = B = unsigned bytes, D = int32; UMMA_K = 32 bytes, the same 32-byte descriptor step as kind::f16
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets row (lane base + t)
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -176,6 +195,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // kind::f16 instruction descriptor: D = fp32, A = B = fp16, both K-major, N at bit 17 (>> 3), M at bit 24 (>> 4)
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// kind::i8 instruction descriptor: D = int32 (format 2 at bit 4), A = B = uint8 (format 0 at bits 7 and 10), both K-major
+__host__ __device__ constexpr uint32_t umma_idesc_u8(int M, int N) {
+    return (2u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // grid = (lower-triangle tiles T (T + 1) / 2 in tile_order -- pairs of tile rows for NA = 2 --, groups).  Group `g` contracts the columns [k_begin + g * k_group,
@@ -341,7 +364,11 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // producer warpgroup gives its own back (setmaxnreg): with the 168 registers a 12-warp CTA starts with, ptxas ran the eight
 // dependent fp64 operations of one cell after the other (r2s35: fp64 pipe 33 %, stall_wait 3.5 per issue); with room for
 // eight cells in flight the two epilogue warps of a scheduler keep the fp64 pipe busy.  !REGS is the streaming form.
-template <bool REGS>
+// U8 (register form only): byte operands and int32 accumulators (kind::i8) when no sequence has more than 255 windows --
+// the operand tiles, which at 256 k-mer columns per slot cost more shared-memory fill time (128 KB per tile and slot at
+// ~43 B/clk per SM) than the Welford arithmetic, halve; and the int32 count becomes a double with one fp64 addition
+// (2^52 + v built from the bits, minus 2^52) instead of a quarter-rate conversion.
+template <bool REGS, bool U8 = false>
 __global__ void __launch_bounds__(REGS ? DW_THREADS_REGS : DW_THREADS, REGS ? 1 : 2)
 syrk_tc_welford_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restrict__ tile_order, int64_t nseq, uint32_t nks,
                        const WelfordSpec* __restrict__ wf) {
@@ -360,7 +387,9 @@ syrk_tc_welford_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t*
     const bool diag = I == J;
     const int g = blockIdx.y;
     const uint32_t depth = wf->depth[g], slot0 = wf->slot0[g];
-    const uint32_t nkb = nks / DG_BK;
+    static_assert(REGS || !U8, "byte operands: register form only");
+    constexpr uint32_t BK = U8 ? 2 * DG_BK : DG_BK;              // elements per k-block: one 128-byte swizzle row either way
+    const uint32_t nkb = nks / BK;
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -389,7 +418,7 @@ syrk_tc_welford_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t*
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
                 mbar_arrive_expect_tx(full0 + 8 * s, tx);
                 const uint32_t a = base + s * DW_STAGE_BYTES;
-                const int x = (int)((slot0 + t / nkb) * nks + (t % nkb) * DG_BK);
+                const int x = (int)((slot0 + t / nkb) * nks + (t % nkb) * BK);
                 tma_load_2d(a, &tmap, full0 + 8 * s, x, (int)(I * DG_TILE));
                 if (!diag) tma_load_2d(a + DG_TILE_BYTES, &tmap, full0 + 8 * s, x, (int)(J * DG_TILE));
             }
@@ -397,7 +426,7 @@ syrk_tc_welford_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t*
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(DG_TILE, DG_TILE);
+            constexpr uint32_t idesc = U8 ? umma_idesc_u8(DG_TILE, DG_TILE) : umma_idesc_f16(DG_TILE, DG_TILE);
             uint32_t t = 0;
             for (uint32_t d = 0; d < depth; ++d) {
                 const uint32_t buf = d & 1u;
@@ -410,8 +439,10 @@ syrk_tc_welford_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t*
                     const uint32_t a = base + s * DW_STAGE_BYTES;
                     const uint64_t adesc = umma_desc_sw128(a), bdesc = umma_desc_sw128(diag ? a : a + DG_TILE_BYTES);
 #pragma unroll
-                    for (uint32_t k = 0; k < DG_BK / 16; ++k)
-                        tc_mma_f16(tmem_base + buf * 128u, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0u);
+                    for (uint32_t k = 0; k < DG_BK / 16; ++k) {          // four 32-byte steps along the swizzled row
+                        if constexpr (U8) tc_mma_i8(tmem_base + buf * 128u, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0u);
+                        else tc_mma_f16(tmem_base + buf * 128u, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0u);
+                    }
                     tc_commit(empty0 + 8 * s);
                 }
                 tc_commit(tfull0 + 8 * buf);
@@ -473,7 +504,9 @@ syrk_tc_welford_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t*
                     for (int h = 0; h < 16; h += 8) {
                         double ks[8], delta[8], t[8];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) ks[u] = (double)__uint_as_float(v[h + u]);   // integers below 2^24: exact
+                        for (int u = 0; u < 8; ++u)
+                            ks[u] = U8 ? __dsub_rn(__hiloint2double(0x43300000, (int)v[h + u]), 4503599627370496.0)   // (2^52 + v) - 2^52
+                                       : (double)__uint_as_float(v[h + u]);                                          // integers below 2^24: exact
 #pragma unroll
                         for (int u = 0; u < 8; ++u) delta[u] = __dsub_rn(ks[u], m[c0 + h + u]);
 #pragma unroll

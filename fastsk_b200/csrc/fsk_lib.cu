@@ -131,6 +131,7 @@ struct fsk_handle {
     uint32_t dir_nb = 0;
     uint16_t* d_wkey = nullptr;
     uint2* d_tdir[2] = {nullptr, nullptr};
+    int opt_wf_u8 = 1;                                 // ... with byte operands when no sequence has more than 255 windows (0: always fp16)
     int opt_wf_regs = 1;                               // tensor-core variance mode: running means in registers across a round's slots (0: streamed through L2)
     int opt_fit_smem = 1;                              // accumulate launches ask for the shared memory of their longest row only
     int opt_pf_stride = 128;                           // L2 prefetch granularity of the accumulate's id ranges (64 or 128 bytes)
@@ -176,6 +177,7 @@ struct fsk_handle {
     uint32_t pair_tiles = 0;
     uint32_t* d_tile_order = nullptr;                  // lower-triangle tiles (I << 16 | J) in L2-friendly launch order
     CUtensorMap tmap_C;
+    bool wf_regs = false, dense_u8 = false;            // fixed at upload: form of the Welford contraction, byte operands (ld of d_C then in bytes)
     unsigned long long* d_Kint = nullptr;   // integer partial (exact / skip_variance), or per-slot Ks in variance mode
     int ks_slots = 1;
     std::vector<double*> d_Khat;            // one per local virtual stream
@@ -613,7 +615,14 @@ int run_batch_dense(fsk_handle* h, int nb, const BatchSpec& spec, unsigned long 
         dim3 grid((unsigned)h->N);
         const size_t smem = (size_t)DENSE_COUNT_WARPS * h->nks * 2;
         constexpr int CT = DENSE_COUNT_WARPS * 32;
-        if (h->NW == 2)
+        if (h->dense_u8) {
+            if (h->NW == 2)
+                dense_count_kernel<uint64_t, 2, true><<<grid, CT, smem, h->ls>>>((const uint64_t*)h->d_gw0, h->d_gw1, h->d_woff32, h->nks, h->dense_ld, nb, h->d_C, spec);
+            else if (h->gw32)
+                dense_count_kernel<uint32_t, 1, true><<<grid, CT, smem, h->ls>>>((const uint32_t*)h->d_gw0, nullptr, h->d_woff32, h->nks, h->dense_ld, nb, h->d_C, spec);
+            else
+                dense_count_kernel<uint64_t, 1, true><<<grid, CT, smem, h->ls>>>((const uint64_t*)h->d_gw0, nullptr, h->d_woff32, h->nks, h->dense_ld, nb, h->d_C, spec);
+        } else if (h->NW == 2)
             dense_count_kernel<uint64_t, 2><<<grid, CT, smem, h->ls>>>((const uint64_t*)h->d_gw0, h->d_gw1, h->d_woff32, h->nks, h->dense_ld, nb, h->d_C, spec);
         else if (h->gw32)
             dense_count_kernel<uint32_t, 1><<<grid, CT, smem, h->ls>>>((const uint32_t*)h->d_gw0, nullptr, h->d_woff32, h->nks, h->dense_ld, nb, h->d_C, spec);
@@ -627,7 +636,8 @@ int run_batch_dense(fsk_handle* h, int nb, const BatchSpec& spec, unsigned long 
         const unsigned T = (unsigned)((h->N + DG_TILE - 1) / DG_TILE);
         const unsigned tiles = T * (T + 1) / 2;
         if (h->wf_active) {   // variance mode: every stream's tiles walk the stream's slots in order (Welford in the epilogue)
-            if (h->opt_wf_regs) syrk_tc_welford_kernel<true><<<dim3(tiles, (unsigned)h->wf_groups), DW_THREADS_REGS, dw_smem(true), h->ls>>>(h->tmap_C, h->d_tile_order, h->N, h->nks, h->d_wf);
+            if (h->dense_u8) syrk_tc_welford_kernel<true, true><<<dim3(tiles, (unsigned)h->wf_groups), DW_THREADS_REGS, dw_smem(true), h->ls>>>(h->tmap_C, h->d_tile_order, h->N, h->nks, h->d_wf);
+            else if (h->wf_regs) syrk_tc_welford_kernel<true><<<dim3(tiles, (unsigned)h->wf_groups), DW_THREADS_REGS, dw_smem(true), h->ls>>>(h->tmap_C, h->d_tile_order, h->N, h->nks, h->d_wf);
             else syrk_tc_welford_kernel<false><<<dim3(tiles, (unsigned)h->wf_groups), DW_THREADS, dw_smem(false), h->ls>>>(h->tmap_C, h->d_tile_order, h->N, h->nks, h->d_wf);
             h->launches++;
         } else {
@@ -753,7 +763,7 @@ int run_batch(fsk_handle* h, const int32_t* combos, int nb, unsigned long long* 
 // TMA descriptor of a K-major fp16 operand matrix [N rows][ld columns]: boxes of 128 rows x 64 columns landing with the 128-byte
 // swizzle the UMMA descriptors of syrk_tc_kernel expect; rows past N read as zero.  cuTensorMapEncodeTiled is resolved through
 // the runtime (no link-time dependency on libcuda).
-int encode_operand_map(fsk_handle* h, CUtensorMap* map, __half* ptr, size_t ld) {
+int encode_operand_map(fsk_handle* h, CUtensorMap* map, __half* ptr, size_t ld, bool u8 = false) {   // u8: byte elements, boxes of 128 x 128
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -762,16 +772,17 @@ int encode_operand_map(fsk_handle* h, CUtensorMap* map, __half* ptr, size_t ld) 
     CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
     if (!fn || qres != cudaDriverEntryPointSuccess) return fail(h, FSK_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
     const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)h->N};
-    const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)DG_BK, (cuuint32_t)DG_TILE};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ld * (u8 ? 1 : 2)};
+    const cuuint32_t box[2] = {(cuuint32_t)(u8 ? 2 * DG_BK : DG_BK), (cuuint32_t)DG_TILE};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult cr = ((EncodeFn)fn)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)ptr, gdim, gstride, box, estr,
+    const CUresult cr = ((EncodeFn)fn)(map, u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)ptr, gdim, gstride, box, estr,
                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(h, FSK_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
     CU(smem_opt_in(syrk_tc_kernel<1>, (int)dg_smem(1)));
     CU(smem_opt_in(syrk_tc_kernel<2>, (int)dg_smem(2)));
     CU(smem_opt_in(syrk_tc_welford_kernel<true>, (int)dw_smem(true)));
+    CU(smem_opt_in(syrk_tc_welford_kernel<true, true>, (int)dw_smem(true)));
     CU(smem_opt_in(syrk_tc_welford_kernel<false>, (int)dw_smem(false)));
     return FSK_OK;
 }
@@ -998,7 +1009,7 @@ void sync_team(fsk_handle* h) {
         w->profile = h->profile; w->opt_pad = h->opt_pad; w->opt_acc_cols = h->opt_acc_cols; w->opt_heavy_tau = h->opt_heavy_tau;
         w->opt_ids32 = h->opt_ids32; w->opt_gemm_shape = h->opt_gemm_shape; w->opt_heavy_cap = h->opt_heavy_cap;
         w->out_weights = h->out_weights;
-        w->opt_seg_lean = h->opt_seg_lean; w->opt_spec_depth = h->opt_spec_depth; w->opt_pf_stride = h->opt_pf_stride; w->opt_fit_smem = h->opt_fit_smem; w->opt_wf_regs = h->opt_wf_regs;
+        w->opt_seg_lean = h->opt_seg_lean; w->opt_spec_depth = h->opt_spec_depth; w->opt_pf_stride = h->opt_pf_stride; w->opt_fit_smem = h->opt_fit_smem; w->opt_wf_regs = h->opt_wf_regs; w->opt_wf_u8 = h->opt_wf_u8;
         w->opt_seg_dir = h->opt_seg_dir; w->opt_dir_blocks = h->opt_dir_blocks; w->opt_count_updates = h->opt_count_updates;
     }
 }
@@ -1141,6 +1152,8 @@ int fsk_set_option(fsk_handle* h, const char* key, int64_t value) {
         h->opt_fit_smem = value != 0;
     } else if (!strcmp(key, "wf_regs")) {
         h->opt_wf_regs = value != 0;
+    } else if (!strcmp(key, "wf_u8")) {
+        h->opt_wf_u8 = value != 0;
     } else if (!strcmp(key, "pf_stride")) {
         if (value != 64 && value != 128) return fail(h, FSK_EINVAL, "pf_stride must be 64 or 128");
         h->opt_pf_stride = (int)value;
@@ -1572,14 +1585,20 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         CU(cudaMemcpy(h->d_woff32, w32.data(), sizeof(uint32_t) * (size_t)(N + 1), cudaMemcpyHostToDevice));
     }
     if (h->dense_path) {
-        h->dense_ld = (size_t)B * h->nks;
-        ALLOC(h->d_C, (size_t)N * h->dense_ld);
-        int rc_ = encode_operand_map(h, &h->tmap_C, h->d_C, h->dense_ld);
+        // variance mode: the form of the Welford contraction is fixed here (its means' layout and its operands depend on it)
+        h->wf_regs = h->variance_mode && h->opt_wf_regs;
+        h->dense_u8 = h->wf_regs && h->opt_wf_u8 && maxwin <= 255 && h->nks % (2 * DG_BK) == 0;
+        h->dense_ld = (size_t)B * h->nks;                        // elements per row: bytes when dense_u8
+        ALLOC(h->d_C, h->dense_u8 ? ((size_t)N * h->dense_ld + 1) / 2 : (size_t)N * h->dense_ld);
+        int rc_ = encode_operand_map(h, &h->tmap_C, h->d_C, h->dense_ld, h->dense_u8);
         if (rc_) return rc_;
         const int count_smem = DENSE_COUNT_WARPS * (int)h->nks * 2;
         CU(smem_opt_in(dense_count_kernel<uint64_t, 2>, count_smem));
         CU(smem_opt_in(dense_count_kernel<uint64_t, 1>, count_smem));
         CU(smem_opt_in(dense_count_kernel<uint32_t, 1>, count_smem));
+        CU(smem_opt_in(dense_count_kernel<uint64_t, 2, true>, count_smem));
+        CU(smem_opt_in(dense_count_kernel<uint64_t, 1, true>, count_smem));
+        CU(smem_opt_in(dense_count_kernel<uint32_t, 1, true>, count_smem));
     }
     if (h->heavy_tau) {
         // optional stage: it must not be what makes a large upload run out of memory (K and the outputs are still to come)
@@ -1863,7 +1882,7 @@ int build_partial_once(fsk_handle* h) {
         }
         // merge (fastsk_kernel.cpp:296-313): sum of the streams' running means, in stream order
         for (auto& s : streams) {
-            if (h->dense_path) welford_untile_kernel<<<(unsigned)(Ttiles * (Ttiles + 1) / 2), 256, 0, h->stream>>>(h->d_Kf, s.cur, h->d_tile_order, h->N, h->opt_wf_regs);
+            if (h->dense_path) welford_untile_kernel<<<(unsigned)(Ttiles * (Ttiles + 1) / 2), 256, 0, h->stream>>>(h->d_Kf, s.cur, h->d_tile_order, h->N, h->wf_regs);
             else add_f64_kernel<<<592, 256, 0, h->stream>>>(h->d_Kf, s.cur, h->n_pairs);
             h->launches++;
         }

@@ -646,31 +646,39 @@ def test_speculated_variance_rounds_equal_the_iteration_by_iteration_build(FastS
             assert np.array_equal(got[0], base[0]) and got[1] == base[1], f"depth {depth}"
 
 
-@pytest.mark.parametrize("T,depth", [(1, 0), (3, 0), (2, 1), (1, 7)])
-def test_running_means_kept_in_registers_equal_the_streamed_form(FastSK, oracle_mod, T, depth):
+@pytest.mark.parametrize("T,depth,long_seqs", [(1, 0, False), (3, 0, False), (2, 1, False), (1, 7, False), (2, 0, True)])
+def test_running_means_kept_in_registers_equal_the_streamed_form(FastSK, oracle_mod, T, depth, long_seqs):
     """Tensor-core variance mode, wf_regs = 1 (default): a thread keeps its 64 cells of the running mean in registers over all
-    the slots of a round and the tiles are stored strip-major.  Same Welford steps per cell as the streamed form (wf_regs =
-    0): the means must be bit-equal, the stdevs equal up to the order of one fp64 sum, both equal to the oracle.  300
-    sequences: full, diagonal and ragged tiles, test rows below the training rows."""
+    the slots of a round and the tiles are stored strip-major; with at most 255 windows per sequence the operands are bytes
+    and the accumulators int32 (wf_u8, kind::i8), otherwise fp16 / fp32.  Same Welford steps per cell as the streamed form
+    (wf_regs = 0): the means must be bit-equal, the stdevs equal up to the order of one fp64 sum, all equal to the oracle.
+    300 sequences: full, diagonal and ragged tiles, test rows below the training rows; long_seqs: one sequence of 400
+    characters (391 windows, counts above 255 on a low-complexity stretch) keeps the fp16 operands."""
     rng = np.random.default_rng(77 + T)
     g, m = 9, 5
     X = random_seqs(rng, 300, 4, 20, 70)
+    if long_seqs:
+        X[5] = [1] * 300 + rng.integers(1, 5, 100).tolist()
+        X[250] = [1] * 280 + rng.integers(1, 5, 40).tolist()
     queue = rng.permutation(comb(g, m)).astype(np.int32)
     K, _, sd = oracle_mod.run("c", X[:210], X[210:], g, m, queue, T=T, approx=True, delta=0.05, max_iters=23)
     got = []
-    for regs in (1, 0):
+    for regs, u8 in ((1, 1), (1, 0), (0, 0)):
         f = FastSK(g, m, T, True, 0.05, 23, False, combo_sequence=queue)
         f.set_option("acc_path", 3)
         f.set_option("wf_regs", regs)
+        f.set_option("wf_u8", u8)
         f.set_option("spec_depth", depth)
         f.compute_kernel(X[:210], X[210:])
         got.append((f.get_unnormalised(np.float64), f.get_stdevs(), f.get_train_kernel(), f.get_test_kernel()))
         assert len(got[-1][1]) == len(sd)
         np.testing.assert_allclose(got[-1][1], sd, rtol=RTOL, atol=0)
         np.testing.assert_allclose(got[-1][0], K, rtol=RTOL, atol=0)
-    assert np.array_equal(got[0][0], got[1][0])
-    assert np.array_equal(got[0][2], got[1][2]) and np.array_equal(got[0][3], got[1][3])
-    np.testing.assert_allclose(got[0][1], got[1][1], rtol=RTOL, atol=0)
+    for other in got[1:]:
+        assert np.array_equal(got[0][0], other[0])
+        assert np.array_equal(got[0][2], other[2]) and np.array_equal(got[0][3], other[3])
+        np.testing.assert_allclose(got[0][1], other[1], rtol=RTOL, atol=0)
+    assert got[0][1] == got[1][1]                          # byte and fp16 operands: the same sums in the same order
 
 
 @pytest.mark.parametrize("acc_path", [2, 3], ids=["rows", "dense_tc"])
