@@ -108,6 +108,9 @@ int fsk_output_rows(fsk_handle* h, int64_t* train_r0, int64_t* train_nr, int64_t
  * instead of one filed task per record; at most 16 key bits), "dir_blocks": target number of row blocks (32); "seg_lean": 0 auto, 1 off, 2 on: register-blocked segmentation kernel
  * (records that carry the sequence id); "count_updates": 0 = "profile"
  * times the kernels but does not count entries / runs / pair updates;
+ * "spec_depth": iterations of a virtual stream per launch group in variance mode (0 auto); "wf_regs": 1 (default) the tensor-core
+ * Welford contraction keeps the running means in registers over a round's slots, 0 streams them through L2 every slot; "wf_u8":
+ * 1 (default) byte operands / int32 accumulators for it when no sequence has more than 255 windows, 0 always fp16 / fp32;
  * "acc_prefetch", "acc_unroll", "wave", "rows_threads", "pad", "overlap", "safe_rank": tuning of the row path (defaults are the
  * measured optimum); test hooks: "acc_cols" (forced column-window width of the row path), "ids32" (32-bit id stream) */
 int fsk_set_option(fsk_handle* h, const char* key, int64_t value);
