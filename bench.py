@@ -478,7 +478,7 @@ def run_b200(args):
 def other_workloads(device):
     """BASELINE configs[1] beside the headline: the bundled EP300 TFBS set (4000 x 100 bp DNA, g=10 m=6, exact, all 210
     combinations) through the public API, once per accumulate path.  With 256 distinct k-mers per combination the
-    update is a dense contraction: acc_path 3 builds K += C C^T with tcgen05 MMAs (fsk_dense.cuh); acc_path 2 is the
+    update is a dense contraction: acc_path 3 builds K += C C^T with tcgen05 MMAs (fsk_dense.cuh; byte operands); acc_path 2 is the
     sort + shared-memory row path of the headline workload.  Device milliseconds are CUDA-event spans of the library."""
     tr, te = os.path.join(ROOT, "data", "EP300.train.fasta"), os.path.join(ROOT, "data", "EP300.test.fasta")
     if not (os.path.exists(tr) and os.path.exists(te)):
@@ -511,6 +511,7 @@ def other_workloads(device):
             if path == 3 and st["ms_accumulate"]:
                 n, kdim = st["n_seq"], 256 * st["combos_done"]
                 row["tensor_tflops"] = 2.0 * (n * (n + 128) / 2.0) * kdim / (st["ms_accumulate"] * 1e-3) / 1e12
+                row["tensor_operands"] = "u8 x u8 -> s32 (tcgen05 kind::i8: at most 255 windows per sequence), so these are TOP/s"
             if best is None or row["e2e_s"] < best["e2e_s"]:
                 best = row
             del f

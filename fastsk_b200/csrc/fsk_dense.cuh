@@ -203,7 +203,8 @@ __host__ __device__ constexpr uint32_t umma_idesc_u8(int M, int N) {
 
 // grid = (lower-triangle tiles T (T + 1) / 2 in tile_order -- pairs of tile rows for NA = 2 --, groups).  Group `g` contracts the columns [k_begin + g * k_group,
 // + klen) of C and adds into K + g * out_group_stride (integer modes: one group; variance mode: one per slot).
-template <int NA>
+// U8: byte operands and int32 accumulators (kind::i8; dense_count_kernel<..., true>): half the operand bytes, twice the MMA rate.
+template <int NA, bool U8 = false>
 __global__ void __launch_bounds__(DG_THREADS)
 syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restrict__ tile_order, int64_t nseq, uint32_t k_begin,
                uint32_t k_group, uint32_t klen, unsigned long long* __restrict__ K, size_t out_group_stride,
@@ -232,7 +233,8 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restr
     const uint32_t I = NA == 1 ? ij >> 16 : (ij >> 16) * 2u, J = ij & 0xffffu;
     const bool diag = NA == 1 && I == J;
     const uint32_t kx0 = k_begin + blockIdx.y * k_group;
-    const uint32_t nkb = klen / DG_BK;
+    constexpr uint32_t BK = U8 ? 2 * DG_BK : DG_BK;              // elements per k-block: one 128-byte swizzle row either way
+    const uint32_t nkb = klen / BK;
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < DG_STAGES; ++s) {
@@ -261,7 +263,7 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restr
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);                           // the MMAs that read this stage have completed
                 mbar_arrive_expect_tx(full0 + 8 * s, tx);
                 const uint32_t a = base + s * DG_STAGE_BYTES;
-                const int x = (int)(kx0 + kb * DG_BK);
+                const int x = (int)(kx0 + kb * BK);
                 tma_load_2d(a, &tmap, full0 + 8 * s, x, (int)(I * DG_TILE));
                 if (NA == 2) tma_load_2d(a + DG_TILE_BYTES, &tmap, full0 + 8 * s, x, (int)((I + 1) * DG_TILE));
                 if (!diag) tma_load_2d(a + NA * DG_TILE_BYTES, &tmap, full0 + 8 * s, x, (int)(J * DG_TILE));
@@ -270,7 +272,7 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restr
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(DG_TILE, DG_TILE);
+            constexpr uint32_t idesc = U8 ? umma_idesc_u8(DG_TILE, DG_TILE) : umma_idesc_f16(DG_TILE, DG_TILE);
             for (uint32_t kb = 0; kb < nkb; ++kb) {
                 const uint32_t s = kb % DG_STAGES, ph = (kb / DG_STAGES) & 1u;
                 mbar_wait(full0 + 8 * s, ph);                                 // TMA has landed this stage
@@ -281,8 +283,10 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restr
                 for (int t = 0; t < NA; ++t) {
                     const uint64_t adesc = umma_desc_sw128(a + t * DG_TILE_BYTES);
 #pragma unroll
-                    for (uint32_t k = 0; k < DG_BK / 16; ++k)                 // UMMA_K = 16 fp16 = 32 bytes along the swizzled row
-                        tc_mma_f16(tmem_base + t * 128u, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0u);
+                    for (uint32_t k = 0; k < DG_BK / 16; ++k) {               // UMMA_K = 16 fp16 or 32 bytes = 32 bytes along the swizzled row
+                        if constexpr (U8) tc_mma_i8(tmem_base + t * 128u, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0u);
+                        else tc_mma_f16(tmem_base + t * 128u, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0u);
+                    }
                 }
                 tc_commit(empty0 + 8 * s);                                    // frees the stage once these MMAs are done
             }
@@ -317,7 +321,7 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restr
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int64_t i = ibase + r0 + u;
-                        const uint32_t cnt = __float2uint_rn(ts[(r0 + u) * 33 + lane]);
+                        const uint32_t cnt = U8 ? __float_as_uint(ts[(r0 + u) * 33 + lane]) : __float2uint_rn(ts[(r0 + u) * 33 + lane]);   // (U8: the int32's bits)
                         if (i < nseq && j <= i && cnt)
                             atomicAdd(&Kg[(size_t)(i * (i + 1) / 2 + j)], (unsigned long long)cnt);   // RED.ADD.64: the tile is owned by this CTA
                     }

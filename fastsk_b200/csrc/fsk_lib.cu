@@ -131,7 +131,7 @@ struct fsk_handle {
     uint32_t dir_nb = 0;
     uint16_t* d_wkey = nullptr;
     uint2* d_tdir[2] = {nullptr, nullptr};
-    int opt_wf_u8 = 1;                                 // ... with byte operands when no sequence has more than 255 windows (0: always fp16)
+    int opt_dense_u8 = 1;                              // dense regime: byte operands / int32 accumulators when no sequence has more than 255 windows (0: always fp16 / fp32)
     int opt_wf_regs = 1;                               // tensor-core variance mode: running means in registers across a round's slots (0: streamed through L2)
     int opt_fit_smem = 1;                              // accumulate launches ask for the shared memory of their longest row only
     int opt_pf_stride = 128;                           // L2 prefetch granularity of the accumulate's id ranges (64 or 128 bytes)
@@ -643,8 +643,15 @@ int run_batch_dense(fsk_handle* h, int nb, const BatchSpec& spec, unsigned long 
         } else {
             for (int c0 = 0; c0 < nb; c0 += h->dense_chunk) {
                 const int cs = std::min(h->dense_chunk, nb - c0);
-                if (h->opt_gemm_shape != 1 && (h->opt_gemm_shape == 2 || ((uint32_t)cs * h->nks >= 2048 && T >= 4)))
+                // one tile per CTA (two CTAs per SM: one's epilogue under the other's MMAs) measured faster than the pair shape at
+                // every N from 1 000 to 32 000, byte and fp16 operands alike (profiles/r02_gemm_shape_by_n.txt): the pair is opt-in
+                const bool two = h->opt_gemm_shape == 2;
+                if (two && h->dense_u8)
+                    syrk_tc_kernel<2, true><<<dim3(h->pair_tiles, 1), DG_THREADS, dg_smem(2), h->ls>>>(h->tmap_C, h->d_pair_order, h->N, (uint32_t)c0 * h->nks, 0u, (uint32_t)cs * h->nks, K, 0, nullptr);
+                else if (two)
                     syrk_tc_kernel<2><<<dim3(h->pair_tiles, 1), DG_THREADS, dg_smem(2), h->ls>>>(h->tmap_C, h->d_pair_order, h->N, (uint32_t)c0 * h->nks, 0u, (uint32_t)cs * h->nks, K, 0, nullptr);
+                else if (h->dense_u8)
+                    syrk_tc_kernel<1, true><<<dim3(tiles, 1), DG_THREADS, dg_smem(1), h->ls>>>(h->tmap_C, h->d_tile_order, h->N, (uint32_t)c0 * h->nks, 0u, (uint32_t)cs * h->nks, K, 0, nullptr);
                 else
                     syrk_tc_kernel<1><<<dim3(tiles, 1), DG_THREADS, dg_smem(1), h->ls>>>(h->tmap_C, h->d_tile_order, h->N, (uint32_t)c0 * h->nks, 0u, (uint32_t)cs * h->nks, K, 0, nullptr);
                 h->launches++;
@@ -781,6 +788,8 @@ int encode_operand_map(fsk_handle* h, CUtensorMap* map, __half* ptr, size_t ld, 
     if (cr != CUDA_SUCCESS) return fail(h, FSK_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
     CU(smem_opt_in(syrk_tc_kernel<1>, (int)dg_smem(1)));
     CU(smem_opt_in(syrk_tc_kernel<2>, (int)dg_smem(2)));
+    CU(smem_opt_in(syrk_tc_kernel<1, true>, (int)dg_smem(1)));
+    CU(smem_opt_in(syrk_tc_kernel<2, true>, (int)dg_smem(2)));
     CU(smem_opt_in(syrk_tc_welford_kernel<true>, (int)dw_smem(true)));
     CU(smem_opt_in(syrk_tc_welford_kernel<true, true>, (int)dw_smem(true)));
     CU(smem_opt_in(syrk_tc_welford_kernel<false>, (int)dw_smem(false)));
@@ -1009,7 +1018,7 @@ void sync_team(fsk_handle* h) {
         w->profile = h->profile; w->opt_pad = h->opt_pad; w->opt_acc_cols = h->opt_acc_cols; w->opt_heavy_tau = h->opt_heavy_tau;
         w->opt_ids32 = h->opt_ids32; w->opt_gemm_shape = h->opt_gemm_shape; w->opt_heavy_cap = h->opt_heavy_cap;
         w->out_weights = h->out_weights;
-        w->opt_seg_lean = h->opt_seg_lean; w->opt_spec_depth = h->opt_spec_depth; w->opt_pf_stride = h->opt_pf_stride; w->opt_fit_smem = h->opt_fit_smem; w->opt_wf_regs = h->opt_wf_regs; w->opt_wf_u8 = h->opt_wf_u8;
+        w->opt_seg_lean = h->opt_seg_lean; w->opt_spec_depth = h->opt_spec_depth; w->opt_pf_stride = h->opt_pf_stride; w->opt_fit_smem = h->opt_fit_smem; w->opt_wf_regs = h->opt_wf_regs; w->opt_dense_u8 = h->opt_dense_u8;
         w->opt_seg_dir = h->opt_seg_dir; w->opt_dir_blocks = h->opt_dir_blocks; w->opt_count_updates = h->opt_count_updates;
     }
 }
@@ -1152,8 +1161,8 @@ int fsk_set_option(fsk_handle* h, const char* key, int64_t value) {
         h->opt_fit_smem = value != 0;
     } else if (!strcmp(key, "wf_regs")) {
         h->opt_wf_regs = value != 0;
-    } else if (!strcmp(key, "wf_u8")) {
-        h->opt_wf_u8 = value != 0;
+    } else if (!strcmp(key, "dense_u8")) {
+        h->opt_dense_u8 = value != 0;
     } else if (!strcmp(key, "pf_stride")) {
         if (value != 64 && value != 128) return fail(h, FSK_EINVAL, "pf_stride must be 64 or 128");
         h->opt_pf_stride = (int)value;
@@ -1348,7 +1357,9 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         const uint32_t nks = dense_ok ? (uint32_t)(((1u << h->keybits) + DG_BK - 1) / DG_BK * DG_BK) : 0;
         double keys = 1;
         for (int i = 0; i < h->k; ++i) keys *= A;
-        const double t_dense = 0.5 * (double)N * (double)N * nks / 5e14 + (double)N * nks * 2 / 3e12 + 5e-6;
+        // (byte operands: 2.5e15 int8 op/s measured on the contraction = 1.2e15 MAC/s; fp16: 1.25e15 flop/s = 6e14 MAC/s)
+        const bool u8_ok = h->opt_dense_u8 && maxwin <= 255 && nks % (2 * DG_BK) == 0;
+        const double t_dense = 0.5 * (double)N * (double)N * nks / (u8_ok ? 1.0e15 : 5e14) + (double)N * nks * 2 / 3e12 + 5e-6;
         const double t_sparse = (double)nfeat * (double)nfeat / (2.0 * keys) / 1.2e12 + (double)nfeat * 2.7e-11 + 5e-6;
         if (h->opt_acc_path == 3 && !dense_ok)
             return fail(h, FSK_EINVAL, "acc_path = 3 needs at most 12 key bits and 2048 windows per sequence (key bits = %d, windows = %lld)", h->keybits, (long long)maxwin);
@@ -1587,7 +1598,7 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
     if (h->dense_path) {
         // variance mode: the form of the Welford contraction is fixed here (its means' layout and its operands depend on it)
         h->wf_regs = h->variance_mode && h->opt_wf_regs;
-        h->dense_u8 = h->wf_regs && h->opt_wf_u8 && maxwin <= 255 && h->nks % (2 * DG_BK) == 0;
+        h->dense_u8 = h->opt_dense_u8 && maxwin <= 255 && h->nks % (2 * DG_BK) == 0 && (h->wf_regs || !h->variance_mode);   // (the streamed Welford form is fp16 only)
         h->dense_ld = (size_t)B * h->nks;                        // elements per row: bytes when dense_u8
         ALLOC(h->d_C, h->dense_u8 ? ((size_t)N * h->dense_ld + 1) / 2 : (size_t)N * h->dense_ld);
         int rc_ = encode_operand_map(h, &h->tmap_C, h->d_C, h->dense_ld, h->dense_u8);

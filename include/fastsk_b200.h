@@ -109,8 +109,8 @@ int fsk_output_rows(fsk_handle* h, int64_t* train_r0, int64_t* train_nr, int64_t
  * (records that carry the sequence id); "count_updates": 0 = "profile"
  * times the kernels but does not count entries / runs / pair updates;
  * "spec_depth": iterations of a virtual stream per launch group in variance mode (0 auto); "wf_regs": 1 (default) the tensor-core
- * Welford contraction keeps the running means in registers over a round's slots, 0 streams them through L2 every slot; "wf_u8":
- * 1 (default) byte operands / int32 accumulators for it when no sequence has more than 255 windows, 0 always fp16 / fp32;
+ * Welford contraction keeps the running means in registers over a round's slots, 0 streams them through L2 every slot; "dense_u8":
+ * 1 (default) byte operands / int32 accumulators in the dense regime when no sequence has more than 255 windows, 0 always fp16 / fp32;
  * "acc_prefetch", "acc_unroll", "wave", "rows_threads", "pad", "overlap", "safe_rank": tuning of the row path (defaults are the
  * measured optimum); test hooks: "acc_cols" (forced column-window width of the row path), "ids32" (32-bit id stream) */
 int fsk_set_option(fsk_handle* h, const char* key, int64_t value);

@@ -191,13 +191,23 @@ def test_dense_tensor_core_path_multi_tile_and_chunked(FastSK, oracle_mod):
     X = random_seqs(rng, 333, 4, 60, 100)
     queue = rng.permutation(comb(g, m))[:100].astype(np.int32)   # 100 combinations: a full batch of 96 and a rest
     _, Ki, _ = oracle_mod.run("c", X[:250], X[250:], g, m, queue)
-    for shape in (0, 1, 2):                                   # auto; one tile per CTA; two tiles per CTA sharing the B operand
-        f = FastSK(g, m, combo_sequence=queue)                # (three tile rows: the second pair's lower tile is past the last row)
-        f.set_option("gemm_shape", shape)
+    for shape, u8 in ((0, 1), (1, 1), (2, 1), (1, 0), (2, 0)):   # auto; one tile per CTA; two tiles per CTA sharing the B operand;
+        f = FastSK(g, m, combo_sequence=queue)                # byte (kind::i8, at most 255 windows per sequence) and fp16 operands
+        f.set_option("gemm_shape", shape)                     # (three tile rows: the second pair's lower tile is past the last row)
+        f.set_option("dense_u8", u8)
         f.compute_kernel(X[:250], X[250:])
         st = f.stats()
         assert st["acc_path"] == 3, "the cost model should pick the dense path for 256 k-mers x 333 sequences"
-        assert np.array_equal(f.get_unnormalised().astype(np.uint64), Ki), f"gemm_shape {shape}"
+        assert np.array_equal(f.get_unnormalised().astype(np.uint64), Ki), f"gemm_shape {shape}, dense_u8 {u8}"
+
+    # the edge of the byte operands: homopolymers with exactly 255 windows (every count 255: the largest byte), then 256 (fp16)
+    for length in (255 + g - 1, 256 + g - 1):
+        Xh = [[1 + (i % 2)] * length for i in range(6)] + random_seqs(rng, 150, 4, 30, 60)
+        _, Kh, _ = oracle_mod.run("c", Xh, [], g, m, queue[:20])
+        f = FastSK(g, m, combo_sequence=queue[:20])
+        f.set_option("acc_path", 3)
+        f.compute_train(Xh)
+        assert np.array_equal(f.get_unnormalised().astype(np.uint64), Kh), f"length {length}"
 
     g, m = 8, 4
     X = random_seqs(rng, 14, 4, 900, 1100, True)             # homopolymers: counts up to 1093, products above 2^20
@@ -650,7 +660,7 @@ def test_speculated_variance_rounds_equal_the_iteration_by_iteration_build(FastS
 def test_running_means_kept_in_registers_equal_the_streamed_form(FastSK, oracle_mod, T, depth, long_seqs):
     """Tensor-core variance mode, wf_regs = 1 (default): a thread keeps its 64 cells of the running mean in registers over all
     the slots of a round and the tiles are stored strip-major; with at most 255 windows per sequence the operands are bytes
-    and the accumulators int32 (wf_u8, kind::i8), otherwise fp16 / fp32.  Same Welford steps per cell as the streamed form
+    and the accumulators int32 (dense_u8, kind::i8), otherwise fp16 / fp32.  Same Welford steps per cell as the streamed form
     (wf_regs = 0): the means must be bit-equal, the stdevs equal up to the order of one fp64 sum, all equal to the oracle.
     300 sequences: full, diagonal and ragged tiles, test rows below the training rows; long_seqs: one sequence of 400
     characters (391 windows, counts above 255 on a low-complexity stretch) keeps the fp16 operands."""
@@ -667,7 +677,7 @@ def test_running_means_kept_in_registers_equal_the_streamed_form(FastSK, oracle_
         f = FastSK(g, m, T, True, 0.05, 23, False, combo_sequence=queue)
         f.set_option("acc_path", 3)
         f.set_option("wf_regs", regs)
-        f.set_option("wf_u8", u8)
+        f.set_option("dense_u8", u8)
         f.set_option("spec_depth", depth)
         f.compute_kernel(X[:210], X[210:])
         got.append((f.get_unnormalised(np.float64), f.get_stdevs(), f.get_train_kernel(), f.get_test_kernel()))
