@@ -24,7 +24,7 @@ class FskStats(ctypes.Structure):
                [(n, ctypes.c_double) for n in ("ms_pack", "ms_sort", "ms_segment", "ms_accumulate", "ms_welford",
                                                "ms_normalise", "ms_total")] + \
                [(n, ctypes.c_int32) for n in ("acc_path", "heavy_tau")] + [("heavy_runs", ctypes.c_int64)] + \
-               [(n, ctypes.c_int32) for n in ("n_devices", "seg_mode")]
+               [(n, ctypes.c_int32) for n in ("n_devices", "seg_mode", "dense_mode")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -211,7 +211,8 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restr
                const uint32_t* __restrict__ klen_dev) {
     // heavy-run contraction: the number of columns is only known on the device (heavy_fill_kernel's list)
     if (klen_dev) {
-        klen = (min(*klen_dev, klen) + DG_BK - 1) / DG_BK * DG_BK;     // klen carries the capacity of the list
+        constexpr uint32_t R = U8 ? 2 * DG_BK : DG_BK;
+        klen = (min(*klen_dev, klen) + R - 1) / R * R;                 // klen carries the capacity of the list
         if (klen == 0) return;
     }
     constexpr int DG_STAGES = dg_stages(NA);
@@ -660,11 +661,14 @@ welford_untile_kernel(double* __restrict__ dst, const double* __restrict__ src, 
 // fp16 column of H[sequence][column] (count of the sequence's records in the run), and syrk_tc_kernel adds H H^T to K.
 // Break-even on B200: d > ~0.05 N (1.3e12 updates/s against 6e14 MAC/s).
 
-// zero the first roundup64(*count) columns of H
-__global__ void heavy_zero_kernel(__half* __restrict__ H, size_t ld, int64_t nseq, const uint32_t* __restrict__ count) {
-    const uint32_t cols = (min(*count, (uint32_t)ld) + DG_BK - 1) / DG_BK * DG_BK;   // ld = capacity of the list
+// zero the first roundup(*count) columns of H (whole 128-byte k-blocks of the contraction).  OutT: __half, or uint8_t when
+// no sequence has more than 255 windows (byte operands, syrk_tc_kernel<NA, true>); ld in elements
+template <typename OutT>
+__global__ void heavy_zero_kernel(OutT* __restrict__ H, size_t ld, int64_t nseq, const uint32_t* __restrict__ count) {
+    constexpr uint32_t R = 128 / sizeof(OutT), PER16 = 16 / sizeof(OutT);
+    const uint32_t cols = (min(*count, (uint32_t)ld) + R - 1) / R * R;               // ld = capacity of the list
     if (cols == 0) return;
-    const uint32_t vec = cols / 8;                                   // 16-byte pieces per row
+    const uint32_t vec = cols / PER16;                               // 16-byte pieces per row
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nseq * vec; i += (int64_t)gridDim.x * blockDim.x)
         reinterpret_cast<uint4*>(H + (size_t)(i / vec) * ld)[i % vec] = z;
@@ -672,10 +676,10 @@ __global__ void heavy_zero_kernel(__half* __restrict__ H, size_t ld, int64_t nse
 
 // one CTA per listed run (grid-stride): find the run's end in the sorted records, then every group of equal sequence ids
 // writes its size into the run's column.  `total` accumulates the number of heavy runs since upload (statistics).
-template <typename RecT>
+template <typename RecT, typename OutT>
 __global__ void __launch_bounds__(256)
 heavy_fill_kernel(const RecT* __restrict__ rec, uint32_t n, int idbits, const uint2* __restrict__ list,
-                  const uint32_t* __restrict__ count, __half* __restrict__ H, size_t ld, unsigned long long* __restrict__ total) {
+                  const uint32_t* __restrict__ count, OutT* __restrict__ H, size_t ld, unsigned long long* __restrict__ total) {
     __shared__ uint32_t s_end;
     const uint32_t nh = min(*count, (uint32_t)ld);                    // runs beyond the capacity stayed on the sparse path
     if (blockIdx.x == 0 && threadIdx.x == 0 && total) atomicAdd(total, (unsigned long long)nh);
@@ -701,7 +705,8 @@ heavy_fill_kernel(const RecT* __restrict__ rec, uint32_t n, int idbits, const ui
             if (t == 0 || (uint32_t)(R[rs + t - 1] & idmask) != id) {
                 uint32_t c = 1;
                 while (t + c < d && (uint32_t)(R[rs + t + c] & idmask) == id) ++c;
-                H[(size_t)id * ld + h] = __uint2half_rn(c);
+                if constexpr (sizeof(OutT) == 1) H[(size_t)id * ld + h] = (OutT)c;
+                else H[(size_t)id * ld + h] = __uint2half_rn(c);
             }
         }
         __syncthreads();

@@ -161,6 +161,7 @@ struct fsk_handle {
     uint32_t heavy_tau = 0;                            // 0 = feature off
     uint32_t heavy_tau_min = 0;                        // the break-even threshold the adaptive one never goes below
     uint32_t heavy_now = 0;                            // threshold in force for the batch being launched (0 while the feature sleeps)
+    bool heavy_u8 = false;                             // byte columns in d_H (no sequence has more than 255 windows)
     uint32_t heavy_cap = 0;                            // columns of d_H = upper bound on the heavy runs of a batch
     __half* d_H = nullptr;
     uint2* d_heavy_list = nullptr;
@@ -733,18 +734,34 @@ int run_batch(fsk_handle* h, const int32_t* combos, int nb, unsigned long long* 
         // count lives on the device, so the three launches are unconditional (they return at once when the list is empty)
         Span sp(h, PC_ACCUMULATE);
         const uint32_t* cnt = h->d_ticket + HEAVY_COUNT;
-        heavy_zero_kernel<<<148 * 8, 256, 0, h->ls>>>(h->d_H, (size_t)h->heavy_cap, h->N, cnt);
-        if (h->mode == MODE_R32)
-            heavy_fill_kernel<uint32_t><<<148 * 4, 256, 0, h->ls>>>((const uint32_t*)h->d_recA, (uint32_t)h->nfeat, h->idbits, h->d_heavy_list, cnt,
-                                                                     h->d_H, (size_t)h->heavy_cap, h->d_counters + 3);
-        else
-            heavy_fill_kernel<uint64_t><<<148 * 4, 256, 0, h->ls>>>((const uint64_t*)h->d_recA, (uint32_t)h->nfeat, h->idbits, h->d_heavy_list, cnt,
-                                                                     h->d_H, (size_t)h->heavy_cap, h->d_counters + 3);
         const unsigned T = (unsigned)((h->N + DG_TILE - 1) / DG_TILE);
-        if (h->opt_gemm_shape != 1 && (h->opt_gemm_shape == 2 || T >= 4))
-            syrk_tc_kernel<2><<<dim3(h->pair_tiles, 1), DG_THREADS, dg_smem(2), h->ls>>>(h->tmap_H, h->d_pair_order, h->N, 0u, 0u, h->heavy_cap, K, 0, cnt);
-        else
-            syrk_tc_kernel<1><<<dim3(T * (T + 1) / 2, 1), DG_THREADS, dg_smem(1), h->ls>>>(h->tmap_H, h->d_tile_order, h->N, 0u, 0u, h->heavy_cap, K, 0, cnt);
+        const bool two = h->opt_gemm_shape != 1 && (h->opt_gemm_shape == 2 || T >= 4);
+        if (h->heavy_u8) {
+            uint8_t* H8 = reinterpret_cast<uint8_t*>(h->d_H);
+            heavy_zero_kernel<uint8_t><<<148 * 8, 256, 0, h->ls>>>(H8, (size_t)h->heavy_cap, h->N, cnt);
+            if (h->mode == MODE_R32)
+                heavy_fill_kernel<uint32_t, uint8_t><<<148 * 4, 256, 0, h->ls>>>((const uint32_t*)h->d_recA, (uint32_t)h->nfeat, h->idbits, h->d_heavy_list, cnt,
+                                                                                  H8, (size_t)h->heavy_cap, h->d_counters + 3);
+            else
+                heavy_fill_kernel<uint64_t, uint8_t><<<148 * 4, 256, 0, h->ls>>>((const uint64_t*)h->d_recA, (uint32_t)h->nfeat, h->idbits, h->d_heavy_list, cnt,
+                                                                                  H8, (size_t)h->heavy_cap, h->d_counters + 3);
+            if (two)
+                syrk_tc_kernel<2, true><<<dim3(h->pair_tiles, 1), DG_THREADS, dg_smem(2), h->ls>>>(h->tmap_H, h->d_pair_order, h->N, 0u, 0u, h->heavy_cap, K, 0, cnt);
+            else
+                syrk_tc_kernel<1, true><<<dim3(T * (T + 1) / 2, 1), DG_THREADS, dg_smem(1), h->ls>>>(h->tmap_H, h->d_tile_order, h->N, 0u, 0u, h->heavy_cap, K, 0, cnt);
+        } else {
+            heavy_zero_kernel<__half><<<148 * 8, 256, 0, h->ls>>>(h->d_H, (size_t)h->heavy_cap, h->N, cnt);
+            if (h->mode == MODE_R32)
+                heavy_fill_kernel<uint32_t, __half><<<148 * 4, 256, 0, h->ls>>>((const uint32_t*)h->d_recA, (uint32_t)h->nfeat, h->idbits, h->d_heavy_list, cnt,
+                                                                                 h->d_H, (size_t)h->heavy_cap, h->d_counters + 3);
+            else
+                heavy_fill_kernel<uint64_t, __half><<<148 * 4, 256, 0, h->ls>>>((const uint64_t*)h->d_recA, (uint32_t)h->nfeat, h->idbits, h->d_heavy_list, cnt,
+                                                                                 h->d_H, (size_t)h->heavy_cap, h->d_counters + 3);
+            if (two)
+                syrk_tc_kernel<2><<<dim3(h->pair_tiles, 1), DG_THREADS, dg_smem(2), h->ls>>>(h->tmap_H, h->d_pair_order, h->N, 0u, 0u, h->heavy_cap, K, 0, cnt);
+            else
+                syrk_tc_kernel<1><<<dim3(T * (T + 1) / 2, 1), DG_THREADS, dg_smem(1), h->ls>>>(h->tmap_H, h->d_tile_order, h->N, 0u, 0u, h->heavy_cap, K, 0, cnt);
+        }
         h->launches += 3;
         CU(cudaGetLastError());
         if (!h->heavy_probe_pending) {   // did this batch have any heavy run?  read back without waiting
@@ -1507,6 +1524,7 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         // (<= 2048 windows per sequence) and every fp32 accumulator below 2^24 (slots x maxwin^2).  The threshold is the larger
         // of the measured break-even (~0.05 N; 0.06 N used) and what keeps the batch's heavy runs within 65536 columns / 8 GB.
         h->heavy_tau = 0;
+        h->heavy_u8 = false;
         const bool ok = h->rows_path && !h->variance_mode && h->mode != MODE_KV && maxwin <= 2048 &&
                         (double)Bsel * (double)maxwin * (double)maxwin < 16777216.0 && !h->fused_seg && h->opt_heavy_tau >= 0 &&
                         !h->opt_overlap;   // (the list and its bitmap are single-buffered: not with the two-stream overlap)
@@ -1518,7 +1536,9 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
             if (tau < nfeat) {                                            // a run that long must be possible at all
                 h->heavy_tau = h->heavy_tau_min = (uint32_t)tau;
                 h->heavy_cap = h->opt_heavy_cap ? (uint32_t)h->opt_heavy_cap
-                                                : (uint32_t)std::max<int64_t>(64, std::min<int64_t>(65536, ((8LL << 30) / (N * 2)) & ~63LL));
+                                                : (uint32_t)std::max<int64_t>(128, std::min<int64_t>(65536, ((8LL << 30) / (N * 2)) & ~127LL));
+                // byte columns (kind::i8 contraction) when every count fits a byte and the list is whole 128-column k-blocks
+                h->heavy_u8 = h->opt_dense_u8 && maxwin <= 255 && h->heavy_cap % 128 == 0;
             }
         }
         h->heavy_live = true;
@@ -1618,11 +1638,11 @@ int upload_one(fsk_handle* h, const int32_t* codes, const int64_t* offsets, int6
         if ((double)free_now < (double)N * h->heavy_cap * 2.0 + (double)k_bytes + (double)(2LL << 30)) h->heavy_tau = h->heavy_tau_min = 0;
     }
     if (h->heavy_tau) {
-        ALLOC(h->d_H, (size_t)N * h->heavy_cap);
+        ALLOC(h->d_H, h->heavy_u8 ? ((size_t)N * h->heavy_cap + 1) / 2 : (size_t)N * h->heavy_cap);
         ALLOC(h->d_heavy_list, h->heavy_cap);
         if (!h->h_heavy_count) CU(cudaMallocHost((void**)&h->h_heavy_count, sizeof(uint32_t)));
         if (!h->ev_heavy) CU(cudaEventCreateWithFlags(&h->ev_heavy, cudaEventDisableTiming));
-        int rc_ = encode_operand_map(h, &h->tmap_H, h->d_H, h->heavy_cap);
+        int rc_ = encode_operand_map(h, &h->tmap_H, h->d_H, h->heavy_cap, h->heavy_u8);
         if (rc_) return rc_;
     }
     if (h->dense_path || h->heavy_tau) {
@@ -2468,6 +2488,7 @@ int fsk_get_stats(fsk_handle* h, fsk_stats* out) {
     for (int i = 0; i < PC_COUNT; ++i) out->ms_total += h->ms[i];
     out->n_devices = is_team(h) ? (int32_t)h->team.size() : 1;
     out->seg_mode = (h->dir_mode ? 1 : (h->fused_seg ? 2 : 0)) + (h->lean_seg ? 4 : 0);
+    out->dense_mode = h->dense_path ? (h->dense_u8 ? 2 : 1) + (h->wf_regs ? 4 : 0) : 0;
     // a team: counts add up over the members, times are the slowest member's
     for (size_t i = 1; !h->leader && i < h->team.size(); ++i) {
         fsk_stats o;

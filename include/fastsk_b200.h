@@ -208,6 +208,9 @@ typedef struct fsk_stats {
     int32_t n_devices;          /* GPUs driven by this handle (fsk_set_devices); counts above add up over them, times are the slowest's */
     int32_t seg_mode;           /* segmentation: 0 one task filed per record, 1 run directory (key spaces <= 2^16), 2 fused bucket form; + 4 when
                                    the register-blocked kernel (fsk_segment.cuh) does it */
+    int32_t dense_mode;         /* dense regime (acc_path 3): 1 fp16 operands / fp32 accumulators, 2 byte operands / int32 accumulators
+                                   (no sequence has more than 255 windows); + 4 when the variance mode's Welford contraction keeps the
+                                   running means in registers over a round; 0 outside the dense regime */
 } fsk_stats;
 int fsk_get_stats(fsk_handle* h, fsk_stats* out);
 

@@ -198,6 +198,7 @@ def test_dense_tensor_core_path_multi_tile_and_chunked(FastSK, oracle_mod):
         f.compute_kernel(X[:250], X[250:])
         st = f.stats()
         assert st["acc_path"] == 3, "the cost model should pick the dense path for 256 k-mers x 333 sequences"
+        assert st["dense_mode"] == (2 if u8 else 1)
         assert np.array_equal(f.get_unnormalised().astype(np.uint64), Ki), f"gemm_shape {shape}, dense_u8 {u8}"
 
     # the edge of the byte operands: homopolymers with exactly 255 windows (every count 255: the largest byte), then 256 (fp16)
@@ -207,6 +208,7 @@ def test_dense_tensor_core_path_multi_tile_and_chunked(FastSK, oracle_mod):
         f = FastSK(g, m, combo_sequence=queue[:20])
         f.set_option("acc_path", 3)
         f.compute_train(Xh)
+        assert f.stats()["dense_mode"] == (2 if length == 255 + g - 1 else 1)
         assert np.array_equal(f.get_unnormalised().astype(np.uint64), Kh), f"length {length}"
 
     g, m = 8, 4
@@ -680,6 +682,7 @@ def test_running_means_kept_in_registers_equal_the_streamed_form(FastSK, oracle_
         f.set_option("dense_u8", u8)
         f.set_option("spec_depth", depth)
         f.compute_kernel(X[:210], X[210:])
+        assert f.stats()["dense_mode"] == (4 if regs else 0) + (2 if regs and u8 and not long_seqs else 1)
         got.append((f.get_unnormalised(np.float64), f.get_stdevs(), f.get_train_kernel(), f.get_test_kernel()))
         assert len(got[-1][1]) == len(sd)
         np.testing.assert_allclose(got[-1][1], sd, rtol=RTOL, atol=0)

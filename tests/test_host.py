@@ -56,12 +56,12 @@ def test_option_validation_needs_no_device():
     f = FastSK(10, 6)
     for key, good, bad in (("acc_path", 3, 4), ("seg_fused", 2, 3), ("heavy_tau", -1, -2), ("heavy_cap", 128, 100),
                            ("acc_cols", 64, 48), ("batch", 384, 385), ("seg_dir", 2, 3), ("seg_lean", 2, 3), ("dir_blocks", 64, 0),
-                           ("spec_depth", 384, 385), ("pf_stride", 64, 96)):
+                           ("spec_depth", 384, 385), ("pf_stride", 64, 96)):   # (wf_regs / dense_u8 are booleans: any value)
         f.set_option(key, good)
         with pytest.raises(ValueError):
             f.set_option(key, bad)
     st = f.stats()
-    assert {"acc_path", "heavy_tau", "heavy_runs", "n_devices", "seg_mode"} <= set(st) and st["heavy_runs"] == 0
+    assert {"acc_path", "heavy_tau", "heavy_runs", "n_devices", "seg_mode", "dense_mode"} <= set(st) and st["heavy_runs"] == 0 and st["dense_mode"] == 0
 
 
 def test_seeded_queue_equals_libstdcxx_reference_shuffle():
