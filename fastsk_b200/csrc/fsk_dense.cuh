@@ -57,11 +57,42 @@ dense_count_kernel(const GwT* __restrict__ gw0, const uint64_t* __restrict__ gw1
     uint32_t* __restrict__ hist = hist_all + (size_t)warp * words;
     const uint32_t seq = blockIdx.x;
     const uint32_t w0 = woff[seq], nw = woff[seq + 1] - w0;
+    // short sequences (at most 96 windows: the TFBS sets): a lane keeps its three windows' g-mer words in registers over all the
+    // slots instead of re-reading them per slot
+    constexpr int HOLD = 3;
+    const bool held = nw <= 32u * HOLD;
+    KeyT lo_r[HOLD], hi_r[HOLD];
+#pragma unroll
+    for (int t = 0; t < HOLD; ++t) {
+        const uint32_t p = lane + 32u * t;
+        lo_r[t] = held && p < nw ? (KeyT)gw0[w0 + p] : (KeyT)0;
+        hi_r[t] = NW == 2 && held && p < nw ? (KeyT)gw1[w0 + p] : (KeyT)0;
+    }
     for (int slot = warp; slot < nb; slot += DENSE_COUNT_WARPS) {
         for (uint32_t i = lane; i < words; i += 32) hist[i] = 0;
         const int nseg = spec.nseg[slot];
         if (lane < nseg) seg[lane] = spec.seg[slot][lane];     // the slot's stretch descriptors: broadcast reads below
         __syncwarp();
+        if (held) {
+            KeyT key[HOLD];
+#pragma unroll
+            for (int t = 0; t < HOLD; ++t) key[t] = 0;
+            uint32_t dst = 0;
+            for (int j = 0; j < nseg; ++j) {            // same stretch packing as pack_hist_kernel, three windows at a time
+                const uint32_t e = seg[j];
+                const uint32_t src = e & 63u, width = (e >> 7) + 1u;
+                const KeyT m = (KeyT)((KeyT) ~(KeyT)0 >> (KB - width)) << dst;
+                const uint32_t r = (src - dst) & (KB - 1u);
+#pragma unroll
+                for (int t = 0; t < HOLD; ++t) key[t] |= rotr_key<KeyT>((NW == 2 && (e & 64u)) ? hi_r[t] : lo_r[t], r) & m;
+                dst += width;
+            }
+#pragma unroll
+            for (int t = 0; t < HOLD; ++t) {
+                const uint32_t kk = (uint32_t)key[t];
+                if (lane + 32u * t < nw) atomicAdd(&hist[kk >> 1], 1u << ((kk & 1u) << 4));
+            }
+        } else
         for (uint32_t p = lane; p < nw; p += 32) {
             const KeyT lo = (KeyT)gw0[w0 + p];
             const KeyT hi = NW == 2 ? (KeyT)gw1[w0 + p] : (KeyT)0;
