@@ -25,6 +25,7 @@ Deliberate deviations from the reference:
 from __future__ import annotations
 
 import ctypes
+import itertools
 import os
 
 import numpy as np
@@ -46,6 +47,11 @@ def _flatten(X):
     lens = np.fromiter((len(x) for x in X), dtype=np.int64, count=n)
     offsets = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(lens, out=offsets[1:])
+    if n and isinstance(X[0], list):          # lists of Python ints (the reference's input): one C-level pass, ~25 % faster
+        try:
+            return np.fromiter(itertools.chain.from_iterable(X), dtype=np.int32, count=int(offsets[-1])), offsets
+        except TypeError:                     # a mix of lists and arrays: the general path below
+            pass
     codes = np.empty(int(offsets[-1]), dtype=np.int32)
     for i, x in enumerate(X):
         codes[offsets[i]:offsets[i + 1]] = x
