@@ -198,3 +198,23 @@ def test_set_devices_validation_and_team_options():
     one = (ctypes.c_int * 1)(0)
     assert lib.fsk_set_devices(f._h, one, 1) == _lib.FSK_OK              # back to one GPU: shard 0 of 1 again
     assert f.stats()["n_devices"] == 1 and lib.fsk_set_shard(f._h, 1, 2) == _lib.FSK_OK
+
+
+def test_flatten_accepts_every_input_form():
+    """FastSK._flatten: lists of Python ints (one C-level pass), lists of arrays, a mix, a 2-D array, a flat pair; empty
+    sequences and an empty set keep their offsets."""
+    from fastsk_b200.fastsk import _flatten
+    rng = np.random.default_rng(5)
+    X = [rng.integers(1, 21, size=int(rng.integers(0, 30))).tolist() for _ in range(40)]
+    want = np.concatenate([np.asarray(x, dtype=np.int32) for x in X])
+    off = np.concatenate([[0], np.cumsum([len(x) for x in X])])
+    for form in (X, [np.asarray(x, dtype=np.int64) for x in X], [x if i % 2 else np.asarray(x, dtype=np.int32) for i, x in enumerate(X)]):
+        c, o = _flatten(form)
+        assert c.dtype == np.int32 and o.dtype == np.int64 and np.array_equal(c, want) and np.array_equal(o, off)
+    c, o = _flatten((want, off.astype(np.int64)))
+    assert np.array_equal(c, want) and np.array_equal(o, off)
+    A = rng.integers(1, 5, size=(7, 9))
+    c, o = _flatten(A)
+    assert np.array_equal(c, A.reshape(-1)) and np.array_equal(o, np.arange(8) * 9)
+    c, o = _flatten([])
+    assert len(c) == 0 and o.tolist() == [0]
