@@ -13,6 +13,14 @@
 // Exactness: counts are integers <= maxwin <= 2048 (exact in fp16), products < 2^22, and the host cuts the
 // contraction dimension so that no fp32 accumulator can exceed 2^24 (slots per GEMM <= 2^24 / maxwin^2): every
 // intermediate is an exactly representable integer, so the result is bit-identical to the integer sum.
+//
+// Byte operands (round 2): when no sequence has more than 255 windows every count fits a byte, and the same kernels run
+// with U8 = true -- C (and the heavy runs' H) as uint8, tcgen05.mma kind::i8 with int32 accumulators, 128 k-mer columns
+// per 128-byte swizzle row instead of 64: half the operand bytes (what bounds these short-K contractions: L2 -> shared
+// memory at ~43 B/clk and SM), twice the MMA rate, integer accumulation exact by construction.
+//
+//   syrk_tc_welford_kernel   variance mode: a CTA owns one tile of one virtual stream's running mean over all the
+//                        iterations of a launch group; <true>: the means stay in registers (see there).
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -25,9 +33,9 @@ constexpr int DG_BK = 64;                                        // fp16 element
 constexpr int DG_THREADS = 192;                                  // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
 constexpr uint32_t DG_TILE_BYTES = DG_TILE * DG_BK * 2;          // 16 KB
 // Two shapes of the same kernel.  NA = 1: one 128 x 128 output tile per CTA, 3 stages x 32 KB, two CTAs per SM (one's epilogue
-// runs under the other's MMAs): short contractions (variance mode).  NA = 2: two vertically adjacent tiles per CTA share their
+// runs under the other's MMAs): the default (faster at every N measured in round 2, profiles/r02_gemm_shape_by_n.txt).  NA = 2: two vertically adjacent tiles per CTA share their
 // B operand (3 loads feed 8 MMAs per k-block: 24 KB of L2 -> shared-memory traffic per M-MAC instead of 32), 4 stages x 48 KB,
-// one CTA per SM, 256 TMEM columns: long contractions, where the operand traffic bounds the 128 x 128 shape.
+// one CTA per SM, 256 TMEM columns: opt-in (gemm_shape = 2) and the heavy-run contraction.
 __host__ __device__ constexpr int dg_stages(int NA) { return NA == 1 ? 3 : 4; }
 __host__ __device__ constexpr uint32_t dg_stage_bytes(int NA) { return (uint32_t)(NA + 1) * DG_TILE_BYTES; }
 __host__ __device__ constexpr size_t dg_smem(int NA) {
