@@ -218,3 +218,27 @@ def test_flatten_accepts_every_input_form():
     assert np.array_equal(c, A.reshape(-1)) and np.array_equal(o, np.arange(8) * 9)
     c, o = _flatten([])
     assert len(c) == 0 and o.tolist() == [0]
+
+
+def test_shard_rows_is_a_partition_for_any_weights():
+    """shard_rows (the arithmetic fsk_finalize uses for its row shares): the ranks' ranges tile [0, n) in rank order for equal
+    shares and for any non-negative weights; a rank with weight 0 holds no rows."""
+    from fastsk_b200 import shard_rows
+    rng = np.random.default_rng(9)
+    for trial in range(200):
+        world = int(rng.integers(1, 9))
+        n = int(rng.integers(0, 5000))
+        weights = None
+        if trial % 3:
+            weights = rng.integers(0, 4, size=world).astype(float).tolist()
+            if sum(weights) == 0:
+                weights[int(rng.integers(0, world))] = 1.0
+        pos = 0
+        for r in range(world):
+            r0, nr = shard_rows(n, r, world, weights)
+            assert r0 == pos and nr >= 0
+            if weights is not None and weights[r] == 0:
+                assert nr == 0
+            pos += nr
+        assert pos == n
+    assert [shard_rows(10, r, 4, [0, 1, 0, 1]) for r in range(4)] == [(0, 0), (0, 5), (5, 0), (5, 5)]
