@@ -68,6 +68,16 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
+        except Exception:
+            pass
+    return 2250.0, "nominal (B200_PROFILING.md)"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -512,6 +522,12 @@ def other_workloads(device):
                 n, kdim = st["n_seq"], 256 * st["combos_done"]
                 row["tensor_tflops"] = 2.0 * (n * (n + 128) / 2.0) * kdim / (st["ms_accumulate"] * 1e-3) / 1e12
                 row["tensor_operands"] = "u8 x u8 -> s32 (tcgen05 kind::i8: at most 255 windows per sequence), so these are TOP/s"
+                bf16, src = measured_tensor_peak()
+                row["roofline"] = {"kernel": "syrk_tc_kernel<1, true>", "bound": "tensor", "achieved": row["tensor_tflops"], "peak": 2.0 * bf16,
+                                   "unit": "TOP/s", "frac": row["tensor_tflops"] / (2.0 * bf16), "traffic": None,
+                                   "peak_source": "2 x the dense bf16 rate (int8 MMAs issue at twice the bf16 rate): " + src,
+                                   "note": "bound by the fill of shared memory with operand tiles (ncu: L2 throughput 62 %, profiles/r02_ncu_dense_u8.txt), "
+                                           "528 tiles = 1.78 waves at EP300's size"}
             if best is None or row["e2e_s"] < best["e2e_s"]:
                 best = row
             del f
